@@ -1,0 +1,192 @@
+"""ctypes binding of libbq_b200.so (C-ABI in include/bq_b200.h).
+
+There is no CPU fallback: if the CUDA library cannot be loaded, or no sm_100 device is
+present, every entry point raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbq_b200.so")
+NC_MAX = 16
+
+ST_OK, ST_SHORTCUT, ST_NOTPD, ST_ESM_INF, ST_EM_INF, ST_ESM_BAD, ST_EM_BAD, ST_XA_BAD = 0, 1, 2, 4, 8, 16, 32, 64
+SETUP_OK, SETUP_KTL_NOTPD, SETUP_KL_NOTPD, SETUP_MEAN_TOO_LARGE, SETUP_BAD_INPUT = 0, 1, 2, 3, 4
+EINVAL, EUNSUPPORTED, ESTATE, ENUMERIC = -1, -2, -3, -4
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+_vp = ctypes.c_void_p
+_ll = ctypes.c_longlong
+
+#: every symbol include/bq_b200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = {
+    "bqb_last_error": (ctypes.c_char_p, []),
+    "bqb_version": (ctypes.c_int, []),
+    "bqb_device_count": (ctypes.c_int, [_ip]),
+    "bqb_ns_capacity": (ctypes.c_int, [ctypes.c_int]),
+    "bqb_batch_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "bqb_batch_destroy": (None, [_vp]),
+    "bqb_batch_setup": (ctypes.c_int, [_vp, _ip, _ip, _dp, _dp, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, _vp]),
+    "bqb_batch_info": (ctypes.c_int, [_vp, _dp, _dp, _dp, _ip, _dp]),
+    "bqb_score_device": (ctypes.c_int, [_vp, _vp, _ll, ctypes.c_int, _vp, _vp, _vp, _ll, _vp]),
+    "bqb_score_host": (ctypes.c_int, [_vp, _dp, _ll, ctypes.c_int, _dp, _dp, _ip]),
+    "bqb_expected_var_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _ll, _vp, _vp]),
+    "bqb_mean_neg_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp]),
+    "bqb_argmin_device": (ctypes.c_int, [_vp, _vp, _ll, _dp, ctypes.POINTER(_ll), _vp]),
+    "bqb_launch_count": (ctypes.c_ulonglong, [_vp]),
+    "bqb_model_doubles": (ctypes.c_int, [_vp]),
+    "bqb_model_read": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
+}
+
+_lib = None
+
+
+class BQB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the CUDA library; raises ImportError when it is missing (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "bayesian_quadrature_b200: %s is missing — build it with "
+                "`python -m bayesian_quadrature_b200.build` (needs nvcc, sm_100a). "
+                "There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = load().bqb_last_error().decode("utf-8", "replace")
+        if rc == EINVAL:
+            raise ValueError("%s: %s" % (what, msg))
+        if rc == EUNSUPPORTED:
+            raise NotImplementedError("%s: %s" % (what, msg))
+        if rc == ENUMERIC:
+            raise np.linalg.LinAlgError("%s: %s" % (what, msg))
+        raise BQB200Error("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    _check(load().bqb_device_count(ctypes.byref(n)), "bqb_device_count")
+    return n.value
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _pd(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class Batch(object):
+    """B model instances (one BQ problem under one hyper-parameter set each) resident on one GPU."""
+
+    def __init__(self, n_inst, ns_max, device=0):
+        self._h = _vp()
+        self.n_inst, self.ns_max, self.device = int(n_inst), int(ns_max), int(device)
+        _check(load().bqb_batch_create(ctypes.byref(self._h), self.device, self.n_inst, self.ns_max), "bqb_batch_create")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().bqb_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def setup(self, ns, nc, x_s, l_s, x_c, hyp, prior, check_max=False, stream=None):
+        """x_s, l_s: [B, in_stride]; x_c: [B, <=16]; hyp: [B, 6]; prior: [B, 3] (host arrays)."""
+        B = self.n_inst
+        ns = np.ascontiguousarray(np.broadcast_to(np.asarray(ns, dtype=np.int32), (B,)))
+        nc = np.ascontiguousarray(np.broadcast_to(np.asarray(nc, dtype=np.int32), (B,)))
+        x_s, l_s = _d(x_s).reshape(B, -1), _d(l_s).reshape(B, -1)
+        xc = np.zeros((B, NC_MAX))
+        x_c = _d(x_c).reshape(B, -1)
+        if x_c.shape[1] > NC_MAX:
+            raise NotImplementedError("more than %d candidates per instance" % NC_MAX)
+        xc[:, :x_c.shape[1]] = x_c
+        hyp, prior = _d(hyp).reshape(B, 6), _d(prior).reshape(B, 3)
+        _check(load().bqb_batch_setup(self._h, ns.ctypes.data_as(_ip), nc.ctypes.data_as(_ip), _pd(x_s), _pd(l_s),
+                                      x_s.shape[1], _pd(xc), _pd(hyp), _pd(prior), int(check_max),
+                                      _vp(stream) if stream else None), "bqb_batch_setup")
+        self.ns, self.nc = ns, nc
+        return self.info()
+
+    def info(self):
+        B = self.n_inst
+        Zm, Zv, llh = np.empty(B), np.empty(B), np.empty(B)
+        st = np.empty(B, dtype=np.int32)
+        l_c = np.empty((B, NC_MAX))
+        _check(load().bqb_batch_info(self._h, _pd(Zm), _pd(Zv), _pd(llh), st.ctypes.data_as(_ip), _pd(l_c)), "bqb_batch_info")
+        return {"Z_mean": Zm, "Z_var": Zv, "log_lh": llh, "status": st, "l_c": l_c}
+
+    def score_host(self, x_a, want_em=True, want_status=True):
+        """x_a: [na] shared by all instances, or [B, na].  Returns (esm, em, status) as [B, na] numpy arrays."""
+        x_a = _d(x_a)
+        B = self.n_inst
+        if x_a.ndim == 1:
+            stride, na = 0, x_a.shape[0]
+        else:
+            if x_a.shape[0] != B:
+                raise ValueError("x_a must be [na] or [n_inst, na]")
+            stride, na = x_a.shape[1], x_a.shape[1]
+        esm = np.empty((B, na))
+        em = np.empty((B, na)) if want_em else None
+        st = np.empty((B, na), dtype=np.int32) if want_status else None
+        _check(load().bqb_score_host(self._h, _pd(x_a), stride, na, _pd(esm), _pd(em) if want_em else None,
+                                     st.ctypes.data_as(_ip) if want_status else None), "bqb_score_host")
+        return esm, em, st
+
+    def score_device(self, x_a, esm, em=None, status=None, stream=None):
+        """torch CUDA tensors: x_a float64 [na] or [B, na]; esm/em float64 [B, na]; status int32 [B, na]."""
+        if x_a.dim() == 1:
+            stride, na = 0, x_a.shape[0]
+        else:
+            stride, na = x_a.stride(0), x_a.shape[1]
+        out_stride = esm.stride(0) if esm.dim() == 2 else esm.shape[0]
+        _check(load().bqb_score_device(self._h, _ptr(x_a), stride, na, _ptr(esm), _ptr(em), _ptr(status), out_stride,
+                                       _vp(stream) if stream else None), "bqb_score_device")
+
+    def expected_var_device(self, inst, esm, out, stream=None):
+        _check(load().bqb_expected_var_device(self._h, int(inst), _ptr(esm), esm.numel(), _ptr(out),
+                                              _vp(stream) if stream else None), "bqb_expected_var_device")
+
+    def mean_neg_device(self, esm, loss, stream=None):
+        _check(load().bqb_mean_neg_device(self._h, _ptr(esm), esm.stride(0), esm.shape[1], _ptr(loss),
+                                          _vp(stream) if stream else None), "bqb_mean_neg_device")
+
+    def argmin_device(self, v, stream=None):
+        mn, idx = ctypes.c_double(0), _ll(0)
+        _check(load().bqb_argmin_device(self._h, _ptr(v), v.numel(), ctypes.byref(mn), ctypes.byref(idx),
+                                        _vp(stream) if stream else None), "bqb_argmin_device")
+        return mn.value, idx.value
+
+    @property
+    def launch_count(self):
+        return int(load().bqb_launch_count(self._h))
+
+    def read_model(self, inst=0):
+        n = load().bqb_model_doubles(self._h)
+        out = np.empty(n)
+        _check(load().bqb_model_read(self._h, int(inst), _pd(out)), "bqb_model_read")
+        return out

@@ -1,0 +1,297 @@
+// C-ABI of the B200 expected-variance scoring library (declared in include/bq_b200.h).
+// Plain pointers and sizes only; no torch types.  Every entry point returns 0 on success,
+// a negative BQB_E* code for argument errors and a positive cudaError_t otherwise; the
+// message is kept per thread (bqb_last_error).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bq_b200.h"
+#include "bq_common.cuh"
+
+namespace bqb {
+struct SetupArgs {
+    const int *ns, *nc;
+    const double *x_s, *l_s, *x_c, *hyp, *prior;
+    int in_stride, check_max;
+    double *models;
+    Layout lay;
+    double *work;
+    size_t work_stride;
+    int n_cap, inst0;
+};
+struct ScoreArgs {
+    const double *models;
+    Layout lay;
+    const double *x_a;
+    long long xa_stride;
+    int na;
+    double *esm, *em;
+    int *status;
+    long long out_stride;
+    const double *exp_tab;
+    int inst0;
+};
+void launch_setup(const SetupArgs &a, int n_inst, cudaStream_t stream);
+cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream);
+cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, long long na, double *loss, cudaStream_t s);
+cudaError_t launch_expected_var(const double *esm, long long na, double msm, double *out, cudaStream_t s);
+cudaError_t launch_argmin(const double *v, long long n, double *scratch_val, long long *scratch_idx, int sm_count,
+                          cudaStream_t s);
+}  // namespace bqb
+
+using namespace bqb;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail((int)e_, std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct bqb_batch {
+    int device, n_inst, ns_cap, sm_count;
+    Layout lay;
+    double *d_models = nullptr, *d_tab = nullptr, *d_work = nullptr;
+    int work_inst = 0, n_cap = 0;
+    size_t work_stride = 0;
+    // staged inputs
+    int *d_ns = nullptr, *d_nc = nullptr;
+    double *d_xs = nullptr, *d_ls = nullptr, *d_xc = nullptr, *d_hyp = nullptr, *d_prior = nullptr;
+    // host-buffer scoring staging (grown on demand)
+    double *d_xa = nullptr, *d_esm = nullptr, *d_em = nullptr;
+    int *d_st = nullptr;
+    size_t cap_xa = 0, cap_out = 0;
+    double *d_red_val = nullptr;
+    long long *d_red_idx = nullptr;
+    std::vector<double> h_hdr;
+    bool ready = false;
+    unsigned long long launches = 0;
+};
+
+extern "C" {
+
+const char *bqb_last_error(void) { return g_err.c_str(); }
+
+int bqb_version(void) { return 100; }
+
+int bqb_device_count(int *count) {
+    CU(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int bqb_ns_capacity(int ns) {
+    if (ns < 1) return BQB_EINVAL;
+    if (ns <= 16) return 16;
+    if (ns <= 64) return 64;
+    if (ns <= 128) return 128;
+    return BQB_EUNSUPPORTED;
+}
+
+int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
+    if (!out || n_inst < 1) return fail(BQB_EINVAL, "bqb_batch_create: bad arguments");
+    const int cap = bqb_ns_capacity(ns_max);
+    if (cap < 0) return fail(cap, "bqb_batch_create: ns_max outside the supported range [1, 128]");
+    CU(cudaSetDevice(device));
+    bqb_batch *b = new bqb_batch();
+    b->device = device; b->n_inst = n_inst; b->ns_cap = cap; b->lay = make_layout(cap);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { delete b; return fail(BQB_EUNSUPPORTED, "bqb_batch_create: needs an sm_100a device (B200)"); }
+    b->sm_count = prop.multiProcessorCount;
+    CU(cudaMalloc(&b->d_models, sizeof(double) * (size_t)n_inst * b->lay.total));
+    CU(cudaMalloc(&b->d_tab, sizeof(double) * EXP_TAB));
+    std::vector<double> tab(EXP_TAB);
+    for (int j = 0; j < EXP_TAB; ++j) tab[j] = (double)exp2l((long double)j / EXP_TAB);
+    CU(cudaMemcpy(b->d_tab, tab.data(), sizeof(double) * EXP_TAB, cudaMemcpyHostToDevice));
+    b->n_cap = cap + NC_MAX;
+    b->work_stride = 4 * (size_t)b->n_cap * b->n_cap + 32 * (size_t)b->n_cap;
+    b->work_inst = n_inst < 2048 ? n_inst : 2048;
+    CU(cudaMalloc(&b->d_work, sizeof(double) * b->work_stride * b->work_inst));
+    CU(cudaMalloc(&b->d_ns, sizeof(int) * n_inst));
+    CU(cudaMalloc(&b->d_nc, sizeof(int) * n_inst));
+    CU(cudaMalloc(&b->d_xs, sizeof(double) * (size_t)n_inst * cap));
+    CU(cudaMalloc(&b->d_ls, sizeof(double) * (size_t)n_inst * cap));
+    CU(cudaMalloc(&b->d_xc, sizeof(double) * (size_t)n_inst * NC_MAX));
+    CU(cudaMalloc(&b->d_hyp, sizeof(double) * (size_t)n_inst * 6));
+    CU(cudaMalloc(&b->d_prior, sizeof(double) * (size_t)n_inst * 3));
+    CU(cudaMalloc(&b->d_red_val, sizeof(double) * 4096));
+    CU(cudaMalloc(&b->d_red_idx, sizeof(long long) * 4096));
+    b->h_hdr.resize((size_t)n_inst * H_COUNT);
+    *out = b;
+    return 0;
+}
+
+void bqb_batch_destroy(bqb_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    void *ptrs[] = {b->d_models, b->d_tab, b->d_work, b->d_ns, b->d_nc, b->d_xs, b->d_ls, b->d_xc, b->d_hyp, b->d_prior,
+                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete b;
+}
+
+int bqb_batch_setup(bqb_batch *b, const int *ns, const int *nc, const double *x_s, const double *l_s, int in_stride,
+                    const double *x_c, const double *hyp, const double *prior, int check_max, void *stream) {
+    if (!b || !ns || !nc || !x_s || !l_s || !hyp || !prior) return fail(BQB_EINVAL, "bqb_batch_setup: null argument");
+    if (in_stride < 1 || in_stride > b->ns_cap) return fail(BQB_EINVAL, "bqb_batch_setup: in_stride exceeds the batch capacity");
+    for (int i = 0; i < b->n_inst; ++i) {
+        if (ns[i] < 1 || ns[i] > in_stride) return fail(BQB_EINVAL, "bqb_batch_setup: ns out of range");
+        if (nc[i] < 0 || nc[i] > NC_MAX) return fail(BQB_EUNSUPPORTED, "bqb_batch_setup: more than 16 candidates");
+        if (nc[i] > 0 && !x_c) return fail(BQB_EINVAL, "bqb_batch_setup: x_c is null");
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(b->device));
+    const int B = b->n_inst;
+    CU(cudaMemcpyAsync(b->d_ns, ns, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->d_nc, nc, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->d_xs, x_s, sizeof(double) * (size_t)B * in_stride, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->d_ls, l_s, sizeof(double) * (size_t)B * in_stride, cudaMemcpyHostToDevice, s));
+    if (x_c) CU(cudaMemcpyAsync(b->d_xc, x_c, sizeof(double) * (size_t)B * NC_MAX, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->d_hyp, hyp, sizeof(double) * (size_t)B * 6, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->d_prior, prior, sizeof(double) * (size_t)B * 3, cudaMemcpyHostToDevice, s));
+    SetupArgs a;
+    a.ns = b->d_ns; a.nc = b->d_nc; a.x_s = b->d_xs; a.l_s = b->d_ls; a.x_c = b->d_xc; a.hyp = b->d_hyp; a.prior = b->d_prior;
+    a.in_stride = in_stride; a.check_max = check_max; a.models = b->d_models; a.lay = b->lay;
+    a.work = b->d_work; a.work_stride = b->work_stride; a.n_cap = b->n_cap;
+    for (int i0 = 0; i0 < B; i0 += b->work_inst) {
+        const int cnt = (B - i0 < b->work_inst) ? B - i0 : b->work_inst;
+        a.inst0 = i0;
+        launch_setup(a, cnt, s);
+        CU(cudaGetLastError());
+        b->launches++;
+    }
+    // headers back to the host (Z_mean, Z_var, log_lh, status)
+    CU(cudaMemcpy2DAsync(b->h_hdr.data(), sizeof(double) * H_COUNT, b->d_models, sizeof(double) * b->lay.total,
+                         sizeof(double) * H_COUNT, B, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    b->ready = true;
+    return 0;
+}
+
+int bqb_batch_info(bqb_batch *b, double *Z_mean, double *Z_var, double *log_lh, int *status, double *l_c) {
+    if (!b || !b->ready) return fail(BQB_ESTATE, "bqb_batch_info: batch was not set up");
+    for (int i = 0; i < b->n_inst; ++i) {
+        const double *h = &b->h_hdr[(size_t)i * H_COUNT];
+        if (Z_mean) Z_mean[i] = h[H_ZM];
+        if (Z_var) Z_var[i] = h[H_ZV];
+        if (log_lh) log_lh[i] = h[H_LOGLH];
+        if (status) status[i] = (int)h[H_STATUS];
+    }
+    if (l_c) {
+        CU(cudaSetDevice(b->device));
+        CU(cudaMemcpy2D(l_c, sizeof(double) * NC_MAX, b->d_models + b->lay.off_lc, sizeof(double) * b->lay.total,
+                        sizeof(double) * NC_MAX, b->n_inst, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+static int check_ready(bqb_batch *b, const char *who) {
+    if (!b || !b->ready) return fail(BQB_ESTATE, std::string(who) + ": batch was not set up");
+    for (int i = 0; i < b->n_inst; ++i)
+        if ((int)b->h_hdr[(size_t)i * H_COUNT + H_STATUS] != SETUP_OK)
+            return fail(BQB_ENUMERIC, std::string(who) + ": an instance failed setup (see bqb_batch_info status)");
+    return 0;
+}
+
+int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int na, double *d_esm, double *d_em,
+                     int *d_status, long long out_stride, void *stream) {
+    int rc = check_ready(b, "bqb_score_device");
+    if (rc) return rc;
+    if (!d_x_a || !d_esm || na < 0 || out_stride < na) return fail(BQB_EINVAL, "bqb_score_device: bad arguments");
+    if (na == 0) return 0;
+    CU(cudaSetDevice(b->device));
+    ScoreArgs a;
+    a.models = b->d_models; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = xa_stride; a.na = na;
+    a.esm = d_esm; a.em = d_em; a.status = d_status; a.out_stride = out_stride; a.exp_tab = b->d_tab;
+    // gridDim.y is limited to 65535
+    for (int i0 = 0; i0 < b->n_inst; i0 += 32768) {
+        const int cnt = (b->n_inst - i0 < 32768) ? b->n_inst - i0 : 32768;
+        a.inst0 = i0;
+        CU(launch_score(a, cnt, b->sm_count, (cudaStream_t)stream));
+        b->launches++;
+    }
+    return 0;
+}
+
+static int grow(bqb_batch *b, size_t n_xa, size_t n_out) {
+    if (n_xa > b->cap_xa) {
+        if (b->d_xa) cudaFree(b->d_xa);
+        CU(cudaMalloc(&b->d_xa, sizeof(double) * n_xa));
+        b->cap_xa = n_xa;
+    }
+    if (n_out > b->cap_out) {
+        if (b->d_esm) cudaFree(b->d_esm);
+        if (b->d_em) cudaFree(b->d_em);
+        if (b->d_st) cudaFree(b->d_st);
+        CU(cudaMalloc(&b->d_esm, sizeof(double) * n_out));
+        CU(cudaMalloc(&b->d_em, sizeof(double) * n_out));
+        CU(cudaMalloc(&b->d_st, sizeof(int) * n_out));
+        b->cap_out = n_out;
+    }
+    return 0;
+}
+
+int bqb_score_host(bqb_batch *b, const double *x_a, long long xa_stride, int na, double *esm, double *em, int *status) {
+    int rc = check_ready(b, "bqb_score_host");
+    if (rc) return rc;
+    if (!x_a || !esm || na < 0) return fail(BQB_EINVAL, "bqb_score_host: bad arguments");
+    if (na == 0) return 0;
+    CU(cudaSetDevice(b->device));
+    const size_t B = b->n_inst;
+    const size_t n_xa = xa_stride ? B * (size_t)xa_stride : (size_t)na;
+    rc = grow(b, n_xa, B * (size_t)na);
+    if (rc) return rc;
+    cudaStream_t s = 0;
+    CU(cudaMemcpyAsync(b->d_xa, x_a, sizeof(double) * n_xa, cudaMemcpyHostToDevice, s));
+    rc = bqb_score_device(b, b->d_xa, xa_stride, na, b->d_esm, em ? b->d_em : nullptr, status ? b->d_st : nullptr, na, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(esm, b->d_esm, sizeof(double) * B * na, cudaMemcpyDeviceToHost, s));
+    if (em) CU(cudaMemcpyAsync(em, b->d_em, sizeof(double) * B * na, cudaMemcpyDeviceToHost, s));
+    if (status) CU(cudaMemcpyAsync(status, b->d_st, sizeof(int) * B * na, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int bqb_mean_neg_device(bqb_batch *b, const double *d_esm, long long stride, long long na, double *d_loss, void *stream) {
+    if (!b || !d_esm || !d_loss || na < 0) return fail(BQB_EINVAL, "bqb_mean_neg_device: bad arguments");
+    CU(cudaSetDevice(b->device));
+    CU(launch_mean_neg(d_esm, stride, b->n_inst, na, d_loss, (cudaStream_t)stream));
+    b->launches++;
+    return 0;
+}
+
+int bqb_expected_var_device(bqb_batch *b, int inst, const double *d_esm, long long na, double *d_out, void *stream) {
+    int rc = check_ready(b, "bqb_expected_var_device");
+    if (rc) return rc;
+    if (inst < 0 || inst >= b->n_inst || !d_esm || !d_out) return fail(BQB_EINVAL, "bqb_expected_var_device: bad arguments");
+    const double *h = &b->h_hdr[(size_t)inst * H_COUNT];
+    CU(cudaSetDevice(b->device));
+    CU(launch_expected_var(d_esm, na, h[H_ZM] * h[H_ZM] + h[H_ZV], d_out, (cudaStream_t)stream));   // bq.py:374-377
+    b->launches++;
+    return 0;
+}
+
+int bqb_argmin_device(bqb_batch *b, const double *d_v, long long n, double *min_out, long long *idx_out, void *stream) {
+    if (!b || !d_v || n < 1 || !min_out || !idx_out) return fail(BQB_EINVAL, "bqb_argmin_device: bad arguments");
+    CU(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(launch_argmin(d_v, n, b->d_red_val, b->d_red_idx, b->sm_count, s));
+    b->launches += 2;
+    CU(cudaMemcpyAsync(min_out, b->d_red_val, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(idx_out, b->d_red_idx, sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+unsigned long long bqb_launch_count(bqb_batch *b) { return b ? b->launches : 0; }
+
+int bqb_model_doubles(bqb_batch *b) { return b ? b->lay.total : 0; }
+
+int bqb_model_read(bqb_batch *b, int inst, double *out) {
+    if (!b || !b->ready || inst < 0 || inst >= b->n_inst || !out) return fail(BQB_EINVAL, "bqb_model_read: bad arguments");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpy(out, b->d_models + (size_t)inst * b->lay.total, sizeof(double) * b->lay.total, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Reductions of choose_next / marginalize (bq.py:640-665): the mean over hyper-parameter
+// samples of -esm (sequential in sample order, like numpy's mean(axis=0) over rows), the
+// expected variance Zm^2 + Zv - esm (bq.py:374-377), and a deterministic (min, first index)
+// reduction that shards combine across GPUs.
+#include "bq_common.cuh"
+
+namespace bqb {
+
+__global__ void mean_neg_kernel(const double *__restrict__ esm, long long stride, int n_inst, long long na,
+                                double *__restrict__ loss) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < na; p += (long long)gridDim.x * blockDim.x) {
+        double s = 0;
+        for (int b = 0; b < n_inst; ++b) s += -esm[(size_t)b * stride + p];   // pairwise-free: sample order
+        loss[p] = s / n_inst;
+    }
+}
+
+__global__ void expected_var_kernel(const double *__restrict__ esm, long long na, double msm, double *__restrict__ out) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < na; p += (long long)gridDim.x * blockDim.x)
+        out[p] = msm - esm[p];
+}
+
+__device__ __forceinline__ void better(double &v, long long &i, double v2, long long i2) {
+    // NaN never wins; ties keep the smaller index (np.argmin semantics for finite data)
+    if (v2 < v || (v2 == v && i2 < i)) { v = v2; i = i2; }
+}
+
+__global__ void argmin_kernel(const double *__restrict__ v, long long n, double *bv, long long *bi) {
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    double best = INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x)
+        better(best, idx, v[p], p);
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        better(best, idx, v2, i2);
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) better(best, idx, sv[w], si[w]);
+        bv[blockIdx.x] = best;
+        bi[blockIdx.x] = idx;
+    }
+}
+
+__global__ void argmin_final_kernel(double *bv, long long *bi, int nblocks) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double best = bv[0];
+        long long idx = bi[0];
+        for (int b = 1; b < nblocks; ++b) better(best, idx, bv[b], bi[b]);
+        bv[0] = best;
+        bi[0] = idx;
+    }
+}
+
+cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, long long na, double *loss, cudaStream_t s) {
+    const int blocks = (int)((na + 255) / 256 < 2368 ? (na + 255) / 256 : 2368);
+    mean_neg_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(esm, stride, n_inst, na, loss);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_expected_var(const double *esm, long long na, double msm, double *out, cudaStream_t s) {
+    const int blocks = (int)((na + 255) / 256 < 2368 ? (na + 255) / 256 : 2368);
+    expected_var_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(esm, na, msm, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_argmin(const double *v, long long n, double *bv, long long *bi, int sm_count, cudaStream_t s) {
+    int blocks = (int)((n + 1023) / 1024);
+    if (blocks > sm_count * 4) blocks = sm_count * 4;
+    if (blocks > 4096) blocks = 4096;
+    if (blocks < 1) blocks = 1;
+    argmin_kernel<<<blocks, 256, 0, s>>>(v, n, bv, bi);
+    argmin_final_kernel<<<1, 32, 0, s>>>(bv, bi, blocks);
+    return cudaGetLastError();
+}
+
+}  // namespace bqb

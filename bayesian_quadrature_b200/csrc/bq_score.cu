@@ -1,0 +1,382 @@
+// Scoring kernel: expected_squared_mean / expected_mean of every query point x_a
+// (replaces the per-point Python loop bq.py:399-402 -> _esm_and_em bq.py:447-527 ->
+//  bq_c.expected_squared_mean_and_mean bq_c.pyx:493-535 -> _esm_and_em bq_c.pyx:425-490).
+//
+// The reference rebuilds and refactorises the (nsc+1)^2 bordered Gram matrix for every point.
+// Here the factor of K_l(x_sc, x_sc) is fixed per model instance and every point only needs the
+// border:  v = L^-1 k_a,  s = (k_aa + jitter) - v.v,  A_a = (b_a - k_a.gamma) / s, ...
+// Written as  V = (c L_ss^-1) E  for a tile of points, where E[k][p] = exp(-(x_p - x_s[k])^2 / 2w^2),
+// this is a lower-triangular FP64 GEMM whose B operand is *generated*, not loaded:
+//
+//   * one warp owns 8*NT query points and ALL rows; lane l computes exactly the B-fragment element
+//     it must feed to mma.m8n8k4 (k = 4 ks + (l & 3), point = l >> 2), so the cross-kernel tile
+//     lives in registers (KS*NT doubles per lane) and never touches shared memory or HBM;
+//   * the A operand (c L_ss^-1, the candidate rows W, g_gamma, g_alpha; and c L_tl^-1) is stored
+//     by the setup kernel in fragment order, so one conflict-free LDS.64 per lane feeds NT DMMAs;
+//   * only v.v is needed from the triangular part: accumulators are squared and summed in
+//     registers, one block of 8 rows at a time, and no n x n (or n x T) intermediate is stored;
+//   * the candidate block (nc <= 16 rows) and the scalar algebra run per point in a warp tail.
+//
+// Grid: persistent CTAs (a multiple of the SM count) striding over point tiles; gridDim.y = model
+// instances (hyper-parameter sets or independent problems).
+#include "bq_common.cuh"
+
+namespace bqb {
+
+struct ScoreArgs {
+    const double *models;     // [B][lay.total]
+    Layout lay;
+    const double *x_a;        // [na] (xa_stride = 0) or [B][xa_stride]
+    long long xa_stride;
+    int na;
+    double *esm, *em;         // [B][out_stride]; em may be null
+    int *status;              // [B][out_stride]; may be null
+    long long out_stride;
+    const double *exp_tab;    // [EXP_TAB]
+    int inst0;
+};
+
+template <int KS, int NT, int WARPS>
+struct ScoreSmem {
+    static constexpr int NBC = KS / 2;
+    static constexpr int TRI = NBC * (NBC + 1) * 32;       // doubles per triangular operand
+    static constexpr int DENSE = 3 * KS * 32;
+    static constexpr int SCR_D = NT * 24 * 8;              // dense-row outputs of one warp
+    static constexpr int SCR_V = NT * 8 * 4;               // qs, qt, tm, flag
+    static constexpr int SCR = SCR_D + SCR_V;
+    static __host__ __device__ constexpr int doubles(int n_small) {
+        return EXP_TAB + n_small + 2 * TRI + DENSE + WARPS * SCR;
+    }
+};
+
+template <int KS, int NT, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a) {
+    using SM = ScoreSmem<KS, NT, WARPS>;
+    extern __shared__ __align__(16) double smem[];
+    const Layout lay = a.lay;
+    double *s_tab = smem;
+    double *s_small = s_tab + EXP_TAB;
+    double *s_af_l = s_small + lay.n_small;
+    double *s_af_d = s_af_l + SM::TRI;
+    double *s_af_t = s_af_d + SM::DENSE;
+    double *s_scr = s_af_t + SM::TRI;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int inst = a.inst0 + blockIdx.y;
+    const double *M = a.models + (size_t)inst * lay.total;
+
+    for (int i = tid; i < EXP_TAB; i += WARPS * 32) s_tab[i] = a.exp_tab[i];
+    for (int i = tid; i < lay.n_small; i += WARPS * 32) s_small[i] = M[i];
+    __syncthreads();
+    const int ns = (int)s_small[H_NS], nc = (int)s_small[H_NC], nsp = (int)s_small[H_NSP], ndb = (int)s_small[H_NDB];
+    const int nb = nsp >> 3, nks = nsp >> 2;
+    {
+        const int ntri = tri_frags(nb) * 32, nd = ndb * nks * 32;
+        for (int i = tid; i < ntri; i += WARPS * 32) {
+            s_af_l[i] = M[lay.off_af_l_tri + i];
+            s_af_t[i] = M[lay.off_af_tl_tri + i];
+        }
+        for (int i = tid; i < nd; i += WARPS * 32) s_af_d[i] = M[lay.off_af_l_dense + i];
+    }
+    __syncthreads();
+
+    const double *s_xs = s_small + lay.off_xs, *s_tol = s_small + lay.off_tol, *s_atl = s_small + lay.off_atl;
+    const double nhl = s_small[H_NHL], nhtl = s_small[H_NHTL];
+    double *scr_d = s_scr + warp * SM::SCR;
+    double *scr_v = scr_d + SM::SCR_D;
+
+    const double *xa = a.x_a + (size_t)inst * a.xa_stride;
+    double *o_esm = a.esm + (size_t)inst * a.out_stride;
+    double *o_em = a.em ? a.em + (size_t)inst * a.out_stride : nullptr;
+    int *o_st = a.status ? a.status + (size_t)inst * a.out_stride : nullptr;
+
+    const int kq = lane & 3, pq = lane >> 2;
+    const int tile_pts = WARPS * 8 * NT;
+    const int ntiles = (a.na + tile_pts - 1) / tile_pts;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int base = tile * tile_pts + warp * 8 * NT;
+        if (base >= a.na) continue;            // warp-uniform
+        double x[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int p = base + nt * 8 + pq;
+            double v = (p < a.na) ? xa[p] : 0.0;
+            x[nt] = isfinite(v) ? v : 0.0;     // invalid x_a is reported by the tail (ST_XA_BAD)
+        }
+        double bf[KS][NT];
+        double q0[NT], q1[NT];
+
+        // ================= phase L: K_l cross-kernel fragments, triangular + dense rows
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            if (ks < nks) {
+                const double xs = s_xs[4 * ks + kq];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double d = x[nt] - xs;
+                    bf[ks][nt] = exp_neg((d * d) * nhl, s_tab);
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { q0[nt] = 0.0; q1[nt] = 0.0; }
+#pragma unroll
+        for (int rb = 0; rb < KS / 2; ++rb) {
+            if (rb < nb) {
+                double c0[NT], c1[NT];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) { c0[nt] = 0.0; c1[nt] = 0.0; }
+                const double *af = s_af_l + (rb * (rb + 1)) * 32 + lane;
+#pragma unroll
+                for (int ks = 0; ks < 2 * rb + 2; ++ks) {
+                    const double av = af[ks * 32];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) dmma(c0[nt], c1[nt], av, bf[ks][nt]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    q0[nt] = fma(c0[nt], c0[nt], q0[nt]);
+                    q1[nt] = fma(c1[nt], c1[nt], q1[nt]);
+                }
+            }
+        }
+#pragma unroll
+        for (int db = 0; db < 3; ++db) {
+            if (db < ndb) {
+                double c0[NT], c1[NT];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) { c0[nt] = 0.0; c1[nt] = 0.0; }
+                const double *af = s_af_d + (db * nks) * 32 + lane;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    if (ks < nks) {
+                        const double av = af[ks * 32];
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) dmma(c0[nt], c1[nt], av, bf[ks][nt]);
+                    }
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    double *d = scr_d + (nt * 24 + db * 8 + pq) * 8 + 2 * kq;
+                    d[0] = c0[nt];
+                    d[1] = c1[nt];
+                }
+            }
+        }
+        // v_s . v_s : sum the 8 row slots (lanes with equal l & 3)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                q0[nt] += __shfl_xor_sync(0xffffffffu, q0[nt], o);
+                q1[nt] += __shfl_xor_sync(0xffffffffu, q1[nt], o);
+            }
+            if (pq == 0) { scr_v[nt * 32 + 2 * kq] = q0[nt]; scr_v[nt * 32 + 2 * kq + 1] = q1[nt]; }
+        }
+
+        // ================= phase TL: K_tl fragments; also gp_log_l.mean (tm) and the isclose test
+        double tm[NT];
+        int close[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { tm[nt] = 0.0; close[nt] = 0; }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            if (ks < nks) {
+                const int k = 4 * ks + kq;
+                const double xs = s_xs[k], tol = s_tol[k], at = s_atl[k];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double d = x[nt] - xs;
+                    close[nt] |= (fabs(d) <= tol);            // np.isclose(x_a, x_s, atol=1e-4)  bq.py:456
+                    const double e = exp_neg((d * d) * nhtl, s_tab);
+                    bf[ks][nt] = e;
+                    tm[nt] = fma(at, e, tm[nt]);              // gp_log_l.mean(x_a)                bq.py:493
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { q0[nt] = 0.0; q1[nt] = 0.0; }
+#pragma unroll
+        for (int rb = 0; rb < KS / 2; ++rb) {
+            if (rb < nb) {
+                double c0[NT], c1[NT];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) { c0[nt] = 0.0; c1[nt] = 0.0; }
+                const double *af = s_af_t + (rb * (rb + 1)) * 32 + lane;
+#pragma unroll
+                for (int ks = 0; ks < 2 * rb + 2; ++ks) {
+                    const double av = af[ks * 32];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) dmma(c0[nt], c1[nt], av, bf[ks][nt]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    q0[nt] = fma(c0[nt], c0[nt], q0[nt]);
+                    q1[nt] = fma(c1[nt], c1[nt], q1[nt]);
+                }
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+                q0[nt] += __shfl_xor_sync(0xffffffffu, q0[nt], o);
+                q1[nt] += __shfl_xor_sync(0xffffffffu, q1[nt], o);
+            }
+            tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 1);
+            tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 2);
+            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 1);
+            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 2);
+            if (pq == 0) { scr_v[nt * 32 + 8 + 2 * kq] = q0[nt]; scr_v[nt * 32 + 8 + 2 * kq + 1] = q1[nt]; }
+            if (kq == 0) { scr_v[nt * 32 + 16 + pq] = tm[nt]; scr_v[nt * 32 + 24 + pq] = close[nt] ? 1.0 : 0.0; }
+        }
+        __syncwarp();
+
+        // ================= tail: one lane per point
+        if (lane < 8 * NT) {
+            const int nt = lane >> 3, pn = lane & 7;
+            const int p = base + lane;
+            if (p < a.na) {
+                const double xv = xa[p];
+                const double Zm = s_small[H_ZM];
+                double esm, em;
+                int st = ST_OK;
+                if (!isfinite(xv)) {
+                    esm = em = nan("");
+                    st = ST_XA_BAD;
+                } else if (scr_v[nt * 32 + 24 + pn] != 0.0) {
+                    em = Zm; esm = Zm * Zm; st = ST_SHORTCUT;
+                } else {
+                    const double qs = scr_v[nt * 32 + pn], qt = scr_v[nt * 32 + 8 + pn], tmv = scr_v[nt * 32 + 16 + pn];
+                    const double *dr = scr_d + (nt * 24) * 8 + pn;          // dense row r at dr[r * 8]
+                    const double c_l = s_small[H_CL], w_l = s_small[H_WL], thresh = s_small[H_THRESH];
+                    const double *s_xc = s_small + lay.off_xc;
+                    double w[NC_MAX], v[NC_MAX];
+                    unsigned mask = 0;
+                    for (int j = 0; j < nc; ++j) {
+                        const double dc = s_xc[j] - xv;
+                        if (fabs(dc) < thresh) mask |= 1u << j;             // bq.py:470 (strict <)
+                        w[j] = c_l * exp(-0.5 * (dc * dc) / (w_l * w_l)) + dr[j * 8];
+                    }
+                    double qc = 0, vg = 0, va = 0, bg = 0, kaa;     // bg = u_gamma_c . u_alpha_c of this pattern
+                    bool pd = true;
+                    if (mask == 0) {
+                        const double *Lc = s_small + lay.off_lcc0, *ug = s_small + lay.off_ug0, *ua = s_small + lay.off_ua0;
+                        for (int i = 0; i < nc; ++i) {
+                            double s = w[i];
+                            for (int k = 0; k < i; ++k) s -= Lc[i * NC_MAX + k] * v[k];
+                            s /= Lc[i * NC_MAX + i];
+                            v[i] = s;
+                            qc = fma(s, s, qc); vg = fma(s, ug[i], vg); va = fma(s, ua[i], va);
+                            bg = fma(ug[i], ua[i], bg);
+                        }
+                        kaa = s_small[H_KAA_E];
+                    } else {
+                        // jitter on the close candidates (bq.py:471-473): refactorise the nc x nc Schur block
+                        const double *S0 = s_small + lay.off_s0, *wb = s_small + lay.off_wb, *wa = s_small + lay.off_wa;
+                        const double j1 = s_small[H_J1];
+                        double Lc[NC_MAX * (NC_MAX + 1) / 2], ug[NC_MAX], ua[NC_MAX];
+                        for (int i = 0; i < nc && pd; ++i) {
+                            for (int j = 0; j <= i; ++j) {
+                                double s = S0[i * NC_MAX + j];
+                                if (i == j && ((mask >> i) & 1u)) s += j1;
+                                for (int k = 0; k < j; ++k) s -= Lc[i * (i + 1) / 2 + k] * Lc[j * (j + 1) / 2 + k];
+                                if (i == j) {
+                                    if (!(s > 0.0)) { pd = false; break; }
+                                    Lc[i * (i + 1) / 2 + i] = sqrt(s);
+                                } else {
+                                    Lc[i * (i + 1) / 2 + j] = s / Lc[j * (j + 1) / 2 + j];
+                                }
+                            }
+                        }
+                        if (pd) {
+                            for (int i = 0; i < nc; ++i) {
+                                double s = w[i], sg = wb[i], sa = wa[i];
+                                for (int k = 0; k < i; ++k) {
+                                    const double l = Lc[i * (i + 1) / 2 + k];
+                                    s -= l * v[k]; sg -= l * ug[k]; sa -= l * ua[k];
+                                }
+                                const double d = Lc[i * (i + 1) / 2 + i];
+                                s /= d; sg /= d; sa /= d;
+                                v[i] = s; ug[i] = sg; ua[i] = sa;
+                                qc = fma(s, s, qc); vg = fma(s, sg, vg); va = fma(s, sa, va);
+                                bg = fma(sg, sa, bg);
+                            }
+                        }
+                        kaa = s_small[H_KAA_N];
+                    }
+                    const double s_ = kaa - (qs + qc);                        // Schur pivot of the new point
+                    if (!pd || !(s_ > 0.0)) {
+                        em = Zm; esm = Zm * Zm; st = ST_NOTPD;                // bq.py:481-490
+                    } else {
+                        const double ba = s_small[H_BA_S] + bg;               // int_K(x_sc) . alpha_P
+                        const double kg = dr[nc * 8] + vg;                    // k_a . gamma_P
+                        const double ka = dr[(nc + 1) * 8] + va;              // k_a . alpha_P
+                        // int_K at the new point (gauss_c.pyx:162)
+                        const double Lb = s_small[H_LB];
+                        const double diff = xv - s_small[H_MU];
+                        const double b_a = s_small[H_HL2] *
+                            exp(-0.5 * ((1.8378770664093453 + s_small[H_LOGDETB]) + diff * ((diff / Lb) / Lb)));
+                        const double A_a = (b_a - kg) / s_;                   // last entry of K_sca^-1 int_K (bq_c.pyx:467-469)
+                        const double A_sc_l = ba - A_a * ka;                  // dot(A_sca[:-1], l_sc)       (bq_c.pyx:470)
+                        const double tC = s_small[H_KTT] - qt;                // gp_log_l.cov(x_a)            bq.py:496
+                        const double a1 = tmv + 0.5 * tC;                     // int_exp_norm(1, tm, tC)      gauss_c.pyx:87
+                        const double a2 = 2.0 * tmv + 2.0 * tC;               // int_exp_norm(2, tm, tC)
+                        if (a1 > MAX_EXPONENT) {                              // bq_c.pyx:472-475
+                            esm = em = INFINITY;
+                        } else {
+                            const double e1 = exp(a1);
+                            em = A_sc_l + A_a * e1;                           // bq_c.pyx:477
+                            if (a2 > MAX_EXPONENT) {
+                                esm = INFINITY;                               // bq_c.pyx:479-483
+                            } else {
+                                const double e2 = exp(a2);
+                                esm = (A_sc_l * A_sc_l) + (2 * A_sc_l * A_a * e1) + ((A_a * A_a) * e2);   // bq_c.pyx:485
+                            }
+                        }
+                        if (isnan(esm) || esm < 0) st |= ST_ESM_BAD;          // bq.py:514
+                        if (isnan(em)) st |= ST_EM_BAD;                       // bq.py:518
+                        if (isinf(esm)) st |= ST_ESM_INF;                     // bq.py:522
+                        if (isinf(em)) st |= ST_EM_INF;                       // bq.py:524
+                    }
+                }
+                o_esm[p] = esm;
+                if (o_em) o_em[p] = em;
+                if (o_st) o_st[p] = st;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int KS, int NT, int WARPS, int MINB>
+static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream) {
+    using SM = ScoreSmem<KS, NT, WARPS>;
+    const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small);
+    auto kern = bq_score_kernel<KS, NT, WARPS, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    const int tile_pts = WARPS * 8 * NT;
+    const int ntiles = (a.na + tile_pts - 1) / tile_pts;
+    int per_inst = (sm_count * MINB + n_inst - 1) / n_inst;      // persistent: ~MINB CTAs per SM in total
+    if (per_inst > ntiles) per_inst = ntiles;
+    if (per_inst < 1) per_inst = 1;
+    dim3 grid(per_inst, n_inst);
+    kern<<<grid, WARPS * 32, bytes, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// nsp_cap selects the instantiation: 16, 64, 128 (k-steps 4, 16, 32)
+cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream) {
+    switch (a.lay.nsp_cap) {
+        case 16: return launch_cfg<4, 2, 8, 2>(a, n_inst, sm_count, stream);
+        case 64: return launch_cfg<16, 2, 8, 2>(a, n_inst, sm_count, stream);
+        case 128: return launch_cfg<32, 2, 8, 1>(a, n_inst, sm_count, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+int score_launch_count_per_call() { return 1; }
+
+}  // namespace bqb

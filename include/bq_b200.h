@@ -1,0 +1,125 @@
+/* bq_b200.h — C-ABI of the B200-native expected-variance active-sampling path of
+ * jhamrick/bayesian-quadrature (v0.2.0).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / numpy / C++ types.  It
+ * replaces the native entry points the reference's Python layer binds for this path
+ * (Cython typed-memoryview functions); each function below names the reference
+ * interface it stands in for (paths relative to the reference repository).
+ *
+ * A *batch* is B independent model instances — one BQ problem under one hyper-parameter set
+ * each — resident in HBM.  The reference evaluates one query point per call of
+ * BQ._esm_and_em (bayesian_quadrature/bq.py:447-527); here ONE call scores a whole vector of
+ * query points for every instance of the batch.
+ *
+ * All floating point data is IEEE float64.  Return value: 0 = success; < 0 = argument/state
+ * error (BQB_E*, the reference raises ValueError via la.value_error, linalg_c.pyx:49-50);
+ * > 0 = a cudaError_t.  bqb_last_error() gives the message (thread local).  Functions never
+ * throw and never retain caller pointers.
+ */
+#ifndef BQ_B200_H
+#define BQ_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BQB_EINVAL (-1)        /* bad argument (reference: ValueError) */
+#define BQB_EUNSUPPORTED (-2)  /* outside device limits: ns > 128 (this round), nc > 16, not sm_100 */
+#define BQB_ESTATE (-3)        /* batch not set up */
+#define BQB_ENUMERIC (-4)      /* an instance failed setup (reference: numpy.linalg.LinAlgError) */
+
+/* per-point status bits written by the scoring kernel; the host shim turns them into the
+ * reference's exceptions / warnings */
+#define BQB_ST_OK 0
+#define BQB_ST_SHORTCUT 1   /* bq.py:456-459: x_a isclose to an observation -> (Z_mean^2, Z_mean) */
+#define BQB_ST_NOTPD 2      /* bq.py:481-490: bordered matrix not PD (LinAlgError) -> (Z_mean^2, Z_mean) */
+#define BQB_ST_ESM_INF 4    /* bq.py:522-523: logger.warn */
+#define BQB_ST_EM_INF 8     /* bq.py:524-525: logger.warn */
+#define BQB_ST_ESM_BAD 16   /* bq.py:514-517: RuntimeError */
+#define BQB_ST_EM_BAD 32    /* bq.py:518-520: RuntimeError */
+#define BQB_ST_XA_BAD 64    /* bq.py:451-452: ValueError */
+
+/* per-instance setup status (bqb_batch_info) */
+#define BQB_SETUP_OK 0
+#define BQB_SETUP_KTL_NOTPD 1       /* gp_log_l.Kxx not positive definite (LinAlgError) */
+#define BQB_SETUP_KL_NOTPD 2        /* gp_l.Kxx not positive definite (LinAlgError) */
+#define BQB_SETUP_MEAN_TOO_LARGE 3  /* bq.py:945-947 LinAlgError("GP mean is too large") */
+#define BQB_SETUP_BAD_INPUT 4       /* non-finite x / l <= 0 / non-positive hyper-parameters (ValueError) */
+
+#define BQB_NC_MAX 16               /* row stride of every x_c / l_c array */
+
+typedef struct bqb_batch bqb_batch;
+
+const char *bqb_last_error(void);
+int bqb_version(void);
+int bqb_device_count(int *count);
+
+/* Padded observation capacity the library would use for `ns` observations (16, 64 or 128), or
+ * BQB_EUNSUPPORTED. */
+int bqb_ns_capacity(int ns);
+
+/* Allocates a batch of n_inst instances on CUDA device `device`, each able to hold up to ns_max
+ * observations and BQB_NC_MAX candidates.  Stands in for BQ.__init__ state allocation
+ * (bq.py:55-92) plus the `gp` objects of BQ.init (bq.py:147-165). */
+int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max);
+void bqb_batch_destroy(bqb_batch *b);
+
+/* Uploads the instances (HOST pointers) and runs the setup kernel.  Per instance i:
+ *   ns[i], nc[i]            observation / candidate counts
+ *   x_s, l_s [i*in_stride]  observation locations and (positive) likelihood values
+ *   x_c [i*BQB_NC_MAX]      candidate locations (already drawn/filtered on the host, bq.py:967-991)
+ *   hyp [i*6]               h_tl, w_tl, s_tl, h_l, w_l, s_l   (GP params of bq.py:132-165)
+ *   prior [i*3]             x_mean, x_var, candidate_thresh   (options of bq.py:94-127)
+ * Computes on device what the reference obtains from the `gp` package and linalg_c:
+ * tl_s = log l_s (bq.py:73), K_tl and its Cholesky factor (gp.Lxx; linalg_c.cho_factor
+ * linalg_c.pyx:55), l_c = exp(gp_log_l.mean(x_c)) (bq.py:985, :949), the factor of K_l(x_sc, x_sc),
+ * alpha_l (gp.inv_Kxx_y), Z_mean (bq_c.Z_mean bq_c.pyx:157), Z_var (bq_c.Z_var bq_c.pyx:264 with
+ * gauss_c.int_int_K1_K2_K1 gauss_c.pyx:416 and gauss_c.int_K1_K2 gauss_c.pyx:235) and
+ * gp_log_l.log_lh + gp_l.log_lh (bq.py:546).  check_max != 0 applies the guard of
+ * BQ._set_gp_log_l_params (bq.py:942-947).  Synchronises `stream` (a cudaStream_t, may be 0). */
+int bqb_batch_setup(bqb_batch *b, const int *ns, const int *nc, const double *x_s, const double *l_s,
+                    int in_stride, const double *x_c, const double *hyp, const double *prior,
+                    int check_max, void *stream);
+
+/* Per-instance results of the setup (HOST output arrays of n_inst entries, any may be NULL;
+ * l_c is [n_inst][BQB_NC_MAX]).  Z_mean / Z_var replace BQ._exact_Z_mean (bq.py:268-291) and
+ * BQ._exact_Z_var (bq.py:329-348). */
+int bqb_batch_info(bqb_batch *b, double *Z_mean, double *Z_var, double *log_lh, int *status, double *l_c);
+
+/* Scores na query points for every instance; replaces the loop of
+ * BQ.expected_squared_mean_and_mean (bq.py:425-445) over BQ._esm_and_em (bq.py:447-527) and
+ * bq_c.expected_squared_mean_and_mean (bq_c.pyx:493-535).
+ *   x_a        query points: shared by all instances (xa_stride = 0) or one row per instance
+ *   esm, em    outputs [n_inst][out_stride] (em may be NULL): expected squared mean / expected mean
+ *   status     per-point BQB_ST_* bits [n_inst][out_stride] (may be NULL)
+ * _device: DEVICE pointers, asynchronous on `stream`.  _host: HOST pointers (out_stride = na);
+ * copies in, scores, copies out and synchronises. */
+int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int na, double *d_esm,
+                     double *d_em, int *d_status, long long out_stride, void *stream);
+int bqb_score_host(bqb_batch *b, const double *x_a, long long xa_stride, int na, double *esm, double *em,
+                   int *status);
+
+/* out[p] = Z_mean^2 + Z_var - esm[p] for instance `inst` (BQ.expected_Z_var, bq.py:374-377).
+ * DEVICE pointers. */
+int bqb_expected_var_device(bqb_batch *b, int inst, const double *d_esm, long long na, double *d_out,
+                            void *stream);
+
+/* loss[p] = mean over instances, in instance order, of -esm[i][p]: the marginal loss of
+ * BQ.choose_next (bq.py:660-662: values[0].mean(axis=0)).  DEVICE pointers. */
+int bqb_mean_neg_device(bqb_batch *b, const double *d_esm, long long stride, long long na, double *d_loss,
+                        void *stream);
+
+/* Deterministic minimum of a DEVICE vector and the FIRST index attaining it (np.min / np.argmin of
+ * bq.py:663).  Results are written to HOST scalars; synchronises `stream`. */
+int bqb_argmin_device(bqb_batch *b, const double *d_v, long long n, double *min_out, long long *idx_out,
+                      void *stream);
+
+/* Introspection for tests and the bench harness. */
+unsigned long long bqb_launch_count(bqb_batch *b);   /* kernels launched through this batch so far */
+int bqb_model_doubles(bqb_batch *b);                  /* size of one device model block */
+int bqb_model_read(bqb_batch *b, int inst, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BQ_B200_H */
