@@ -31,7 +31,8 @@ SYMBOLS = {
     "bqb_batch_destroy": (None, [_vp]),
     "bqb_batch_setup": (ctypes.c_int, [_vp, _ip, _ip, _dp, _dp, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, _vp]),
     "bqb_batch_info": (ctypes.c_int, [_vp, _dp, _dp, _dp, _ip, _dp]),
-    "bqb_score_device": (ctypes.c_int, [_vp, _vp, _ll, ctypes.c_int, _vp, _vp, _vp, _ll, _vp]),
+    "bqb_score_device": (ctypes.c_int, [_vp, _vp, _ll, ctypes.c_int, _vp, _vp, _vp, _ll, _vp, _vp]),
+    "bqb_expected_var_host": (ctypes.c_int, [_vp, ctypes.c_int, _dp, ctypes.c_int, _dp, _ip]),
     "bqb_score_host": (ctypes.c_int, [_vp, _dp, _ll, ctypes.c_int, _dp, _dp, _ip]),
     "bqb_expected_var_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _ll, _vp, _vp]),
     "bqb_mean_neg_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp]),
@@ -157,7 +158,16 @@ class Batch(object):
                                      st.ctypes.data_as(_ip) if want_status else None), "bqb_score_host")
         return esm, em, st
 
-    def score_device(self, x_a, esm, em=None, status=None, stream=None):
+    def expected_var_host(self, x_a, inst=0):
+        """BQ.expected_Z_var for one instance: numpy in, numpy out, plus the OR of the status bits."""
+        x_a = _d(x_a)
+        out = np.empty(x_a.shape[0])
+        fl = ctypes.c_int(0)
+        _check(load().bqb_expected_var_host(self._h, int(inst), _pd(x_a), x_a.shape[0], _pd(out), ctypes.byref(fl)),
+               "bqb_expected_var_host")
+        return out, fl.value
+
+    def score_device(self, x_a, esm, em=None, status=None, flags=None, stream=None):
         """torch CUDA tensors: x_a float64 [na] or [B, na]; esm/em float64 [B, na]; status int32 [B, na]."""
         if x_a.dim() == 1:
             stride, na = 0, x_a.shape[0]
@@ -165,7 +175,7 @@ class Batch(object):
             stride, na = x_a.stride(0), x_a.shape[1]
         out_stride = esm.stride(0) if esm.dim() == 2 else esm.shape[0]
         _check(load().bqb_score_device(self._h, _ptr(x_a), stride, na, _ptr(esm), _ptr(em), _ptr(status), out_stride,
-                                       _vp(stream) if stream else None), "bqb_score_device")
+                                       _ptr(flags), _vp(stream) if stream else None), "bqb_score_device")
 
     def expected_var_device(self, inst, esm, out, stream=None):
         _check(load().bqb_expected_var_device(self._h, int(inst), _ptr(esm), esm.numel(), _ptr(out),

@@ -1,0 +1,628 @@
+"""``BQ`` — drop-in for ``bayesian_quadrature.BQ`` (reference: bayesian_quadrature/bq.py) whose
+expected-variance active-sampling path runs on a B200 through libbq_b200.so.
+
+Same constructor, options, methods, return types and exceptions as the reference class.  What
+differs is *where the work happens*:
+
+* ``expected_squared_mean`` / ``expected_mean`` / ``expected_squared_mean_and_mean`` /
+  ``expected_Z_var`` make ONE device call for the whole vector ``x_a`` (the reference loops in
+  Python and refactorises a bordered Gram matrix per point, bq.py:399-402 / :447-527);
+* ``Z_mean`` / ``Z_var`` / ``l_c`` come from the device setup kernel, once per (data, hyper set);
+* ``choose_next`` scores all sampled hyper-parameter sets as one device batch and reduces the
+  marginal loss on device (bq.py:659-666); ``marginalize`` stays a generic host loop because it
+  accepts arbitrary callables (bq.py:604-657).
+
+Host-only pieces (candidate draw with the numpy RNG, hyper-parameter fitting/sampling, plotting,
+pickling) stay host Python.  There is no CPU fallback for the device pieces: without the CUDA
+library or a GPU they raise.
+"""
+import logging
+import os
+import warnings
+from copy import copy, deepcopy
+
+import numpy as np
+
+from . import _lib
+from . import util
+from .gp import GP, GaussianKernel, PeriodicKernel
+
+logger = logging.getLogger("bayesian_quadrature")
+DTYPE = np.dtype("float64")
+MIN = np.log(np.exp2(np.float64(np.finfo(np.float64).minexp + 4)))   # bq.py:15
+MAX = np.log(np.exp2(np.float64(np.finfo(np.float64).maxexp - 4)))   # bq.py:16
+
+_SETUP_ERRORS = {
+    _lib.SETUP_KTL_NOTPD: (np.linalg.LinAlgError, "Matrix is not positive definite (gp_log_l.Kxx)"),
+    _lib.SETUP_KL_NOTPD: (np.linalg.LinAlgError, "Matrix is not positive definite (gp_l.Kxx)"),
+    _lib.SETUP_MEAN_TOO_LARGE: (np.linalg.LinAlgError, "GP mean is too large"),      # bq.py:947
+    _lib.SETUP_BAD_INPUT: (ValueError, "invalid (non-finite or non-positive) model inputs"),
+}
+
+
+def _raise_setup(status):
+    exc, msg = _SETUP_ERRORS.get(int(status), (RuntimeError, "device setup failed with status %s" % status))
+    raise exc(msg)
+
+
+class _DeviceModel(object):
+    """The device-resident factors of ONE (data, candidates, hyper-parameter) state."""
+
+    def __init__(self, key, x_s, l_s, x_c, params_tl, params_l, x_mean, x_var, thresh, device, check_max=False):
+        self.key = key
+        ns, nc = x_s.shape[0], x_c.shape[0]
+        self.batch = _lib.Batch(1, ns, device=device)
+        hyp = np.concatenate([np.asarray(params_tl, dtype=DTYPE), np.asarray(params_l, dtype=DTYPE)])
+        info = self.batch.setup([ns], [nc], x_s[None], l_s[None], x_c[None] if nc else np.zeros((1, 0)),
+                                hyp[None], np.array([[x_mean, x_var, thresh]]), check_max=check_max)
+        self.status = int(info["status"][0])
+        self.Z_mean = float(info["Z_mean"][0])
+        self.Z_var = float(info["Z_var"][0])
+        self.log_lh = float(info["log_lh"][0])
+        self.l_c = np.array(info["l_c"][0, :nc])
+
+
+class BQ(object):
+    r"""Bayesian quadrature estimate of :math:`Z = \int \ell(x) N(x | \mu, \sigma^2) dx` with a GP
+    over :math:`\log\ell` and a second GP over :math:`\exp(\log\ell)` (reference class docstring,
+    bq.py:19-49).
+
+    Parameters
+    ----------
+    x, l : 1-D arrays of sample locations and (strictly positive) likelihood values
+    options : the six mandatory keyword options of :meth:`load_options`
+    """
+
+    def __init__(self, x, l, **options):
+        self.x_s = np.array(x, dtype=DTYPE)
+        self.l_s = np.array(l, dtype=DTYPE)
+        # same validation order and messages as bq.py:63-70
+        if (self.l_s <= 0).any():
+            raise ValueError("l_s contains zero or negative values")
+        if self.x_s.ndim > 1:
+            raise ValueError("invalid number of dimensions for x")
+        if self.l_s.ndim > 1:
+            raise ValueError("invalid number of dimensions for l")
+        if self.x_s.shape != self.l_s.shape:
+            raise ValueError("shape mismatch for x and l")
+        self.tl_s = np.log(self.l_s)
+        self.ns = self.x_s.shape[0]
+
+        self.load_options(**options)
+        self.initialized = False
+        self.gp_log_l = self.gp_l = None
+        self.x_c = self.l_c = self.nc = None
+        self.x_sc = self.l_sc = self.nsc = None
+        self._approx_x = self._approx_px = None
+        self._reset_device_state()
+
+    def _reset_device_state(self):
+        self._dev_model = None
+        self._last_d2h_bytes = 0
+        #: CUDA device index of this object's kernels (one process per GPU: LOCAL_RANK)
+        self.device = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def load_options(self, kernel, n_candidate, candidate_thresh, x_mean, x_var, optim_method):
+        """Same six mandatory options as the reference (bq.py:94-127)."""
+        self.options = {
+            "kernel": kernel,
+            "n_candidate": int(n_candidate),
+            "candidate_thresh": float(candidate_thresh),
+            "x_mean": np.array([x_mean], dtype=DTYPE, order="F"),
+            "x_cov": np.array([[x_var]], dtype=DTYPE, order="F"),
+            "use_approx": not (kernel is GaussianKernel),
+            "wrapped": kernel is PeriodicKernel,
+            "optim_method": optim_method,
+        }
+        if self.options["use_approx"]:
+            logger.debug("Using approximate solutions for non-Gaussian kernel")
+
+    def _require_exact(self, what):
+        if self.options["use_approx"]:
+            raise NotImplementedError(
+                "%s: only GaussianKernel runs on the CUDA path; the reference's trapezoid approximation for "
+                "other kernels (bq_c.pyx:216-261, :358-422, :538-598) is outside this package's scope" % what)
+
+    # ------------------------------------------------------------------ initialisation
+    def init(self, params_tl, params_l):
+        """Build the two GPs and draw the candidate points (bq.py:132-171)."""
+        self._require_exact("init")
+        kernel = self.options["kernel"]
+        self.gp_log_l = GP(kernel(*params_tl[:-1]), self.x_s, self.tl_s, s=params_tl[-1])
+        self.gp_log_l.jitter = np.zeros(self.ns, dtype=DTYPE)
+        self._choose_candidates(params_l)
+        self.gp_l = GP(kernel(*params_l[:-1]), self.x_sc, self.l_sc, s=params_l[-1])
+        self.gp_l.jitter = np.zeros(self.nsc, dtype=DTYPE)
+        self._approx_x = self._make_approx_x()
+        self._approx_px = self._make_approx_px()
+        self.initialized = True
+
+    def _choose_candidates(self, params_l=None):
+        """Candidate draw and filtering on the host with the global numpy RNG, exactly the calls of
+        bq.py:967-991; their values l_c = exp(gp_log_l.mean(x_c)) come from the device."""
+        logger.debug("Choosing candidate points")
+        if self.options["wrapped"]:
+            xmin, xmax = -np.pi * self.gp_log_l.K.p, np.pi * self.gp_log_l.K.p
+        else:
+            xmin = self.x_s.min() - self.gp_log_l.K.w
+            xmax = self.x_s.max() + self.gp_log_l.K.w
+        xc = np.random.uniform(xmin, xmax, self.options["n_candidate"])
+        util.filter_candidates(xc, self.x_s, self.options["candidate_thresh"])
+        self.x_c = np.sort(xc[~np.isnan(xc)])
+        self.nc = self.x_c.shape[0]
+        if params_l is None:
+            params_l = self.gp_l.params
+        model = self._build_device_model(self.gp_log_l.params, np.asarray(params_l, dtype=DTYPE), check_max=False)
+        self.l_c = model.l_c
+        self.x_sc = np.array(np.concatenate([self.x_s, self.x_c]))
+        self.l_sc = np.array(np.concatenate([self.l_s, self.l_c]))
+        self.nsc = self.ns + self.nc
+
+    # ------------------------------------------------------------------ device model cache
+    def _state_key(self, params_tl, params_l):
+        return (self.x_s.tobytes(), self.l_s.tobytes(), self.x_c.tobytes(), tuple(float(p) for p in params_tl),
+                tuple(float(p) for p in params_l), float(self.options["x_mean"][0]), float(self.options["x_cov"][0, 0]),
+                self.options["candidate_thresh"], self.device)
+
+    def _build_device_model(self, params_tl, params_l, check_max):
+        key = self._state_key(params_tl, params_l)
+        if self._dev_model is not None and self._dev_model.key == key:
+            model = self._dev_model
+        else:
+            if self._dev_model is not None:
+                self._dev_model.batch.close()
+            model = _DeviceModel(key, self.x_s, self.l_s, self.x_c, params_tl, params_l,
+                                 float(self.options["x_mean"][0]), float(self.options["x_cov"][0, 0]),
+                                 self.options["candidate_thresh"], self.device, check_max=check_max)
+            self._dev_model = model
+        if model.status != _lib.SETUP_OK:
+            self._dev_model = None
+            _raise_setup(model.status)
+        return model
+
+    def _device_model(self):
+        """Device factors for the *current* state; rebuilt only when data or parameters changed
+        (the counterpart of the `gp` package's memoised Kxx / Lxx / inv_Kxx_y)."""
+        self._require_exact("device model")
+        if not self.initialized and self.gp_l is None:
+            raise RuntimeError("BQ object is not initialized: call init() first")
+        return self._build_device_model(self.gp_log_l.params, self.gp_l.params, check_max=False)
+
+    def _invalidate_device(self):
+        if self._dev_model is not None:
+            self._dev_model.batch.close()
+        self._dev_model = None
+
+    # ------------------------------------------------------------------ mean / variance of l (host GPs)
+    def l_mean(self, x):
+        """Mean of the final approximation to l: the mean of the GP over exp(log l) (bq.py:177-200)."""
+        return self.gp_l.mean(x)
+
+    def l_var(self, x):
+        """Marginal variance of the final approximation (bq.py:202-231)."""
+        v_log_l = np.diag(self.gp_log_l.cov(x)).copy()
+        m_l = self.gp_l.mean(x)
+        l_var = v_log_l * m_l ** 2
+        l_var[l_var < 0] = 0
+        return l_var
+
+    # ------------------------------------------------------------------ Z
+    def Z_mean(self):
+        """E[Z] (bq.py:237-291; bq_c.Z_mean bq_c.pyx:157-213), computed by the setup kernel."""
+        m_Z = self._device_model().Z_mean
+        if m_Z <= 0:
+            warnings.warn("m_Z = %s" % m_Z)          # bq_c.pyx:210-211
+        return m_Z
+
+    def Z_var(self):
+        """V[Z] (bq.py:297-348; bq_c.Z_var bq_c.pyx:264-355), computed by the setup kernel."""
+        V_Z = self._device_model().Z_var
+        if V_Z <= 0:
+            warnings.warn("V_Z = %s" % V_Z)          # bq_c.pyx:352-353
+        return V_Z
+
+    # ------------------------------------------------------------------ expected variance (the hot path)
+    @staticmethod
+    def _check_x_a(x_a):
+        if x_a is None:
+            raise ValueError("invalid value for x_a: %s", x_a)       # bq.py:451-452
+        x_a = np.ascontiguousarray(x_a, dtype=DTYPE)
+        if x_a.ndim != 1:
+            raise ValueError("x_a must be a 1-D array")
+        bad = ~np.isfinite(x_a)
+        if bad.any():
+            raise ValueError("invalid value for x_a: %s", x_a[np.argmax(bad)])
+        return x_a
+
+    def _report(self, x_a, esm, em, status):
+        """The reference's post-checks (bq.py:514-525) on a vector of results."""
+        if status is None:
+            return
+        bad = (status & _lib.ST_ESM_BAD) != 0
+        if bad.any():
+            i = int(np.argmax(bad))
+            raise RuntimeError("invalid expected squared mean for x_a=%s: %s" % (x_a[[i]], esm[i]))
+        bad = (status & _lib.ST_EM_BAD) != 0
+        if bad.any():
+            i = int(np.argmax(bad))
+            raise RuntimeError("invalid expected mean for x_a=%s: %s" % (x_a[[i]], None if em is None else em[i]))
+        for bit, name in ((_lib.ST_ESM_INF, "expected squared mean"), (_lib.ST_EM_INF, "expected mean")):
+            idx = np.nonzero(status & bit)[0]
+            for i in idx[:5]:
+                logger.warning("%s for x_a=%s is infinity!", name, x_a[[i]])
+            if idx.size > 5:
+                logger.warning("%s is infinity for %d more points", name, idx.size - 5)
+
+    def _score(self, x_a, want_em=True):
+        x_a = self._check_x_a(x_a)
+        model = self._device_model()
+        esm, em, st = model.batch.score_host(x_a, want_em=want_em, want_status=True)
+        esm, st = esm[0], st[0]
+        em = em[0] if want_em else None
+        self._last_d2h_bytes = esm.nbytes + st.nbytes + (em.nbytes if want_em else 0)
+        self._report(x_a, esm, em, st)
+        return esm, em, st
+
+    def expected_Z_var(self, x_a):
+        r"""E[V(Z) | l_s, l_a] = E[Z|l_s]^2 + V(Z|l_s) - E[ E[Z|l_s,l_a]^2 ] for every point of `x_a`
+        (bq.py:354-377).  One fused device pass; only the result vector crosses PCIe."""
+        x_a = self._check_x_a(x_a)
+        model = self._device_model()
+        if model.Z_mean <= 0:
+            warnings.warn("m_Z = %s" % model.Z_mean)
+        if model.Z_var <= 0:
+            warnings.warn("V_Z = %s" % model.Z_var)
+        ev, flags = model.batch.expected_var_host(x_a)
+        self._last_d2h_bytes = ev.nbytes + 4
+        if flags & ~(_lib.ST_SHORTCUT | _lib.ST_NOTPD):
+            self._score(x_a, want_em=True)      # slow path: fetch per-point status, raise / warn like bq.py:514-525
+        return ev
+
+    def expected_squared_mean(self, x_a):
+        """E[ E[Z|l_s,l_a]^2 ] for every point of `x_a` (bq.py:379-402)."""
+        return self._score(x_a, want_em=False)[0]
+
+    def expected_mean(self, x_a):
+        """E[ E[Z|l_s,l_a] ] for every point of `x_a` (bq.py:404-423)."""
+        return self._score(x_a)[1]
+
+    def expected_squared_mean_and_mean(self, x_a):
+        """[na, 2] array of (expected squared mean, expected mean) (bq.py:425-445)."""
+        esm, em, _ = self._score(x_a)
+        return np.stack([esm, em], axis=1)
+
+    def _esm_and_em(self, x_a):
+        """Single-point form kept for callers of the reference's private helper (bq.py:447-527)."""
+        if x_a is None or np.isnan(x_a) or np.isinf(x_a):
+            raise ValueError("invalid value for x_a: %s", x_a)
+        esm, em, _ = self._score(np.asarray(x_a, dtype=DTYPE).reshape(1))
+        return esm[0], em[0]
+
+    # ------------------------------------------------------------------ hyper-parameters (host)
+    def _make_llh_params(self, params):
+        """Joint log marginal likelihood of both GPs as a function of the parameter vector
+        (bq.py:533-552); invalid parameters map to -inf."""
+        nparam = len(params)
+
+        def f(x):
+            if x is None or np.isnan(x).any():
+                return -np.inf
+            try:
+                self._set_gp_log_l_params(dict(zip(params, x[:nparam])))
+                self._set_gp_l_params(dict(zip(params, x[nparam:])))
+            except (ValueError, np.linalg.LinAlgError):
+                return -np.inf
+            try:
+                llh = self.gp_log_l.log_lh + self.gp_l.log_lh
+            except (ValueError, np.linalg.LinAlgError):
+                return -np.inf
+            return llh
+        return f
+
+    def _current_params(self, params):
+        p0_tl = [self.gp_log_l.get_param(p) for p in params]
+        p0_l = [self.gp_l.get_param(p) for p in params]
+        return np.array(p0_tl + p0_l)
+
+    def fit_hypers(self, params):
+        """Maximise the joint marginal likelihood over the named parameters (bq.py:554-562)."""
+        f = self._make_llh_params(params)
+        p0 = util.find_good_parameters(f, self._current_params(params), self.options["optim_method"])
+        if p0 is None:
+            raise RuntimeError("couldn't find good parameters")
+
+    def sample_hypers(self, params, n=1, nburn=10):
+        """Slice-sample hyper-parameters of both GPs (bq.py:565-598)."""
+        nparam = len(params)
+        window = 2 * nparam
+        p0 = self._current_params(params)
+        f = self._make_llh_params(params)
+        if f(p0) < MIN:
+            pn = util.find_good_parameters(f, p0, self.options["optim_method"])
+            if pn is None:
+                raise RuntimeError("couldn't find good starting parameters")
+            p0 = pn
+        hypers = util.slice_sample(f, nburn + n, window, p0, nburn=nburn, freq=1)
+        return hypers[:, :nparam], hypers[:, nparam:]
+
+    # ------------------------------------------------------------------ active sampling
+    def marginalize(self, funs, n, params):
+        """Approximate marginals of arbitrary callables over sampled hyper-parameters
+        (bq.py:604-657): generic host loop, one device setup per sample."""
+        state = deepcopy(self.__getstate__())
+        values = []
+        for fun in funs:
+            value = fun()                     # evaluated once just for the output shape (bq.py:626-633)
+            try:
+                m = value.shape
+            except AttributeError:
+                values.append(np.empty(n))
+            else:
+                values.append(np.empty((n,) + m))
+        hypers_tl, hypers_l = self.sample_hypers(params, n=n, nburn=1)
+        for i in range(n):
+            params_tl = dict(zip(params, hypers_tl[i]))
+            params_l = dict(zip(params, hypers_l[i]))
+            self._set_gp_log_l_params(params_tl)
+            self._set_gp_l_params(params_l)
+            for j, fun in enumerate(funs):
+                try:
+                    values[j][i] = fun()
+                except:
+                    logger.error("error with parameters %s and %s", params_tl, params_l)
+                    raise
+        self.__setstate__(state)
+        return values
+
+    def marginal_loss(self, x_a, hypers_tl, hypers_l, params):
+        """Marginal loss of choose_next — the mean over hyper-parameter samples of
+        ``-expected_squared_mean(x_a)`` (bq.py:660-662) — for ALL samples in one device batch.
+        Each sample goes through the semantics of ``_set_gp_log_l_params`` / ``_set_gp_l_params``
+        (bq.py:933-965: l_c recomputed, "GP mean is too large" guard)."""
+        import torch
+        x_a = self._check_x_a(x_a)
+        n = len(hypers_tl)
+        base_tl, base_l = self.gp_log_l.params, self.gp_l.params
+        names = list(self.gp_log_l.K.names) + ["s"]
+        hyp = np.empty((n, 6))
+        for i in range(n):
+            ptl, pl = base_tl.copy(), base_l.copy()
+            for name, v in zip(params, hypers_tl[i]):
+                ptl[names.index(name)] = v
+            for name, v in zip(params, hypers_l[i]):
+                pl[names.index(name)] = v
+            hyp[i, :3], hyp[i, 3:] = ptl, pl
+        batch = _lib.Batch(n, self.ns, device=self.device)
+        try:
+            prior = np.tile([float(self.options["x_mean"][0]), float(self.options["x_cov"][0, 0]),
+                             self.options["candidate_thresh"]], (n, 1))
+            info = batch.setup(np.full(n, self.ns), np.full(n, self.nc), np.tile(self.x_s, (n, 1)),
+                               np.tile(self.l_s, (n, 1)), np.tile(self.x_c, (n, 1)), hyp, prior, check_max=True)
+            bad = np.nonzero(info["status"])[0]
+            if bad.size:
+                logger.error("error with parameters %s", hyp[bad[0]])
+                _raise_setup(info["status"][bad[0]])
+            dev = torch.device("cuda", self.device)
+            x_d = torch.from_numpy(x_a).to(dev)
+            loss = torch.zeros(x_a.shape[0], dtype=torch.float64, device=dev)
+            esm = torch.empty(n, x_a.shape[0], dtype=torch.float64, device=dev)
+            flags = torch.zeros(n, dtype=torch.int32, device=dev)
+            batch.score_device(x_d, esm, None, None, flags)
+            batch.mean_neg_device(esm, loss)
+            fl = int(np.bitwise_or.reduce(flags.cpu().numpy()))
+            if fl & (_lib.ST_ESM_BAD | _lib.ST_EM_BAD):
+                raise RuntimeError("invalid expected squared mean under a sampled hyper-parameter set")
+            return loss, batch
+        except Exception:
+            batch.close()
+            raise
+
+    def choose_next(self, x_a, n, params, plot=False, deterministic=False):
+        """Pick the next query location: argmin over `x_a` of the marginal negative expected squared
+        mean (bq.py:659-681).  Like the reference, ties within ``np.isclose`` of the minimum are
+        broken with ``np.random.choice``; ``deterministic=True`` returns the first minimiser instead."""
+        x_a = self._check_x_a(x_a)
+        state = deepcopy(self.__getstate__())
+        hypers_tl, hypers_l = self.sample_hypers(params, n=n, nburn=1)
+        self.__setstate__(state)
+        loss_d, batch = self.marginal_loss(x_a, hypers_tl, hypers_l, params)
+        try:
+            if deterministic:
+                _, choice = batch.argmin_device(loss_d)
+                loss = None
+            else:
+                loss = loss_d.cpu().numpy()
+                best = np.min(loss)
+                close = np.nonzero(np.isclose(loss, best))[0]
+                choice = np.random.choice(close)
+        finally:
+            batch.close()
+        best = x_a[choice]
+        if plot:
+            self._plot_choice(x_a, loss if loss is not None else loss_d.cpu().numpy(), best)
+        return best
+
+    def add_observation(self, x_a, l_a):
+        """Add (or average in) an observation and re-initialise (bq.py:683-701)."""
+        diffs = np.abs(x_a - self.x_s)
+        if diffs.min() < self.options["candidate_thresh"]:
+            c = diffs.argmin()
+            logger.debug("x_a=%s is close to x_s=%s, averaging them", x_a, self.x_s[c])
+            self.x_s[c] = (self.x_s[c] + x_a) / 2.
+            self.l_s[c] = (self.l_s[c] + l_a) / 2.
+            self.tl_s[c] = np.log(float(self.l_s[c]))
+        else:
+            self.x_s = np.append(self.x_s, float(x_a))
+            self.l_s = np.append(self.l_s, float(l_a))
+            self.tl_s = np.append(self.tl_s, np.log(float(l_a)))
+            self.ns += 1
+        self.init(self.gp_log_l.params, self.gp_l.params)
+
+    # ------------------------------------------------------------------ parameter setters
+    def _set_gp_log_l_params(self, params):
+        """bq.py:933-957: set parameters of the GP over log l, recompute the candidate values
+        l_c = exp(mean(x_c)) (on device, with the "GP mean is too large" guard) and retarget gp_l."""
+        for p, v in params.items():
+            self.gp_log_l.set_param(p, v)
+        self.gp_log_l.jitter.fill(0)
+        model = self._build_device_model(self.gp_log_l.params, self.gp_l.params, check_max=True)
+        self.l_c = model.l_c
+        self.l_sc = np.array(np.concatenate([self.l_s, self.l_c]))
+        self.gp_l.x = self.x_sc
+        self.gp_l.y = self.l_sc
+        self.gp_l.jitter.fill(0)
+
+    def _set_gp_l_params(self, params):
+        """bq.py:959-965."""
+        for p, v in params.items():
+            self.gp_l.set_param(p, v)
+        self.gp_l.jitter.fill(0)
+
+    # ------------------------------------------------------------------ approximation grid (state only)
+    def _make_approx_x(self, xmin=None, xmax=None, n=1000):
+        """bq.py:993-1006 (kept because the grid is part of the pickled state)."""
+        if xmin is None:
+            xmin = -np.pi * self.gp_log_l.K.p if self.options["wrapped"] else self.x_sc.min() - self.gp_log_l.K.w
+        if xmax is None:
+            xmax = np.pi * self.gp_log_l.K.p if self.options["wrapped"] else self.x_sc.max() + self.gp_log_l.K.w
+        return np.linspace(xmin, xmax, n)
+
+    def _make_approx_px(self, x=None):
+        """Prior density on the approximation grid (bq.py:1008-1026, bq_c.p_x_gaussian)."""
+        if x is None:
+            x = self._approx_x
+        mu = float(self.options["x_mean"][0])
+        var = float(self.options["x_cov"][0, 0])
+        return np.exp(-0.5 * (np.log(2 * np.pi) + np.log(var) + (x - mu) ** 2 / var))
+
+    # ------------------------------------------------------------------ plotting (host, optional matplotlib)
+    @staticmethod
+    def _plt():
+        import matplotlib.pyplot as plt
+        return plt
+
+    def plot_gp_log_l(self, ax, f_l=None, xmin=None, xmax=None):
+        x = self._make_approx_x(xmin=xmin, xmax=xmax, n=1000)
+        if f_l is not None:
+            ax.plot(x, np.log(f_l(x)), "k-", lw=2)
+        self.gp_log_l.plot(ax, xlim=[x.min(), x.max()], color="r")
+        ax.plot(self.x_c, np.log(self.l_c), "bs", markersize=4, label=r"$m_{\log\ell}(x_c)$")
+        ax.set_title(r"GP over $\log\ell$")
+        util.set_scientific(ax, -5, 4)
+
+    def plot_gp_l(self, ax, f_l=None, xmin=None, xmax=None):
+        x = self._make_approx_x(xmin=xmin, xmax=xmax, n=1000)
+        if f_l is not None:
+            ax.plot(x, f_l(x), "k-", lw=2)
+        self.gp_l.plot(ax, xlim=[x.min(), x.max()], color="r")
+        ax.plot(self.x_c, self.l_c, "bs", markersize=4, label=r"$\exp(m_{\log\ell}(x_c))$")
+        ax.set_title(r"GP over $\exp(\log\ell)$")
+        util.set_scientific(ax, -5, 4)
+
+    def plot_l(self, ax, f_l=None, xmin=None, xmax=None, legend=True):
+        x = self._make_approx_x(xmin=xmin, xmax=xmax, n=1000)
+        if f_l is not None:
+            ax.plot(x, f_l(x), "k-", lw=2, label=r"$\ell(x)$")
+        l_mean = self.l_mean(x)
+        l_sd = np.sqrt(self.l_var(x))
+        ax.fill_between(x, l_mean - l_sd, l_mean + l_sd, color="r", alpha=0.2)
+        ax.plot(x, l_mean, "r-", lw=2, label="final approx")
+        ax.plot(self.x_s, self.l_s, "ro", markersize=5, label=r"$\ell(x_s)$")
+        ax.plot(self.x_c, self.l_c, "bs", markersize=4, label=r"$\exp(m_{\log\ell}(x_c))$")
+        ax.set_title("Final Approximation")
+        ax.set_xlim(x.min(), x.max())
+        util.set_scientific(ax, -5, 4)
+        if legend:
+            ax.legend(loc=0, fontsize=10)
+
+    def plot_expected_squared_mean(self, ax, xmin=None, xmax=None):
+        x_a = self._make_approx_x(xmin=xmin, xmax=xmax, n=1000)
+        ax.plot(x_a, self.expected_squared_mean(x_a), label=r"$E[\mathrm{m}(Z)^2]$", color="k", lw=2)
+        ax.set_xlim(x_a.min(), x_a.max())
+        util.hlines(ax, self.Z_mean() ** 2, color="#00FF00", lw=2, label=r"$\mathrm{m}(Z)^2$")
+        util.vlines(ax, self.x_sc, color="k", linestyle="--", alpha=0.5)
+        util.set_scientific(ax, -5, 4)
+        ax.legend(loc=0, fontsize=10)
+        ax.set_title(r"Expected squared mean of $Z$")
+
+    def plot_expected_variance(self, ax, xmin=None, xmax=None):
+        x_a = self._make_approx_x(xmin=xmin, xmax=xmax, n=1000)
+        ax.plot(x_a, self.expected_Z_var(x_a), label=r"$E[\mathrm{Var}(Z)]$", color="k", lw=2)
+        ax.set_xlim(x_a.min(), x_a.max())
+        util.hlines(ax, self.Z_var(), color="#00FF00", lw=2, label=r"$\mathrm{Var}(Z)$")
+        util.vlines(ax, self.x_sc, color="k", linestyle="--", alpha=0.5)
+        util.set_scientific(ax, -5, 4)
+        ax.legend(loc=0, fontsize=10)
+        ax.set_title(r"Expected variance of $Z$")
+
+    def plot(self, f_l=None, xmin=None, xmax=None):
+        fig, axes = self._plt().subplots(1, 3)
+        self.plot_gp_log_l(axes[0], f_l=f_l, xmin=xmin, xmax=xmax)
+        self.plot_gp_l(axes[1], f_l=f_l, xmin=xmin, xmax=xmax)
+        self.plot_l(axes[2], f_l=f_l, xmin=xmin, xmax=xmax)
+        ymins, ymaxs = zip(*[ax.get_ylim() for ax in axes[1:]])
+        for ax in axes[1:]:
+            ax.set_ylim(min(ymins), max(ymaxs))
+        fig.set_figwidth(14)
+        fig.set_figheight(3.5)
+        return fig, axes
+
+    def _plot_choice(self, x_a, loss, best):
+        fig, (ax1, ax2) = self._plt().subplots(1, 2, sharex=True)
+        self.plot_l(ax1, xmin=x_a.min(), xmax=x_a.max())
+        util.vlines(ax1, best, color="g", linestyle="--", lw=2)
+        ax2.plot(x_a, loss, "k-", lw=2)
+        util.vlines(ax2, best, color="g", linestyle="--", lw=2)
+        ax2.set_title("Negative expected sq. mean")
+        fig.set_figwidth(10)
+        fig.set_figheight(3.5)
+
+    # ------------------------------------------------------------------ pickling / copying
+    _STATE_KEYS = ("gp_log_l", "gp_log_l_jitter", "gp_l", "gp_l_jitter", "_approx_x", "_approx_px")
+
+    def __getstate__(self):
+        """Same keys as the reference (bq.py:840-860, pinned by its test_getstate); device buffers
+        are caches rebuilt from this state and are never pickled."""
+        state = {"x_s": self.x_s, "l_s": self.l_s, "tl_s": self.tl_s, "options": self.options,
+                 "initialized": self.initialized}
+        if self.initialized:
+            state.update(gp_log_l=self.gp_log_l, gp_log_l_jitter=self.gp_log_l.jitter, gp_l=self.gp_l,
+                         gp_l_jitter=self.gp_l.jitter, _approx_x=self._approx_x, _approx_px=self._approx_px)
+        return state
+
+    def __setstate__(self, state):
+        """bq.py:862-902."""
+        self.x_s, self.l_s, self.tl_s = state["x_s"], state["l_s"], state["tl_s"]
+        self.ns = self.x_s.shape[0]
+        self.options = state["options"]
+        self.initialized = state["initialized"]
+        if not hasattr(self, "_dev_model"):
+            self._reset_device_state()
+        if self.initialized:
+            self.gp_log_l = state["gp_log_l"]
+            self.gp_log_l.jitter = state["gp_log_l_jitter"]
+            self.gp_l = state["gp_l"]
+            self.gp_l.jitter = state["gp_l_jitter"]
+            self.x_sc, self.l_sc = self.gp_l._x, self.gp_l._y
+            self.nsc = self.x_sc.shape[0]
+            self.x_c, self.l_c = self.x_sc[self.ns:], self.l_sc[self.ns:]
+            self.nc = self.nsc - self.ns
+            self._approx_x, self._approx_px = state["_approx_x"], state["_approx_px"]
+        else:
+            self.gp_log_l = self.gp_l = None
+            self.x_c = self.l_c = self.nc = None
+            self.x_sc = self.l_sc = self.nsc = None
+            self._approx_x = self._approx_px = None
+
+    def __copy__(self):
+        new = type(self).__new__(type(self))
+        new.__setstate__(self.__getstate__())
+        return new
+
+    def __deepcopy__(self, memo):
+        new = type(self).__new__(type(self))
+        new.__setstate__(deepcopy(self.__getstate__(), memo))
+        return new
+
+    def copy(self, deep=True):
+        return deepcopy(self) if deep else copy(self)

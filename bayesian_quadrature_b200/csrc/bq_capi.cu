@@ -32,6 +32,7 @@ struct ScoreArgs {
     int *status;
     long long out_stride;
     const double *exp_tab;
+    int *flags;
     int inst0;
 };
 void launch_setup(const SetupArgs &a, int n_inst, cudaStream_t stream);
@@ -61,6 +62,7 @@ struct bqb_batch {
     double *d_xa = nullptr, *d_esm = nullptr, *d_em = nullptr;
     int *d_st = nullptr;
     size_t cap_xa = 0, cap_out = 0;
+    int *d_flags = nullptr;
     double *d_red_val = nullptr;
     long long *d_red_idx = nullptr;
     std::vector<double> h_hdr;
@@ -84,13 +86,14 @@ int bqb_ns_capacity(int ns) {
     if (ns <= 16) return 16;
     if (ns <= 64) return 64;
     if (ns <= 128) return 128;
+    if (ns <= 256) return 256;
     return BQB_EUNSUPPORTED;
 }
 
 int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     if (!out || n_inst < 1) return fail(BQB_EINVAL, "bqb_batch_create: bad arguments");
     const int cap = bqb_ns_capacity(ns_max);
-    if (cap < 0) return fail(cap, "bqb_batch_create: ns_max outside the supported range [1, 128]");
+    if (cap < 0) return fail(cap, "bqb_batch_create: ns_max outside the supported range [1, 256]");
     CU(cudaSetDevice(device));
     bqb_batch *b = new bqb_batch();
     b->device = device; b->n_inst = n_inst; b->ns_cap = cap; b->lay = make_layout(cap);
@@ -125,7 +128,7 @@ void bqb_batch_destroy(bqb_batch *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     void *ptrs[] = {b->d_models, b->d_tab, b->d_work, b->d_ns, b->d_nc, b->d_xs, b->d_ls, b->d_xc, b->d_hyp, b->d_prior,
-                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx};
+                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete b;
 }
@@ -194,7 +197,7 @@ static int check_ready(bqb_batch *b, const char *who) {
 }
 
 int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int na, double *d_esm, double *d_em,
-                     int *d_status, long long out_stride, void *stream) {
+                     int *d_status, long long out_stride, int *d_flags, void *stream) {
     int rc = check_ready(b, "bqb_score_device");
     if (rc) return rc;
     if (!d_x_a || !d_esm || na < 0 || out_stride < na) return fail(BQB_EINVAL, "bqb_score_device: bad arguments");
@@ -203,6 +206,8 @@ int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int
     ScoreArgs a;
     a.models = b->d_models; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = xa_stride; a.na = na;
     a.esm = d_esm; a.em = d_em; a.status = d_status; a.out_stride = out_stride; a.exp_tab = b->d_tab;
+    a.flags = d_flags;
+    if (d_flags) CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * b->n_inst, (cudaStream_t)stream));
     // gridDim.y is limited to 65535
     for (int i0 = 0; i0 < b->n_inst; i0 += 32768) {
         const int cnt = (b->n_inst - i0 < 32768) ? b->n_inst - i0 : 32768;
@@ -243,12 +248,41 @@ int bqb_score_host(bqb_batch *b, const double *x_a, long long xa_stride, int na,
     if (rc) return rc;
     cudaStream_t s = 0;
     CU(cudaMemcpyAsync(b->d_xa, x_a, sizeof(double) * n_xa, cudaMemcpyHostToDevice, s));
-    rc = bqb_score_device(b, b->d_xa, xa_stride, na, b->d_esm, em ? b->d_em : nullptr, status ? b->d_st : nullptr, na, s);
+    rc = bqb_score_device(b, b->d_xa, xa_stride, na, b->d_esm, em ? b->d_em : nullptr, status ? b->d_st : nullptr, na,
+                          nullptr, s);
     if (rc) return rc;
     CU(cudaMemcpyAsync(esm, b->d_esm, sizeof(double) * B * na, cudaMemcpyDeviceToHost, s));
     if (em) CU(cudaMemcpyAsync(em, b->d_em, sizeof(double) * B * na, cudaMemcpyDeviceToHost, s));
     if (status) CU(cudaMemcpyAsync(status, b->d_st, sizeof(int) * B * na, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, double *out, int *flags_out) {
+    int rc = check_ready(b, "bqb_expected_var_host");
+    if (rc) return rc;
+    if (inst < 0 || inst >= b->n_inst || !x_a || !out || na < 0) return fail(BQB_EINVAL, "bqb_expected_var_host: bad arguments");
+    if (na == 0) { if (flags_out) *flags_out = 0; return 0; }
+    CU(cudaSetDevice(b->device));
+    rc = grow(b, (size_t)na, (size_t)b->n_inst * na);
+    if (rc) return rc;
+    if (!b->d_flags) CU(cudaMalloc(&b->d_flags, sizeof(int) * b->n_inst));
+    cudaStream_t s = 0;
+    const double *h = &b->h_hdr[(size_t)inst * H_COUNT];
+    CU(cudaMemcpyAsync(b->d_xa, x_a, sizeof(double) * na, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->n_inst, s));
+    ScoreArgs a;
+    a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.x_a = b->d_xa; a.xa_stride = 0; a.na = na;
+    a.esm = b->d_esm; a.em = nullptr; a.status = nullptr; a.out_stride = na; a.exp_tab = b->d_tab;
+    a.flags = b->d_flags; a.inst0 = 0;
+    CU(launch_score(a, 1, b->sm_count, s));
+    CU(launch_expected_var(b->d_esm, na, h[H_ZM] * h[H_ZM] + h[H_ZV], b->d_em, s));   // bq.py:374-377
+    b->launches += 2;
+    CU(cudaMemcpyAsync(out, b->d_em, sizeof(double) * na, cudaMemcpyDeviceToHost, s));
+    int fl = 0;
+    CU(cudaMemcpyAsync(&fl, b->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (flags_out) *flags_out = fl;
     return 0;
 }
 

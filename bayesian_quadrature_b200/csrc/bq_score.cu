@@ -12,7 +12,10 @@
 //     it must feed to mma.m8n8k4 (k = 4 ks + (l & 3), point = l >> 2), so the cross-kernel tile
 //     lives in registers (KS*NT doubles per lane) and never touches shared memory or HBM;
 //   * the A operand (c L_ss^-1, the candidate rows W, g_gamma, g_alpha; and c L_tl^-1) is stored
-//     by the setup kernel in fragment order, so one conflict-free LDS.64 per lane feeds NT DMMAs;
+//     by the setup kernel in fragment order, so one conflict-free LDS.64 per lane feeds NT DMMAs.
+//     For ns <= 128 it is shared-memory resident for the life of the CTA; for ns <= 256 it does
+//     not fit (2 x 264 KB) and is streamed from L2 through a shared-memory chunk buffer, all warps
+//     of the CTA consuming a chunk in lock-step (STREAM);
 //   * only v.v is needed from the triangular part: accumulators are squared and summed in
 //     registers, one block of 8 rows at a time, and no n x n (or n x T) intermediate is stored;
 //   * the candidate block (nc <= 16 rows) and the scalar algebra run per point in a warp tail.
@@ -33,52 +36,123 @@ struct ScoreArgs {
     int *status;              // [B][out_stride]; may be null
     long long out_stride;
     const double *exp_tab;    // [EXP_TAB]
+    int *flags;               // [B] OR of every point's status bits (may be null)
     int inst0;
 };
 
-template <int KS, int NT, int WARPS>
+constexpr int CHUNK_FRAGS = 128;   // STREAM: fragments (256 B each) per staged chunk
+
+// First row block of the chunk that contains row block rb (greedy packing of whole row blocks)
+__host__ __device__ constexpr int chunk_start_rb(int rb) {
+    int start = 0, used = 0;
+    for (int r = 0; r <= rb; ++r) {
+        const int f = 2 * r + 2;
+        if (used + f > CHUNK_FRAGS && used > 0) { start = r; used = 0; }
+        used += f;
+    }
+    return start;
+}
+__host__ __device__ constexpr int chunk_end_rb(int rb, int nb_cap) {   // one past the last row block of rb's chunk
+    const int s = chunk_start_rb(rb);
+    int r = rb;
+    while (r + 1 < nb_cap && chunk_start_rb(r + 1) == s) ++r;
+    return r + 1;
+}
+
+template <int KS, int NT, int WARPS, bool STREAM>
 struct ScoreSmem {
     static constexpr int NBC = KS / 2;
     static constexpr int TRI = NBC * (NBC + 1) * 32;       // doubles per triangular operand
     static constexpr int DENSE = 3 * KS * 32;
+    static constexpr int OPERANDS = STREAM ? CHUNK_FRAGS * 32 : 2 * TRI + DENSE;
     static constexpr int SCR_D = NT * 24 * 8;              // dense-row outputs of one warp
     static constexpr int SCR_V = NT * 8 * 4;               // qs, qt, tm, flag
     static constexpr int SCR = SCR_D + SCR_V;
     static __host__ __device__ constexpr int doubles(int n_small) {
-        return EXP_TAB + n_small + 2 * TRI + DENSE + WARPS * SCR;
+        return EXP_TAB + n_small + OPERANDS + WARPS * SCR;
     }
 };
 
-template <int KS, int NT, int WARPS, int MINB>
+// CTA-wide copy of `count` doubles (multiple of 2) global -> shared, 16 B per thread per step
+template <int THREADS>
+__device__ __forceinline__ void stage(double *dst, const double *__restrict__ src, int count) {
+    const double2 *s2 = reinterpret_cast<const double2 *>(src);
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    for (int i = threadIdx.x; i < count / 2; i += THREADS) d2[i] = __ldg(s2 + i);
+}
+
+// Lower-triangular pass: q += (rows of (A . B))^2, A in fragment order (resident in smem or staged from gmem)
+template <int KS, int NT, int WARPS, bool STREAM>
+__device__ __forceinline__ void tri_pass(const double *af_res, const double *__restrict__ af_gmem, double *s_chunk,
+                                         const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT], int nb, int lane) {
+#pragma unroll
+    for (int rb = 0; rb < KS / 2; ++rb) {
+        if (rb < nb) {
+            const double *af;
+            if constexpr (STREAM) {
+                const int cs = chunk_start_rb(rb);              // compile-time after unrolling
+                if (cs == rb) {
+                    int ce = chunk_end_rb(rb, KS / 2);
+                    if (ce > nb) ce = nb;
+                    __syncthreads();                            // everyone is done with the previous chunk
+                    stage<WARPS * 32>(s_chunk, af_gmem + tri_frags(cs) * 32, (tri_frags(ce) - tri_frags(cs)) * 32);
+                    __syncthreads();
+                }
+                af = s_chunk + (tri_frags(rb) - tri_frags(cs)) * 32 + lane;
+            } else {
+                af = af_res + tri_frags(rb) * 32 + lane;
+            }
+            double c0[NT], c1[NT], e0[NT], e1[NT];              // two independent accumulator chains
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
+#pragma unroll
+            for (int ks = 0; ks < 2 * rb + 2; ks += 2) {
+                const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
+                    dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const double r0 = c0[nt] + e0[nt], r1 = c1[nt] + e1[nt];
+                q0[nt] = fma(r0, r0, q0[nt]);
+                q1[nt] = fma(r1, r1, q1[nt]);
+            }
+        }
+    }
+}
+
+template <int KS, int NT, int WARPS, int MINB, bool STREAM>
 __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a) {
-    using SM = ScoreSmem<KS, NT, WARPS>;
+    using SM = ScoreSmem<KS, NT, WARPS, STREAM>;
+    constexpr int THREADS = WARPS * 32;
     extern __shared__ __align__(16) double smem[];
     const Layout lay = a.lay;
     double *s_tab = smem;
     double *s_small = s_tab + EXP_TAB;
-    double *s_af_l = s_small + lay.n_small;
+    double *s_ops = s_small + lay.n_small;                  // resident operands, or the staging chunk
+    double *s_af_l = s_ops;
     double *s_af_d = s_af_l + SM::TRI;
     double *s_af_t = s_af_d + SM::DENSE;
-    double *s_scr = s_af_t + SM::TRI;
+    double *s_scr = s_ops + SM::OPERANDS;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int inst = a.inst0 + blockIdx.y;
     const double *M = a.models + (size_t)inst * lay.total;
 
-    for (int i = tid; i < EXP_TAB; i += WARPS * 32) s_tab[i] = a.exp_tab[i];
-    for (int i = tid; i < lay.n_small; i += WARPS * 32) s_small[i] = M[i];
+    for (int i = tid; i < EXP_TAB; i += THREADS) s_tab[i] = a.exp_tab[i];
+    for (int i = tid; i < lay.n_small; i += THREADS) s_small[i] = M[i];
     __syncthreads();
-    const int ns = (int)s_small[H_NS], nc = (int)s_small[H_NC], nsp = (int)s_small[H_NSP], ndb = (int)s_small[H_NDB];
+    const int nc = (int)s_small[H_NC], nsp = (int)s_small[H_NSP], ndb = (int)s_small[H_NDB];
     const int nb = nsp >> 3, nks = nsp >> 2;
-    {
-        const int ntri = tri_frags(nb) * 32, nd = ndb * nks * 32;
-        for (int i = tid; i < ntri; i += WARPS * 32) {
-            s_af_l[i] = M[lay.off_af_l_tri + i];
-            s_af_t[i] = M[lay.off_af_tl_tri + i];
-        }
-        for (int i = tid; i < nd; i += WARPS * 32) s_af_d[i] = M[lay.off_af_l_dense + i];
+    if constexpr (!STREAM) {
+        stage<THREADS>(s_af_l, M + lay.off_af_l_tri, tri_frags(nb) * 32);
+        stage<THREADS>(s_af_t, M + lay.off_af_tl_tri, tri_frags(nb) * 32);
+        stage<THREADS>(s_af_d, M + lay.off_af_l_dense, ndb * nks * 32);
+        __syncthreads();
     }
-    __syncthreads();
 
     const double *s_xs = s_small + lay.off_xs, *s_tol = s_small + lay.off_tol, *s_atl = s_small + lay.off_atl;
     const double nhl = s_small[H_NHL], nhtl = s_small[H_NHTL];
@@ -96,13 +170,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int base = tile * tile_pts + warp * 8 * NT;
-        if (base >= a.na) continue;            // warp-uniform
+        if (!STREAM && base >= a.na) continue;       // warp-uniform; STREAM warps must keep hitting the barriers
         double x[NT];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const int p = base + nt * 8 + pq;
             double v = (p < a.na) ? xa[p] : 0.0;
-            x[nt] = isfinite(v) ? v : 0.0;     // invalid x_a is reported by the tail (ST_XA_BAD)
+            x[nt] = isfinite(v) ? v : 0.0;           // invalid x_a is reported by the tail (ST_XA_BAD)
         }
         double bf[KS][NT];
         double q0[NT], q1[NT];
@@ -121,46 +195,38 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
         }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { q0[nt] = 0.0; q1[nt] = 0.0; }
-#pragma unroll
-        for (int rb = 0; rb < KS / 2; ++rb) {
-            if (rb < nb) {
-                double c0[NT], c1[NT];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) { c0[nt] = 0.0; c1[nt] = 0.0; }
-                const double *af = s_af_l + (rb * (rb + 1)) * 32 + lane;
-#pragma unroll
-                for (int ks = 0; ks < 2 * rb + 2; ++ks) {
-                    const double av = af[ks * 32];
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) dmma(c0[nt], c1[nt], av, bf[ks][nt]);
-                }
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    q0[nt] = fma(c0[nt], c0[nt], q0[nt]);
-                    q1[nt] = fma(c1[nt], c1[nt], q1[nt]);
-                }
-            }
-        }
+        tri_pass<KS, NT, WARPS, STREAM>(s_af_l, M + lay.off_af_l_tri, s_ops, bf, q0, q1, nb, lane);
 #pragma unroll
         for (int db = 0; db < 3; ++db) {
             if (db < ndb) {
-                double c0[NT], c1[NT];
+                const double *af;
+                if constexpr (STREAM) {
+                    __syncthreads();
+                    stage<THREADS>(s_ops, M + lay.off_af_l_dense + (db * nks) * 32, nks * 32);
+                    __syncthreads();
+                    af = s_ops + lane;
+                } else {
+                    af = s_af_d + (db * nks) * 32 + lane;
+                }
+                double c0[NT], c1[NT], e0[NT], e1[NT];
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) { c0[nt] = 0.0; c1[nt] = 0.0; }
-                const double *af = s_af_d + (db * nks) * 32 + lane;
+                for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
 #pragma unroll
-                for (int ks = 0; ks < KS; ++ks) {
-                    if (ks < nks) {
-                        const double av = af[ks * 32];
+                for (int ks = 0; ks < KS; ks += 2) {
+                    if (ks < nks) {                  // nks is even
+                        const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
 #pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) dmma(c0[nt], c1[nt], av, bf[ks][nt]);
+                        for (int nt = 0; nt < NT; ++nt) {
+                            dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
+                            dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);
+                        }
                     }
                 }
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     double *d = scr_d + (nt * 24 + db * 8 + pq) * 8 + 2 * kq;
-                    d[0] = c0[nt];
-                    d[1] = c1[nt];
+                    d[0] = c0[nt] + e0[nt];
+                    d[1] = c1[nt] + e1[nt];
                 }
             }
         }
@@ -197,26 +263,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
         }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) { q0[nt] = 0.0; q1[nt] = 0.0; }
-#pragma unroll
-        for (int rb = 0; rb < KS / 2; ++rb) {
-            if (rb < nb) {
-                double c0[NT], c1[NT];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) { c0[nt] = 0.0; c1[nt] = 0.0; }
-                const double *af = s_af_t + (rb * (rb + 1)) * 32 + lane;
-#pragma unroll
-                for (int ks = 0; ks < 2 * rb + 2; ++ks) {
-                    const double av = af[ks * 32];
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) dmma(c0[nt], c1[nt], av, bf[ks][nt]);
-                }
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    q0[nt] = fma(c0[nt], c0[nt], q0[nt]);
-                    q1[nt] = fma(c1[nt], c1[nt], q1[nt]);
-                }
-            }
-        }
+        tri_pass<KS, NT, WARPS, STREAM>(s_af_t, M + lay.off_af_tl_tri, s_ops, bf, q0, q1, nb, lane);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
@@ -344,17 +391,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                 o_esm[p] = esm;
                 if (o_em) o_em[p] = em;
                 if (o_st) o_st[p] = st;
+                if (st && a.flags) atomicOr(a.flags + inst, st);
             }
         }
         __syncwarp();
     }
 }
 
-template <int KS, int NT, int WARPS, int MINB>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM>
 static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream) {
-    using SM = ScoreSmem<KS, NT, WARPS>;
+    using SM = ScoreSmem<KS, NT, WARPS, STREAM>;
     const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small);
-    auto kern = bq_score_kernel<KS, NT, WARPS, MINB>;
+    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     const int tile_pts = WARPS * 8 * NT;
@@ -367,16 +415,15 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
     return cudaGetLastError();
 }
 
-// nsp_cap selects the instantiation: 16, 64, 128 (k-steps 4, 16, 32)
+// nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 256 (operands streamed)
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream) {
     switch (a.lay.nsp_cap) {
-        case 16: return launch_cfg<4, 2, 8, 2>(a, n_inst, sm_count, stream);
-        case 64: return launch_cfg<16, 2, 8, 2>(a, n_inst, sm_count, stream);
-        case 128: return launch_cfg<32, 2, 8, 1>(a, n_inst, sm_count, stream);
+        case 16: return launch_cfg<4, 2, 8, 2, false>(a, n_inst, sm_count, stream);
+        case 64: return launch_cfg<16, 2, 8, 2, false>(a, n_inst, sm_count, stream);
+        case 128: return launch_cfg<32, 2, 8, 1, false>(a, n_inst, sm_count, stream);
+        case 256: return launch_cfg<64, 1, 8, 1, true>(a, n_inst, sm_count, stream);
         default: return cudaErrorInvalidValue;
     }
 }
-
-int score_launch_count_per_call() { return 1; }
 
 }  // namespace bqb

@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — expected_Z_var query-point evaluations per second on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref)
+
+Workload (config.workload): BASELINE.json configs[1] — 1-D BQ, 64 observations, expected_Z_var over
+a 10^6-point grid (SURVEY.md §8(d) generator).  A *step* is one pass of the hot path over the
+grid: the scoring kernel (esm, em, status for every point), the expected-variance kernel
+(Zm^2 + Zv - esm) and the deterministic (min, first index) reduction choose_next needs; at N > 1
+every rank scores its own 10^6-point shard of an N x 10^6 grid (weak scaling) and the ranks
+exchange their (min, index) pairs with one NCCL all-gather.  The per-hyper-set setup kernel (Gram,
+Cholesky, Z_mean, Z_var — amortised over the grid) is timed separately (setup_ms).
+
+`value` is device-resident throughput (inputs already in HBM); `e2e` is the same pass through the
+public host API with host buffers, H2D and D2H copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NS = 64
+NA = 10 ** 6
+METRIC = "expected_Z_var candidate evals/sec"
+UNIT = "evals/s"
+
+
+def w_flop(ns, nc):
+    """Algorithmic FP64 flops per evaluation."""
+    n = ns + nc
+    return n * n + ns * ns + 2 * (3 * n + 2 * ns) + 40
+
+
+def w_exp(ns, nc):
+    return ns + nc + ns + 4
+
+
+def fp64_peak_tflops():
+    """FP64 roofline denominator.  MEASURED_PEAKS.json carries no FP64 figure, so the peak is this
+    repo's own microbenchmark (bench_micro/fp64_peaks.cu, DMMA m8n8k4 on all SMs), committed as
+    profiles/fp64_peaks_r01.json."""
+    p = os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")
+    try:
+        with open(p) as fh:
+            d = json.load(fh)
+        return max(v for k, v in d.items() if k.startswith("dmma") or k.startswith("dfma")), "measured:profiles/fp64_peaks_r01.json"
+    except Exception:
+        return 37.2, "nominal:148 SM x 64 DFMA/clk x 1.965 GHz"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def build_problem():
+    """C2 inputs.  The candidate draw uses the host RNG exactly like BQ.init (bq.py:967-991)."""
+    from bayesian_quadrature_b200 import synthetic
+    from bayesian_quadrature_b200.bq import BQ
+    from bayesian_quadrature_b200.gp import GaussianKernel
+    bq = synthetic.make_bq(BQ, GaussianKernel, NS)
+    return bq
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    lo, hi, na_total = args
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    import warnings
+    warnings.simplefilter("ignore")
+    from oracle import build_ref
+    from bayesian_quadrature_b200 import synthetic
+    bqmod, gp = build_ref.import_reference()
+    bq = synthetic.make_bq(bqmod.BQ, gp.GaussianKernel, NS)
+    x_a = synthetic.query_grid(NS, na_total)[lo:hi]
+    t0 = time.perf_counter()
+    ev = bq.expected_Z_var(x_a)
+    return time.perf_counter() - t0, float(ev.sum())
+
+
+def reference_pass(cores, pts_per_core):
+    """One bounded sample of the C2 workload on the reference's own CPU implementation: `cores`
+    forked processes each score a contiguous slice of the 10^6 grid (the reference itself is single
+    threaded; this is the most favourable multi-core use of it)."""
+    import multiprocessing as mp
+    starts = np.linspace(0, NA - pts_per_core, cores).astype(np.int64)
+    jobs = [(int(s), int(s) + pts_per_core, NA) for s in starts]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    inner = max(r[0] for r in res)      # slowest worker's scoring time (excludes import/setup)
+    return cores * pts_per_core / inner, inner, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import build_ref
+    kind = "reference" if build_ref.built() else "port"
+    cores = os.cpu_count() or 1
+    pts = 1500
+    if kind == "port":
+        raise SystemExit("oracle/_ref is not built; run oracle/build_ref.py where /root/reference exists")
+    for _ in range(min(args.warmup, 1)):
+        reference_pass(cores, 200)
+    vals, times = [], []
+    for _ in range(args.steps):
+        v, inner, _ = reference_pass(cores, pts)
+        vals.append(v)
+        times.append(inner)
+    v = float(np.mean(vals))
+    sample = "%d forked processes x %d contiguous points of the 10^6 grid (ns=64), OPENBLAS_NUM_THREADS=1" % (cores, pts)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: 1-D BQ, ns=64, expected_Z_var over a 10^6-point grid (bounded sample per step)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ CUDA arm
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from bayesian_quadrature_b200 import synthetic, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    bq = build_problem()
+    bq.device = local
+    nc = bq.nc
+    na_total = NA * world
+    grid = synthetic.query_grid(NS, na_total)
+    shard = grid[rank * NA:(rank + 1) * NA]
+
+    # ---- setup (amortised, timed separately)
+    t0 = time.perf_counter()
+    model = bq._device_model()
+    torch.cuda.synchronize()
+    setup_ms_first = (time.perf_counter() - t0) * 1e3
+    batch = model.batch
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    bq._invalidate_device()
+    model = bq._device_model()
+    batch = model.batch
+    ev1.record()
+    torch.cuda.synchronize()
+    setup_ms = ev0.elapsed_time(ev1)
+
+    x_d = torch.from_numpy(shard).to(dev)
+    esm = torch.empty(1, NA, dtype=torch.float64, device=dev)
+    em = torch.empty(1, NA, dtype=torch.float64, device=dev)
+    st = torch.empty(1, NA, dtype=torch.int32, device=dev)
+    evv = torch.empty(NA, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
+    pair = torch.empty(2, dtype=torch.float64, device=dev)
+    pairs = torch.empty(world, 2, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        batch.score_device(x_d, esm, em, st)                       # esm, em, status for the shard
+        batch.expected_var_device(0, esm, evv)                     # bq.py:374-377
+        mn, idx = batch.argmin_device(evv)                         # local (min, first index); syncs
+        if world > 1:
+            pair[0] = mn
+            pair[1] = float(idx + rank * NA)
+            dist.all_gather_into_tensor(pairs.view(-1), pair)
+            p = pairs.cpu().numpy()
+            order = np.lexsort((p[:, 1], p[:, 0]))
+            mn, idx = float(p[order[0], 0]), int(p[order[0], 1])
+        return mn, idx
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    # ---- kernel-only timing of the dominant kernel (CUDA events on the launching stream)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    for _ in range(max(args.steps, 5)):
+        flush.zero_()
+        k0.record()
+        batch.score_device(x_d, esm, em, st)
+        k1.record()
+        torch.cuda.synchronize()
+        kern_ms.append(k0.elapsed_time(k1))
+    kern_ms_avg = float(np.mean(kern_ms))
+
+    # ---- timed region: exactly K steps, L2 flushed between steps (outside the per-step events)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = batch.launch_count
+    step_ms = []
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    result = None
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0.record()
+        result = step()
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+    barrier()
+    launches = batch.launch_count - launches0
+    total_ms = float(np.sum(step_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = na_total / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public host API: numpy in (pinned), numpy out
+    x_pin = torch.from_numpy(shard).pin_memory()
+    x_host = x_pin.numpy()
+    for _ in range(2):
+        bq.expected_Z_var(x_host)
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev_host = bq.expected_Z_var(x_host)
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+    t = torch.tensor([float(np.sum(e2e_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = na_total / (float(t.item()) / args.steps * 1e-3)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peak, peak_src = fp64_peak_tflops()
+        wf = w_flop(NS, nc)
+        achieved = wf * NA / (kern_ms_avg * 1e-3) * 1e-12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2: 1-D BQ, ns=%d nc=%d, expected_Z_var over a 10^6-point grid per GPU (%d points total)"
+                                   % (NS, nc, na_total),
+                       "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "x_a sharded, %d rank(s)" % world},
+            "roofline": {"bound": "fp64", "kernel": "bq_score_kernel<16,2,8,2>", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "flop_per_eval": wf, "exp_per_eval": w_exp(NS, nc), "kernel_ms": kern_ms_avg,
+                         "hbm_bytes_per_eval": 28, "hbm_gbs": 28 * NA / (kern_ms_avg * 1e-3) * 1e-9},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * NA, "d2h_bytes_per_step": bq._last_d2h_bytes},
+            "gpu_launches": int(launches), "setup_ms": setup_ms, "setup_ms_first_call": setup_ms_first,
+            "clocks": clocks, "argmin": {"min": result[0], "index": result[1]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import build_ref
+            if build_ref.built():
+                cores = os.cpu_count() or 1
+                v, inner, wall = reference_pass(cores, 1500)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": "%d forked processes x 1500 contiguous points of the 10^6 grid, %.1f s" % (cores, wall)}
+            else:
+                line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define BQB_EINVAL (-1)        /* bad argument (reference: ValueError) */
-#define BQB_EUNSUPPORTED (-2)  /* outside device limits: ns > 128 (this round), nc > 16, not sm_100 */
+#define BQB_EUNSUPPORTED (-2)  /* outside device limits: ns > 256, nc > 16, not sm_100 */
 #define BQB_ESTATE (-3)        /* batch not set up */
 #define BQB_ENUMERIC (-4)      /* an instance failed setup (reference: numpy.linalg.LinAlgError) */
 
@@ -54,7 +54,7 @@ const char *bqb_last_error(void);
 int bqb_version(void);
 int bqb_device_count(int *count);
 
-/* Padded observation capacity the library would use for `ns` observations (16, 64 or 128), or
+/* Padded observation capacity the library would use for `ns` observations (16, 64, 128 or 256), or
  * BQB_EUNSUPPORTED. */
 int bqb_ns_capacity(int ns);
 
@@ -92,10 +92,12 @@ int bqb_batch_info(bqb_batch *b, double *Z_mean, double *Z_var, double *log_lh, 
  *   x_a        query points: shared by all instances (xa_stride = 0) or one row per instance
  *   esm, em    outputs [n_inst][out_stride] (em may be NULL): expected squared mean / expected mean
  *   status     per-point BQB_ST_* bits [n_inst][out_stride] (may be NULL)
+ *   d_flags    [n_inst] OR of all status bits of an instance (may be NULL): lets the caller skip
+ *              the status vector unless something other than BQB_ST_OK happened
  * _device: DEVICE pointers, asynchronous on `stream`.  _host: HOST pointers (out_stride = na);
  * copies in, scores, copies out and synchronises. */
 int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int na, double *d_esm,
-                     double *d_em, int *d_status, long long out_stride, void *stream);
+                     double *d_em, int *d_status, long long out_stride, int *d_flags, void *stream);
 int bqb_score_host(bqb_batch *b, const double *x_a, long long xa_stride, int na, double *esm, double *em,
                    int *status);
 
@@ -103,6 +105,10 @@ int bqb_score_host(bqb_batch *b, const double *x_a, long long xa_stride, int na,
  * DEVICE pointers. */
 int bqb_expected_var_device(bqb_batch *b, int inst, const double *d_esm, long long na, double *d_out,
                             void *stream);
+
+/* BQ.expected_Z_var(x_a) (bq.py:354-377) end to end for instance `inst`: HOST x_a in, HOST
+ * out[p] = Z_mean^2 + Z_var - esm[p]; *flags_out = OR of the points' status bits.  Synchronous. */
+int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, double *out, int *flags_out);
 
 /* loss[p] = mean over instances, in instance order, of -esm[i][p]: the marginal loss of
  * BQ.choose_next (bq.py:660-662: values[0].mean(axis=0)).  DEVICE pointers. */

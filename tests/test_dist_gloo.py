@@ -1,0 +1,73 @@
+"""world_size-2 gloo tests (CPU) of the multi-rank host logic: sharding, score all-gather, the
+(min, first index) exchange of choose_next and the C4 loss all-reduce."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from bayesian_quadrature_b200 import dist as bqdist
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 10 ** 6, 10 ** 7 + 3):
+        for W in (1, 2, 3, 8):
+            b = [bqdist.shard_bounds(n, W, r) for r in range(W)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(W - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_combine_argmin_ties_and_nan():
+    assert bqdist.combine_argmin([[1.0, 5], [0.5, 9], [0.5, 7]]) == (0.5, 7)
+    assert bqdist.combine_argmin([[np.nan, 0], [2.0, 3]]) == (2.0, 3)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(0)
+        full = rs.standard_normal(n)
+        full[[n // 3, n // 3 + 4]] = full.min() - 1.0           # a tie that spans positions, first one must win
+        lo, hi = bqdist.shard_bounds(n, world, rank)
+        local = torch.from_numpy(full[lo:hi].copy())
+        gathered = bqdist.all_gather_scores(local, n)
+        ok_gather = bool((gathered.numpy() == full).all())
+        mn, idx = bqdist.all_argmin(float(local.min()), int(local.argmin()), lo)
+        ok_argmin = (idx == int(np.argmin(full))) and (mn == full.min())
+        part = torch.from_numpy(full[lo:hi].copy()).sum().reshape(1)
+        loss = bqdist.all_reduce_loss(part, n)
+        ok_loss = abs(float(loss) - full.mean()) < 1e-12
+        q.put((rank, ok_gather, ok_argmin, ok_loss))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [11, 1001])
+def test_two_rank_gloo(n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, g, a, l in res:
+        assert g and a and l, (rank, g, a, l)

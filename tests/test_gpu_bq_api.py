@@ -1,0 +1,165 @@
+"""GPU tests of the drop-in BQ class: the reference's own behavioural tests for the scoring path
+(bayesian_quadrature/tests/test_bq_object.py:94-176, :286-300, :361-411, :413-555, :631-681),
+restated on this package's BQ, plus fixture parity through the public API."""
+import pickle
+
+import numpy as np
+import pytest
+import scipy.stats
+
+from conftest import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def make_bq(n=9, x=None, nc=None, init=True):
+    # the reference fixture (tests/util.py:12-59)
+    from bayesian_quadrature_b200 import BQ, GaussianKernel
+    if x is None:
+        x = np.linspace(-5, 5, n)
+    y = scipy.stats.norm.pdf(x, 0, 1)
+    opt = dict(n_candidate=10 if nc is None else nc, x_mean=0.0, x_var=10.0, candidate_thresh=0.5,
+               kernel=GaussianKernel, optim_method="L-BFGS-B")
+    np.random.seed(8728)
+    bq = BQ(x, y, **opt)
+    if init:
+        bq.init(params_tl=(15, 2, 0), params_l=(0.2, 1.3, 0))
+    return bq
+
+
+def test_fixture_through_public_api():
+    g = load_golden("fixture")
+    bq = make_bq()
+    assert_close(bq.x_c, g["x_c"], "x_c (same RNG draw as the reference)", rtol=0, atol=0)
+    assert_close(bq.l_c, g["l_c"], "l_c")
+    assert bq.nc == 2 and bq.nsc == 11 and bq.initialized
+    # the seven-digit notebook goldens through the API (visual-tests.ipynb:640, :694)
+    assert abs(bq.Z_mean() - 0.119771005796) < 5e-12 * 0.12
+    assert abs(bq.Z_var() - 5.98039315292e-07) < 1e-14
+    r = bq.expected_squared_mean_and_mean(g["x_a"])
+    assert r.shape == (g["x_a"].size, 2)
+    assert_close(r[:, 0], g["esm"], "esm")
+    assert_close(r[:, 1], g["em"], "em")
+    assert (bq.expected_squared_mean(g["x_a"]) == r[:, 0]).all()
+    assert (bq.expected_mean(g["x_a"]) == r[:, 1]).all()
+    assert_close(bq.expected_Z_var(g["x_a"]), g["expected_Z_var"], "expected_Z_var", atol=1e-12)
+    esm1, em1 = bq._esm_and_em(g["x_a"][[17]])
+    assert esm1 == r[17, 0] and em1 == r[17, 1]
+
+
+@pytest.mark.parametrize("name,ns", [("c1", 8), ("c2", 64), ("c5", 128)])
+def test_synthetic_configs_through_public_api(name, ns):
+    from bayesian_quadrature_b200 import BQ, GaussianKernel, synthetic
+    g = load_golden(name)
+    bq = synthetic.make_bq(BQ, GaussianKernel, ns)
+    assert_close(bq.x_c, g["x_c"], "x_c", rtol=0, atol=0)
+    assert_close(bq.expected_Z_var(g["x_a"]), g["expected_Z_var"], name + " expected_Z_var", atol=1e-12)
+    assert_close(bq.expected_squared_mean(g["x_a"]), g["esm"], name + " esm")
+
+
+def test_expected_Z_var_close_to_Z_var_at_observations():
+    # reference test_expected_Z_var_close (test_bq_object.py:145-151)
+    bq = make_bq()
+    assert np.allclose(bq.expected_Z_var(bq.x_s), bq.Z_var(), atol=1e-4)
+
+
+def test_expected_squared_mean_valid_and_params():
+    # reference tests :153-170
+    bq = make_bq()
+    assert (bq.expected_squared_mean(np.linspace(-10, 10, 20)) >= 0).all()
+    for bad in (np.nan, np.inf, -np.inf):
+        with pytest.raises(ValueError):
+            bq.expected_squared_mean(np.array([bad]))
+        with pytest.raises(ValueError):
+            bq.expected_Z_var(np.array([0.1, bad]))
+
+
+def test_expected_squared_mean_single_observation():
+    # reference test_expected_squared_mean_1 (test_bq_object.py:286-300)
+    X = np.array([0.0])
+    for eps in (0.0, 1e-10, 1e-8):
+        bq = make_bq(x=X, nc=0)
+        m2 = bq.Z_mean() ** 2
+        assert bq.nc == 0
+        assert np.allclose(bq.expected_squared_mean(X + eps), m2, atol=1e-12)
+
+
+def test_add_observation_and_reinit():
+    # reference test_add_observation (test_bq_object.py:361-411)
+    bq = make_bq()
+    x_a, l_a = 20.0, 1e-4
+    ns = bq.ns
+    bq.add_observation(x_a, l_a)
+    assert bq.ns == ns + 1 and bq.x_s[-1] == x_a and bq.l_s[-1] == l_a and bq.tl_s[-1] == np.log(l_a)
+    assert bq.x_sc.shape[0] == bq.nsc == bq.ns + bq.nc
+    assert (bq.gp_log_l.x == bq.x_s).all() and (bq.gp_l.x == bq.x_sc).all() and (bq.gp_l.y == bq.l_sc).all()
+    z1 = bq.Z_mean()
+    bq.add_observation(bq.x_s[0] + 1e-3, bq.l_s[0])           # merges into the nearest observation
+    assert bq.ns == ns + 1
+    assert np.isfinite(bq.expected_Z_var(np.linspace(-8, 25, 50))).all() and np.isfinite(z1)
+
+
+def test_pickle_and_copy_round_trip():
+    # reference tests :413-555: state keys, and results survive pickling / copying
+    bq = make_bq()
+    state = bq.__getstate__()
+    assert sorted(state) == sorted(["x_s", "l_s", "tl_s", "options", "initialized", "gp_log_l", "gp_log_l_jitter",
+                                    "gp_l", "gp_l_jitter", "_approx_x", "_approx_px"])
+    x_a = np.linspace(-9, 9, 33)
+    want = bq.expected_Z_var(x_a)
+    for other in (pickle.loads(pickle.dumps(bq)), bq.copy(deep=True), bq.copy(deep=False)):
+        assert other.nc == bq.nc and (other.x_c == bq.x_c).all()
+        assert (other.expected_Z_var(x_a) == want).all()
+    un = make_bq(init=False)
+    st = un.__getstate__()
+    assert sorted(st) == ["initialized", "l_s", "options", "tl_s", "x_s"]
+    assert pickle.loads(pickle.dumps(un)).gp_l is None
+
+
+def test_set_params_changes_results_and_restores():
+    bq = make_bq()
+    x_a = np.linspace(-9, 9, 21)
+    base = bq.expected_squared_mean(x_a)
+    l_c0 = bq.l_c.copy()
+    bq._set_gp_log_l_params({"h": 14.0, "w": 1.9})
+    bq._set_gp_l_params({"h": 0.25, "w": 1.2})
+    assert not np.allclose(bq.l_c, l_c0) and (bq.gp_l.y[bq.ns:] == bq.l_c).all()
+    assert not np.allclose(bq.expected_squared_mean(x_a), base)
+    bq._set_gp_log_l_params({"h": 15.0, "w": 2.0})
+    bq._set_gp_l_params({"h": 0.2, "w": 1.3})
+    assert_close(bq.expected_squared_mean(x_a), base, "restored esm")
+    with pytest.raises(np.linalg.LinAlgError):
+        bq._set_gp_log_l_params({"h": 1e6})                 # "GP mean is too large" (bq.py:945-947)
+
+
+def test_marginalize_shapes_and_choose_next():
+    # reference tests :631-681
+    bq = make_bq()
+    x_a = np.linspace(-10, 10, 60)
+    np.random.seed(8728)
+    f = lambda: bq.expected_squared_mean(x_a)
+    vals = bq.marginalize([bq.Z_mean, bq.Z_var, f], 4, ["h", "w"])
+    assert vals[0].shape == (4,) and vals[1].shape == (4,) and vals[2].shape == (4, 60)
+    z0 = bq.Z_mean()
+    np.random.seed(8728)
+    nxt = bq.choose_next(x_a, 5, ["h", "w"])
+    assert nxt in x_a
+    assert bq.Z_mean() == z0                                  # state restored after sampling
+    np.random.seed(8728)
+    nxt_det = bq.choose_next(x_a, 5, ["h", "w"], deterministic=True)
+    assert nxt_det in x_a
+    # the batched device path equals the generic host loop on the same hyper-parameter samples
+    np.random.seed(3)
+    htl, hl = bq.sample_hypers(["h", "w"], n=3, nburn=1)
+    loss_d, batch = bq.marginal_loss(x_a, htl, hl, ["h", "w"])
+    batch.close()
+    state = bq.__getstate__()
+    import copy
+    saved = copy.deepcopy(state)
+    rows = []
+    for i in range(3):
+        bq._set_gp_log_l_params(dict(zip(["h", "w"], htl[i])))
+        bq._set_gp_l_params(dict(zip(["h", "w"], hl[i])))
+        rows.append(-bq.expected_squared_mean(x_a))
+    bq.__setstate__(saved)
+    assert_close(loss_d.cpu().numpy(), np.mean(rows, axis=0), "marginal loss")

@@ -1,0 +1,242 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every compute call goes through the
+C-ABI (libbq_b200.so, via the ctypes binding) or the BQ class on top of it.
+
+Checked against: (i) fixtures produced by the unmodified reference (tests/golden/*.npz),
+(ii) the CPU oracle (oracle/bq_oracle.c) on seeded inputs, (iii) size-independent properties at
+BASELINE.json's full sizes.  Tolerance: north_star's rtol 1e-9 / atol 1e-12 in float64 (conftest);
+Z_var is a 6-10 digit cancellation and is judged by atol.
+"""
+import numpy as np
+import pytest
+
+from conftest import ATOL, RTOL, assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from bayesian_quadrature_b200 import _lib
+    _lib.load()
+    assert _lib.device_count() >= 1
+    return _lib
+
+
+def batch_of(lib, g, **kw):
+    ns, nc = g["x_s"].size, g["x_c"].size
+    b = lib.Batch(1, ns)
+    hyp = np.concatenate([g["params_tl"], g["params_l"]])
+    prior = np.array([float(g["x_mean"]), float(g["x_var"]), float(g["candidate_thresh"])])
+    info = b.setup([ns], [nc], g["x_s"][None], g["l_s"][None], g["x_c"][None], hyp[None], prior[None], **kw)
+    assert info["status"][0] == lib.SETUP_OK
+    return b, info
+
+
+@pytest.mark.parametrize("name", ["fixture", "c1", "c2", "c5", "c3"])
+def test_capi_vs_reference_fixture(lib, name):
+    g = load_golden(name)
+    b, info = batch_of(lib, g)
+    nc = g["x_c"].size
+    assert_close(info["l_c"][0, :nc], g["l_c"], name + " l_c")
+    assert_close(info["Z_mean"][0], g["Z_mean"], name + " Z_mean")
+    assert abs(info["Z_var"][0] - float(g["Z_var"])) < 1e-13
+    assert abs(info["log_lh"][0] - float(g["log_lh"])) <= 1e-7 * abs(float(g["log_lh"]))
+    esm, em, st = b.score_host(g["x_a"])
+    assert_close(esm[0], g["esm"], name + " esm")
+    assert_close(em[0], g["em"], name + " em")
+    assert ((st[0] & lib.ST_SHORTCUT) == g["shortcut"]).all()
+    assert not (st[0] & (lib.ST_ESM_BAD | lib.ST_EM_BAD | lib.ST_XA_BAD)).any()
+    ev = info["Z_mean"][0] ** 2 + info["Z_var"][0] - esm[0]
+    assert_close(ev, g["expected_Z_var"], name + " expected_Z_var", atol=max(ATOL, 1e-13))
+    ev2, flags = b.expected_var_host(g["x_a"])
+    assert (ev2 == ev).all()
+    if "grid_idx" in g and g["grid_idx"].size < g["x_a"].size:
+        k = g["grid_idx"].size                       # the dense window around the peak is inside [:k]
+        assert int(np.argmax(esm[0][:k])) == int(np.argmax(g["esm"][:k]))
+    b.close()
+
+
+@pytest.mark.parametrize("ns,seed", [(1, 0), (2, 1), (9, 2), (16, 3), (17, 4), (40, 5), (64, 6), (65, 7), (100, 8), (128, 9), (150, 10), (256, 11)])
+def test_capi_vs_oracle_random(lib, oracle, ns, seed):
+    """Seeded random problems of every capacity class, random + edge query points."""
+    rs = np.random.RandomState(seed)
+    x_s = np.sort(rs.uniform(-0.625 * ns, 0.625 * ns, ns)) if ns > 1 else np.array([0.3])
+    if ns > 1:                                       # keep observations >= 0.6 apart (well conditioned)
+        x_s = np.linspace(x_s.min(), x_s.max() + 0.6 * ns, ns) + rs.uniform(-0.2, 0.2, ns)
+    l_s = np.exp(-0.5 * (x_s / (0.3 * max(np.ptp(x_s), 1.0))) ** 2) * rs.uniform(0.5, 1.5, ns) * 0.3 + 1e-3
+    nc = int(rs.randint(0, 7))
+    x_c = np.sort(rs.uniform(x_s.min() - 2, x_s.max() + 2, nc))
+    if nc:
+        keep = np.ones(nc, bool)
+        for j in range(nc):
+            if (np.abs(x_c[j] - x_s) < 0.5).any() or (j and keep[j - 1] and x_c[j] - x_c[j - 1] < 0.5):
+                keep[j] = False
+        x_c = x_c[keep]
+        nc = x_c.size
+    ptl, pl = (rs.uniform(3, 6), rs.uniform(1.0, 1.6), 0.0), (rs.uniform(0.2, 0.8), rs.uniform(0.8, 1.2), 0.0)
+    mu, var, thresh = float(rs.uniform(-1, 1)), float(max(np.ptp(x_s), 2.0) ** 2 / 4), 0.5
+    m = oracle.OracleModel(x_s, l_s, x_c, ptl, pl, mu, var, thresh)
+    lo, hi = x_s.min() - 6, x_s.max() + 6
+    x_a = np.concatenate([rs.uniform(lo, hi, 3000), x_s, x_s + 1.05e-4, x_s - 0.9e-4, x_c, x_c + 0.49, x_c - 0.5,
+                          x_c + 0.25, [lo - 100, hi + 1e4]])
+    b = lib.Batch(1, ns)
+    info = b.setup([ns], [nc], x_s[None], l_s[None], x_c[None] if nc else np.zeros((1, 0)),
+                   np.array([ptl + pl]), np.array([[mu, var, thresh]]))
+    assert info["status"][0] == 0
+    assert_close(info["Z_mean"][0], m.Z_mean(), "Z_mean")
+    assert abs(info["Z_var"][0] - m.Z_var()) < 1e-12 * max(1.0, abs(m.Z_mean()) ** 2 * 1e3)
+    esm, em, st = b.score_host(x_a)
+    o_esm, o_em, o_st = m.esm_and_em(x_a)
+    assert ((st[0] & 3) == (o_st & 3)).all()
+    assert_close(esm[0], o_esm, "esm ns=%d" % ns)
+    assert_close(em[0], o_em, "em ns=%d" % ns)
+    b.close()
+
+
+def test_hyper_set_batch_vs_reference(lib):
+    """C4 semantics: one instance per hyper-parameter set, shared x_a, marginal loss and argmin."""
+    import torch
+    g = load_golden("c4")
+    H, ns, nc = g["hypers"].shape[0], g["x_s"].size, g["x_c"].size
+    b = lib.Batch(H, ns)
+    hyp = np.zeros((H, 6))
+    hyp[:, 0], hyp[:, 1], hyp[:, 3], hyp[:, 4] = g["hypers"].T
+    prior = np.tile([float(g["x_mean"]), float(g["x_var"]), float(g["candidate_thresh"])], (H, 1))
+    info = b.setup(np.full(H, ns), np.full(H, nc), np.tile(g["x_s"], (H, 1)), np.tile(g["l_s"], (H, 1)),
+                   np.tile(g["x_c"], (H, 1)), hyp, prior, check_max=True)
+    assert (info["status"] == 0).all()
+    assert_close(info["l_c"][:, :nc], g["l_c"], "c4 l_c")
+    assert_close(info["Z_mean"], g["Z_mean"], "c4 Z_mean")
+    esm, em, st = b.score_host(g["x_a"])
+    assert_close(esm, g["esm"], "c4 esm")
+    assert_close(em, g["em"], "c4 em")
+    dev = torch.device("cuda", 0)
+    x_d = torch.from_numpy(g["x_a"]).to(dev)
+    esm_d = torch.empty(H, g["x_a"].size, dtype=torch.float64, device=dev)
+    loss_d = torch.empty(g["x_a"].size, dtype=torch.float64, device=dev)
+    b.score_device(x_d, esm_d)
+    b.mean_neg_device(esm_d, loss_d)
+    torch.cuda.synchronize()
+    assert (esm_d.cpu().numpy() == esm).all()                      # host and device entry points agree bitwise
+    assert_close(loss_d.cpu().numpy(), g["loss"], "c4 loss")
+    mn, idx = b.argmin_device(loss_d)
+    assert idx == int(g["argmin"]) and mn == loss_d.cpu().numpy().min()
+    b.close()
+
+
+def test_independent_problems_batch(lib, oracle):
+    """C5 semantics: instances with different ns / nc / data in one batch, each with its own x_a."""
+    rs = np.random.RandomState(11)
+    B, cap = 6, 40
+    ns = rs.randint(20, cap + 1, B)
+    nc = rs.randint(0, 4, B)
+    x_s, l_s, x_c = np.zeros((B, cap)), np.ones((B, cap)), np.zeros((B, 16))
+    x_a = np.empty((B, 700))
+    models = []
+    for i in range(B):
+        xs = 1.25 * (np.arange(ns[i]) - (ns[i] - 1) / 2.0) + rs.uniform(-0.1, 0.1, ns[i])
+        ls = np.exp(-0.5 * ((xs - rs.uniform(-3, 3)) / 6.0) ** 2) * 0.2 + 1e-4
+        xc = np.sort(rs.choice(xs[:-1], nc[i], replace=False) + 0.625)
+        x_s[i, :ns[i]], l_s[i, :ns[i]], x_c[i, :nc[i]] = xs, ls, xc
+        x_a[i] = rs.uniform(xs.min() - 8, xs.max() + 8, 700)
+        models.append(oracle.OracleModel(xs, ls, xc, (15, 2, 0), (0.2, 1.3, 0), 0.0, 10.0 * (ns[i] / 8.0) ** 2, 0.5))
+    b = lib.Batch(B, cap)
+    hyp = np.tile([15, 2, 0, 0.2, 1.3, 0], (B, 1)).astype(float)
+    prior = np.stack([[0.0, 10.0 * (n / 8.0) ** 2, 0.5] for n in ns])
+    info = b.setup(ns, nc, x_s, l_s, x_c, hyp, prior)
+    assert (info["status"] == 0).all()
+    esm, em, st = b.score_host(x_a)
+    for i in range(B):
+        o_esm, o_em, o_st = models[i].esm_and_em(x_a[i])
+        assert_close(esm[i], o_esm, "problem %d esm" % i)
+        assert_close(em[i], o_em, "problem %d em" % i)
+        assert_close(info["Z_mean"][i], models[i].Z_mean(), "problem %d Z_mean" % i)
+    b.close()
+
+
+def test_status_codes_and_edge_sizes(lib):
+    g = load_golden("fixture")
+    b, info = batch_of(lib, g)
+    Zm = info["Z_mean"][0]
+    x = np.array([np.nan, np.inf, -np.inf, g["x_s"][2], g["x_s"][2] + 1e-8, g["x_s"][2] + 1e-10, 0.3])
+    esm, em, st = b.score_host(x)
+    assert (st[0][:3] == lib.ST_XA_BAD).all() and np.isnan(esm[0][:3]).all()
+    assert (st[0][3:6] == lib.ST_SHORTCUT).all()
+    assert (esm[0][3:6] == Zm * Zm).all() and (em[0][3:6] == Zm).all()      # exactly Z_mean^2 (bq.py:457-459)
+    assert st[0][6] == lib.ST_OK
+    # ragged sizes: empty, 1 point, sizes straddling warp / CTA tiles
+    e0, _, _ = b.score_host(np.empty(0))
+    assert e0.shape == (1, 0)
+    xs = np.linspace(-9, 9, 1000)
+    full, _, _ = b.score_host(xs)
+    for n in (1, 7, 8, 9, 15, 16, 17, 127, 128, 129, 255, 257):
+        part, _, _ = b.score_host(xs[:n])
+        assert (part[0] == full[0][:n]).all()                                 # independent of tiling
+    b.close()
+
+
+def test_setup_failures_are_reported(lib):
+    g = load_golden("fixture")
+    b = lib.Batch(1, 9)
+    hyp = np.array([[1000.0, 2.0, 0, 0.2, 1.3, 0]])
+    prior = np.array([[0.0, 10.0, 0.5]])
+    info = b.setup([9], [2], g["x_s"][None], g["l_s"][None], (g["x_c"] + 40.0)[None], hyp, prior, check_max=True)
+    assert info["status"][0] == lib.SETUP_MEAN_TOO_LARGE                       # bq.py:945-947
+    with pytest.raises(np.linalg.LinAlgError):
+        b.score_host(np.zeros(3))
+    # a numerically singular Gram matrix (length scale >> data range) fails the Cholesky like numpy's would
+    info = b.setup([9], [2], g["x_s"][None], g["l_s"][None], g["x_c"][None], np.array([[15, 1e7, 0, 0.2, 1.3, 0]]), prior)
+    assert info["status"][0] == lib.SETUP_KTL_NOTPD
+    info = b.setup([9], [2], g["x_s"][None], -g["l_s"][None], g["x_c"][None], np.array([[15, 2.0, 0, 0.2, 1.3, 0]]), prior)
+    assert info["status"][0] == lib.SETUP_BAD_INPUT
+    b.close()
+    with pytest.raises(NotImplementedError):
+        lib.Batch(1, 10 ** 4)
+
+
+def test_full_size_properties_c2(lib, oracle):
+    """BASELINE configs[1] at full size (ns=64, 10^6 points): determinism, tiling independence,
+    non-negativity, device argmin == host argmin, and a 4000-point subsample against the oracle."""
+    import torch
+    from bayesian_quadrature_b200 import synthetic
+    g = load_golden("c2")
+    b, info = batch_of(lib, g)
+    grid = synthetic.query_grid(64, 10 ** 6)
+    dev = torch.device("cuda", 0)
+    x_d = torch.from_numpy(grid).to(dev)
+    esm = torch.empty(1, grid.size, dtype=torch.float64, device=dev)
+    em = torch.empty_like(esm)
+    st = torch.empty(1, grid.size, dtype=torch.int32, device=dev)
+    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    b.score_device(x_d, esm, em, st, flags)
+    torch.cuda.synchronize()
+    esm2 = torch.empty_like(esm)
+    b.score_device(x_d, esm2)
+    half = grid.size // 2 + 13
+    esm3 = torch.empty_like(esm)
+    b.score_device(x_d[:half], esm3[:, :half])
+    b.score_device(x_d[half:], esm3[:, half:])
+    torch.cuda.synchronize()
+    assert torch.equal(esm, esm2) and torch.equal(esm, esm3)
+    e = esm[0].cpu().numpy()
+    s = st[0].cpu().numpy()
+    assert (e >= 0).all() and np.isfinite(e).all()
+    assert int(flags.item()) == int(np.bitwise_or.reduce(s))
+    assert not (s & ~(lib.ST_SHORTCUT | lib.ST_NOTPD)).any()
+    # the fixture's grid subset must reproduce the reference at the same grid points
+    k = g["grid_idx"].size
+    assert_close(e[g["grid_idx"]], g["esm"][:k], "c2 full-grid esm at fixture indices")
+    ev = torch.empty(grid.size, dtype=torch.float64, device=dev)
+    b.expected_var_device(0, esm, ev)
+    mn, idx = b.argmin_device(ev)
+    ev_h = ev.cpu().numpy()
+    assert idx == int(np.argmin(ev_h)) and mn == ev_h.min()
+    assert idx == int(g["grid_idx"][int(np.argmax(g["esm"][:k]))])          # same chosen point as the reference
+    sub = np.random.RandomState(5).choice(grid.size, 4000, replace=False)
+    m = oracle.OracleModel(g["x_s"], g["l_s"], g["x_c"], g["params_tl"], g["params_l"], float(g["x_mean"]),
+                           float(g["x_var"]), float(g["candidate_thresh"]))
+    o_esm, o_em, o_st = m.esm_and_em(grid[sub])
+    assert_close(e[sub], o_esm, "c2 subsample esm")
+    assert_close(em[0].cpu().numpy()[sub], o_em, "c2 subsample em")
+    assert ((s[sub] & 3) == (o_st & 3)).all()
+    b.close()
