@@ -34,6 +34,7 @@ struct ScoreArgs {
     const double *exp_tab;
     int *flags;
     int inst0;
+    int ndb_max;
 };
 void launch_setup(const SetupArgs &a, int n_inst, cudaStream_t stream);
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream);
@@ -67,6 +68,7 @@ struct bqb_batch {
     long long *d_red_idx = nullptr;
     std::vector<double> h_hdr;
     bool ready = false;
+    int ndb_max = 1;
     unsigned long long launches = 0;
 };
 
@@ -102,10 +104,11 @@ int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     if (prop.major < 10) { delete b; return fail(BQB_EUNSUPPORTED, "bqb_batch_create: needs an sm_100a device (B200)"); }
     b->sm_count = prop.multiProcessorCount;
     CU(cudaMalloc(&b->d_models, sizeof(double) * (size_t)n_inst * b->lay.total));
-    CU(cudaMalloc(&b->d_tab, sizeof(double) * EXP_TAB));
-    std::vector<double> tab(EXP_TAB);
-    for (int j = 0; j < EXP_TAB; ++j) tab[j] = (double)exp2l((long double)j / EXP_TAB);
-    CU(cudaMemcpy(b->d_tab, tab.data(), sizeof(double) * EXP_TAB, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&b->d_tab, sizeof(double) * (2048 + 512)));
+    std::vector<double> tab(2048 + 512);
+    for (int j = 0; j < 2048; ++j) tab[j] = (double)exp2l((long double)j / 2048);
+    for (int j = 0; j < 512; ++j) tab[2048 + j] = (double)exp2l((long double)j / 512);
+    CU(cudaMemcpy(b->d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
     b->n_cap = cap + NC_MAX;
     b->work_stride = 4 * (size_t)b->n_cap * b->n_cap + 32 * (size_t)b->n_cap;
     b->work_inst = n_inst < 2048 ? n_inst : 2048;
@@ -167,6 +170,8 @@ int bqb_batch_setup(bqb_batch *b, const int *ns, const int *nc, const double *x_
     CU(cudaMemcpy2DAsync(b->h_hdr.data(), sizeof(double) * H_COUNT, b->d_models, sizeof(double) * b->lay.total,
                          sizeof(double) * H_COUNT, B, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    b->ndb_max = 1;
+    for (int i = 0; i < B; ++i) { const int d = (nc[i] + 2 + 7) / 8; if (d > b->ndb_max) b->ndb_max = d; }
     b->ready = true;
     return 0;
 }
@@ -206,7 +211,7 @@ int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int
     ScoreArgs a;
     a.models = b->d_models; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = xa_stride; a.na = na;
     a.esm = d_esm; a.em = d_em; a.status = d_status; a.out_stride = out_stride; a.exp_tab = b->d_tab;
-    a.flags = d_flags;
+    a.flags = d_flags; a.ndb_max = b->ndb_max;
     if (d_flags) CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * b->n_inst, (cudaStream_t)stream));
     // gridDim.y is limited to 65535
     for (int i0 = 0; i0 < b->n_inst; i0 += 32768) {
@@ -274,7 +279,7 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
     ScoreArgs a;
     a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.x_a = b->d_xa; a.xa_stride = 0; a.na = na;
     a.esm = b->d_esm; a.em = nullptr; a.status = nullptr; a.out_stride = na; a.exp_tab = b->d_tab;
-    a.flags = b->d_flags; a.inst0 = 0;
+    a.flags = b->d_flags; a.inst0 = 0; a.ndb_max = b->ndb_max;
     CU(launch_score(a, 1, b->sm_count, s));
     CU(launch_expected_var(b->d_esm, na, h[H_ZM] * h[H_ZM] + h[H_ZV], b->d_em, s));   // bq.py:374-377
     b->launches += 2;

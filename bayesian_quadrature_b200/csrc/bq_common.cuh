@@ -26,14 +26,14 @@ constexpr int SETUP_MEAN_TOO_LARGE = 3;  // bq.py:945-947 "GP mean is too large"
 constexpr int SETUP_BAD_INPUT = 4;    // non-finite / non-positive inputs
 
 constexpr int NC_MAX = 16;            // candidates per instance supported on device
-constexpr int EXP_TAB = 512;          // entries of the 2^(j/512) table
+constexpr int EXP_TAB_MAX = 2048;     // device table: [0, 2048) = 2^(j/2048), [2048, 2560) = 2^(j/512)
 constexpr double MAX_EXPONENT = 707.0101241711442;   // log(2^1020): gauss_c.pyx:16, bq.py:16
 constexpr double EPS = 2.220446049250313e-16;        // np.finfo(float64).eps, bq_c.pyx:28
 
 // ---- header slots of a model block (doubles)
 enum Hdr {
     H_NS = 0, H_NC, H_NSP, H_STATUS, H_CL, H_NHL, H_CTL, H_NHTL, H_KAA_E, H_KAA_N, H_J1, H_KTT, H_MU,
-    H_HL2, H_LB, H_LOGDETB, H_ZM, H_ZV, H_THRESH, H_LOGLH, H_BA_S, H_NDB, H_WL, H_COUNT = 32
+    H_CB, H_NHB, H_ZM, H_ZV, H_THRESH, H_LOGLH, H_BA_S, H_NDB, H_WL, H_COUNT = 32
 };
 
 // Model block layout (offsets in doubles) for an instance capacity of nsp_cap observations
@@ -43,7 +43,7 @@ struct Layout {
     int nsp_cap;     // padded observation capacity (multiple of 8)
     int nb_cap;      // row blocks of 8
     int nks_cap;     // k-steps of 4
-    int off_xs, off_tol, off_atl, off_xc, off_lc, off_s0, off_lcc0, off_wb, off_wa, off_ug0, off_ua0;
+    int off_xs, off_tol, off_atl, off_xc, off_lc, off_s0, off_lcc0, off_wb, off_wa, off_ug0, off_ua0, off_rd0;
     int off_af_l_tri, off_af_l_dense, off_af_tl_tri;
     int n_small;     // doubles before the fragment arrays (header + vectors + small matrices)
     int total;       // doubles per instance (multiple of 32)
@@ -68,6 +68,7 @@ __host__ __device__ inline Layout make_layout(int nsp_cap) {
     L.off_wa = o; o += NC_MAX;
     L.off_ug0 = o; o += NC_MAX;
     L.off_ua0 = o; o += NC_MAX;
+    L.off_rd0 = o; o += NC_MAX;                         // 1 / diag(L_cc)
     o = (o + 31) & ~31;
     L.n_small = o;
     L.off_af_l_tri = o; o += tri_frags(L.nb_cap) * 32;
@@ -86,28 +87,78 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// exp(x) for x <= 0 (kernel exponents are -(d^2)/(2 w^2)), ~1 ulp: x = (512 e + j) ln2/512 + r,
-// exp(x) = 2^e * T[j] * (1 + expm1(r)), |r| <= ln2/1024, Taylor degree 4 (remainder < 2e-18).
-// 9 FP64-pipe operations instead of libm's ~21; results below 2^-1021 flush to zero.
-__device__ __forceinline__ double exp_neg(double x, const double *__restrict__ tab) {
-    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52
-    const double INV = 0x1.71547652b82fep+9;             // 512 / ln 2
-    const double HI = 0x1.62e42fef00000p-10;             // ln2/512, top 33 bits
-    const double LO = 0x1.473de6af278edp-43;
-    double t = fma(x, INV, MAGIC);
-    int ki = __double2loint(t);
-    double kf = t - MAGIC;
-    double r = fma(kf, -HI, x);
-    r = fma(kf, -LO, r);
-    double q = fma(r, 1.0 / 24.0, 1.0 / 6.0);
-    q = fma(q, r, 0.5);
-    double p = fma(q, r * r, r);
-    double T = tab[ki & (EXP_TAB - 1)];
+// ---- table-driven FP64 exp.  T[j] = 2^(j/N) lives in shared memory (N = 2048 or 512).
+//
+// DMMA and DFMA share one FP64 datapath on B200 (profiles/fp64_mix_r01.json), so every FP64 instruction
+// spent on the cross-kernel exponentials is taken from the GEMM.  libm's exp costs ~21 FP64-pipe
+// operations; exp_kernel below costs 7 (N = 2048) or 8 (N = 512).
+template <int N> struct ExpC;
+template <> struct ExpC<2048> {
+    static constexpr int SHIFT = 11;
+    static constexpr double INVN = 0x1.71547652b82fep+11;          // N / ln 2
+    static constexpr double HI = 0x1.62e42fec00000p-12;            // ln2 / N, top 31 bits
+    static constexpr double LO = 0x1.d1cf79abc9e3bp-43;
+    static constexpr long long T_MIN = 0x4337ffffffe015b0LL;       // bits(1.5 * 2^52 - 4 * 522900): arg >= -708
+};
+template <> struct ExpC<512> {
+    static constexpr int SHIFT = 9;
+    static constexpr double INVN = 0x1.71547652b82fep+9;
+    static constexpr double HI = 0x1.62e42fef00000p-10;            // top 33 bits
+    static constexpr double LO = 0x1.473de6af278edp-43;
+    static constexpr long long T_MIN = 0x4337fffffff8056cLL;       // bits(1.5 * 2^52 - 522900)
+};
+constexpr double EXP_MAGIC = 6755399441055744.0;                   // 1.5 * 2^52
+
+// exp(d2 * nh) for d2 >= 0, nh < 0, given C = nh * N / ln 2 (rounded once).  The argument is reduced in
+// *table units*: u = d2 * C, k = rint(u), r = u - k computed by ONE fma (exact product, |r| <= 1/2), so no
+// hi/lo split of ln 2 is needed; exp(r ln2 / N) - 1 is a degree-3 (N = 2048, fitted, 0.05 ulp) or degree-4
+// (N = 512, Taylor, 0.01 ulp) polynomial in r.  Total error ~1 ulp + |arg| * 1.6e-16 (the rounding of d2
+// and of C, i.e. a 1e-16 relative perturbation of the length scale w).
+// d2 is clamped to d2max (<= 700 / |nh|) with ONE integer min on its high word (non-negative doubles order
+// like their bit patterns), so far-away points give ~1e-304 instead of an exact 0 and the result is always a
+// normal number; it also maps d2 = +inf to a finite value.  All of this keeps work off the FP64 pipe, which a
+// warp instruction occupies for 2 issue cycles (DSETP / DMNMX would cost as much as a DFMA).
+template <int N>
+__device__ __forceinline__ double exp_kernel(double d2, double C, int d2max_hi, const double *__restrict__ tab) {
+    d2 = __hiloint2double(min(__double2hiint(d2), d2max_hi), __double2loint(d2));
+    const double t = fma(d2, C, EXP_MAGIC);
+    const int ki = __double2loint(t);
+    const double kf = t - EXP_MAGIC;
+    const double r = fma(d2, C, -kf);
+    double q;
+    if (N == 2048) {
+        q = fma(0x1.c6b08d79d8fa9p-38, r, 0x1.ebfbe00896926p-25);
+        q = fma(q, r, 0x1.62e42fefa39efp-12);
+    } else {
+        q = fma(0x1.3b2ab6fba4e77p-43, r, 0x1.c6b08d704a0c0p-32);
+        q = fma(q, r, 0x1.ebfbdff82c58fp-21);
+        q = fma(q, r, 0x1.62e42fefa39efp-10);
+    }
+    const double T = tab[ki & (N - 1)];
+    const double y = fma(T * r, q, T);
+    // scale by 2^(k >> log2 N): add to the exponent field; (ki & ~(N-1)) << (20 - log2 N) == (ki >> log2 N) << 20
+    return __hiloint2double(__double2hiint(y) + ((ki & ~(N - 1)) << (20 - ExpC<N>::SHIFT)), __double2loint(y));
+}
+
+// high word of the largest d2 the kernel exponent may see: 700 / |nh| (exp(-700) ~ 1e-304)
+__device__ __forceinline__ int exp_d2max_hi(double nh) { return __double2hiint(700.0 / fabs(nh)); }
+
+// exp(x) for any finite x <= 709 (used a few times per point in the tail, where the argument can be large
+// and positive): classic Cody-Waite reduction with a hi/lo split of ln2/N so that large |x| keeps full
+// relative accuracy; Taylor degree 3 (N = 2048, 0.31 ulp) or 4 (N = 512).
+template <int N>
+__device__ __forceinline__ double exp_tab(double x, const double *__restrict__ tab) {
+    const double t = fma(x, ExpC<N>::INVN, EXP_MAGIC);
+    const int ki = __double2loint(t);
+    const double kf = t - EXP_MAGIC;
+    double r = fma(kf, -ExpC<N>::HI, x);
+    r = fma(kf, -ExpC<N>::LO, r);
+    double q = (N == 2048) ? fma(r, 1.0 / 6.0, 0.5) : fma(fma(r, 1.0 / 24.0, 1.0 / 6.0), r, 0.5);
+    const double p = fma(q, r * r, r);
+    const double T = tab[ki & (N - 1)];
     double y = fma(T, p, T);
-    int hi = __double2hiint(y) + ((ki >> 9) << 20);
-    y = __hiloint2double(hi, __double2loint(y));
-    // x < -708 (including -inf): below the normal range -> 0.  Integer compare on the high word.
-    return ((unsigned)__double2hiint(x) > 0xC0862000u) ? 0.0 : y;
+    y = __hiloint2double(__double2hiint(y) + ((ki >> ExpC<N>::SHIFT) << 20), __double2loint(y));
+    return (x < -708.0) ? 0.0 : y;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -18,10 +18,14 @@
 //     of the CTA consuming a chunk in lock-step (STREAM);
 //   * only v.v is needed from the triangular part: accumulators are squared and summed in
 //     registers, one block of 8 rows at a time, and no n x n (or n x T) intermediate is stored;
-//   * the candidate block (nc <= 16 rows) and the scalar algebra run per point in a warp tail.
+//   * a warp works on a super-tile of 32 points (32 / (8 NT) sub-tiles); per-point partial results
+//     (v_s.v_s, v_t.v_t, tm, the candidate rows) are parked in a small shared-memory scratch and the
+//     candidate block (nc <= 16) plus the scalar algebra then run with one point per lane.
 //
 // Grid: persistent CTAs (a multiple of the SM count) striding over point tiles; gridDim.y = model
 // instances (hyper-parameter sets or independent problems).
+#include <cstdlib>
+
 #include "bq_common.cuh"
 
 namespace bqb {
@@ -38,6 +42,7 @@ struct ScoreArgs {
     const double *exp_tab;    // [EXP_TAB]
     int *flags;               // [B] OR of every point's status bits (may be null)
     int inst0;
+    int ndb_max;              // dense row blocks to reserve scratch for: ceil((max nc + 2) / 8)
 };
 
 constexpr int CHUNK_FRAGS = 128;   // STREAM: fragments (256 B each) per staged chunk
@@ -59,17 +64,18 @@ __host__ __device__ constexpr int chunk_end_rb(int rb, int nb_cap) {   // one pa
     return r + 1;
 }
 
-template <int KS, int NT, int WARPS, bool STREAM>
+
+constexpr int SCR_STRIDE = 40;     // doubles per scratch row: 32 points + 8 pad (conflict-free 16 B fragment stores)
+
+template <int KS, int NT, int WARPS, bool STREAM, int TABN>
 struct ScoreSmem {
     static constexpr int NBC = KS / 2;
     static constexpr int TRI = NBC * (NBC + 1) * 32;       // doubles per triangular operand
     static constexpr int DENSE = 3 * KS * 32;
     static constexpr int OPERANDS = STREAM ? CHUNK_FRAGS * 32 : 2 * TRI + DENSE;
-    static constexpr int SCR_D = NT * 24 * 8;              // dense-row outputs of one warp
-    static constexpr int SCR_V = NT * 8 * 4;               // qs, qt, tm, flag
-    static constexpr int SCR = SCR_D + SCR_V;
-    static __host__ __device__ constexpr int doubles(int n_small) {
-        return EXP_TAB + n_small + OPERANDS + WARPS * SCR;
+    static __host__ __device__ constexpr int scr(int ndb_max) { return (4 + 8 * ndb_max) * SCR_STRIDE; }
+    static __host__ __device__ constexpr int doubles(int n_small, int ndb_max) {
+        return TABN + n_small + OPERANDS + WARPS * scr(ndb_max);
     }
 };
 
@@ -81,10 +87,44 @@ __device__ __forceinline__ void stage(double *dst, const double *__restrict__ sr
     for (int i = threadIdx.x; i < count / 2; i += THREADS) d2[i] = __ldg(s2 + i);
 }
 
+// Cross-kernel B fragments of one sub-tile: bf[ks][nt] = exp(-(x - x_s[k])^2 / (2 w^2)), k = 4 ks + (lane & 3).
+// Groups of 4 k-steps are branch free so that the 4 NT independent exp chains interleave.  TL additionally
+// accumulates gp_log_l.mean (bq.py:493) and evaluates np.isclose(x_a, x_s, atol=1e-4) (bq.py:456) with an
+// integer compare of |d| against the precomputed tolerance (non-negative doubles order like their bits).
+template <int KS, int NT, int TABN, bool TL>
+__device__ __forceinline__ void gen_fragments(double (&bf)[KS][NT], const double (&x)[NT], double C, int d2max_hi, int nks, int kq,
+                                              const double *s_xs, const double *s_tol, const double *s_atl,
+                                              const double *s_tab, double (&tm)[NT], int (&close)[NT]) {
+#pragma unroll
+    for (int g = 0; g < (KS + 3) / 4; ++g) {
+        if (4 * g < nks) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ks = 4 * g + j;
+                if (ks < KS) {
+                    const int k = 4 * ks + kq;
+                    const double xs = s_xs[k];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const double d = x[nt] - xs;
+                        const double e = exp_kernel<TABN>(d * d, C, d2max_hi, s_tab);
+                        bf[ks][nt] = e;
+                        if (TL) {
+                            close[nt] |= ((__double_as_longlong(d) & 0x7fffffffffffffffLL) <= __double_as_longlong(s_tol[k]));
+                            tm[nt] = fma(s_atl[k], e, tm[nt]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Lower-triangular pass: q += (rows of (A . B))^2, A in fragment order (resident in smem or staged from gmem)
-template <int KS, int NT, int WARPS, bool STREAM>
+template <int KS, int NT, int WARPS, bool STREAM, bool ALIGN>
 __device__ __forceinline__ void tri_pass(const double *af_res, const double *__restrict__ af_gmem, double *s_chunk,
                                          const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT], int nb, int lane) {
+    if (ALIGN) __syncthreads();                                 // all warps of the CTA enter the DMMA phase together
 #pragma unroll
     for (int rb = 0; rb < KS / 2; ++rb) {
         if (rb < nb) {
@@ -102,7 +142,10 @@ __device__ __forceinline__ void tri_pass(const double *af_res, const double *__r
             } else {
                 af = af_res + tri_frags(rb) * 32 + lane;
             }
-            double c0[NT], c1[NT], e0[NT], e1[NT];              // two independent accumulator chains
+            // NT >= 2 gives >= 2 independent DMMA chains per warp, enough to cover the 26-cycle DMMA latency at
+            // one issue per 16 cycles; NT == 1 splits even / odd k-steps into two chains instead.
+            constexpr bool DUAL = (NT == 1);
+            double c0[NT], c1[NT], e0[NT], e1[NT];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
 #pragma unroll
@@ -111,12 +154,13 @@ __device__ __forceinline__ void tri_pass(const double *af_res, const double *__r
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
-                    dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);
+                    if (DUAL) dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);
+                    else dmma(c0[nt], c1[nt], a1, bf[ks + 1][nt]);
                 }
             }
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const double r0 = c0[nt] + e0[nt], r1 = c1[nt] + e1[nt];
+                const double r0 = DUAL ? c0[nt] + e0[nt] : c0[nt], r1 = DUAL ? c1[nt] + e1[nt] : c1[nt];
                 q0[nt] = fma(r0, r0, q0[nt]);
                 q1[nt] = fma(r1, r1, q1[nt]);
             }
@@ -124,14 +168,30 @@ __device__ __forceinline__ void tri_pass(const double *af_res, const double *__r
     }
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM>
+// Sum the 8 row slots of the squared accumulators (lanes with equal lane & 3) and park them in scratch row `row`
+template <int NT>
+__device__ __forceinline__ void park_q(double (&q0)[NT], double (&q1)[NT], double *scr, int row, int col0, int kq, int pq) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            q0[nt] += __shfl_xor_sync(0xffffffffu, q0[nt], o);
+            q1[nt] += __shfl_xor_sync(0xffffffffu, q1[nt], o);
+        }
+        if (pq == 0) *reinterpret_cast<double2 *>(scr + row * SCR_STRIDE + col0 + nt * 8 + 2 * kq) = make_double2(q0[nt], q1[nt]);
+    }
+}
+
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN>
 __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a) {
-    using SM = ScoreSmem<KS, NT, WARPS, STREAM>;
+    using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
+    constexpr bool LOCKSTEP = STREAM || ALIGN;              // warps must keep reaching the CTA barriers
     constexpr int THREADS = WARPS * 32;
+    constexpr int SUB = 4 / NT;                             // sub-tiles of 8 NT points per 32-point super-tile
     extern __shared__ __align__(16) double smem[];
     const Layout lay = a.lay;
     double *s_tab = smem;
-    double *s_small = s_tab + EXP_TAB;
+    double *s_small = s_tab + TABN;
     double *s_ops = s_small + lay.n_small;                  // resident operands, or the staging chunk
     double *s_af_l = s_ops;
     double *s_af_d = s_af_l + SM::TRI;
@@ -142,7 +202,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     const int inst = a.inst0 + blockIdx.y;
     const double *M = a.models + (size_t)inst * lay.total;
 
-    for (int i = tid; i < EXP_TAB; i += THREADS) s_tab[i] = a.exp_tab[i];
+    for (int i = tid; i < TABN; i += THREADS) s_tab[i] = a.exp_tab[(TABN == 2048 ? 0 : 2048) + i];
     for (int i = tid; i < lay.n_small; i += THREADS) s_small[i] = M[i];
     __syncthreads();
     const int nc = (int)s_small[H_NC], nsp = (int)s_small[H_NSP], ndb = (int)s_small[H_NDB];
@@ -155,9 +215,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     }
 
     const double *s_xs = s_small + lay.off_xs, *s_tol = s_small + lay.off_tol, *s_atl = s_small + lay.off_atl;
-    const double nhl = s_small[H_NHL], nhtl = s_small[H_NHTL];
-    double *scr_d = s_scr + warp * SM::SCR;
-    double *scr_v = scr_d + SM::SCR_D;
+    const double nhl = s_small[H_NHL];
+    const double Cl = nhl * ExpC<TABN>::INVN, Ctl = s_small[H_NHTL] * ExpC<TABN>::INVN;   // exponent scale in table units
+    const int dmax_l = exp_d2max_hi(nhl), dmax_tl = exp_d2max_hi(s_small[H_NHTL]);
+    double *scr = s_scr + warp * SM::scr(a.ndb_max);        // rows: 0 qs, 1 qt, 2 tm, 3 isclose, 4.. dense rows
 
     const double *xa = a.x_a + (size_t)inst * a.xa_stride;
     double *o_esm = a.esm + (size_t)inst * a.out_stride;
@@ -165,250 +226,210 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     int *o_st = a.status ? a.status + (size_t)inst * a.out_stride : nullptr;
 
     const int kq = lane & 3, pq = lane >> 2;
-    const int tile_pts = WARPS * 8 * NT;
-    const int ntiles = (a.na + tile_pts - 1) / tile_pts;
+    const int nsuper = (a.na + WARPS * 32 - 1) / (WARPS * 32);
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int base = tile * tile_pts + warp * 8 * NT;
-        if (!STREAM && base >= a.na) continue;       // warp-uniform; STREAM warps must keep hitting the barriers
-        double x[NT];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int p = base + nt * 8 + pq;
-            double v = (p < a.na) ? xa[p] : 0.0;
-            x[nt] = isfinite(v) ? v : 0.0;           // invalid x_a is reported by the tail (ST_XA_BAD)
-        }
-        double bf[KS][NT];
-        double q0[NT], q1[NT];
+    for (int st_i = blockIdx.x; st_i < nsuper; st_i += gridDim.x) {
+        const int base = (st_i * WARPS + warp) * 32;
+        if (!LOCKSTEP && base >= a.na) continue;     // warp-uniform; lock-step warps must keep hitting the barriers
 
-        // ================= phase L: K_l cross-kernel fragments, triangular + dense rows
+#pragma unroll 1
+        for (int sub = 0; sub < SUB; ++sub) {
+            const int col0 = sub * 8 * NT;
+            double x[NT];
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            if (ks < nks) {
-                const double xs = s_xs[4 * ks + kq];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const double d = x[nt] - xs;
-                    bf[ks][nt] = exp_neg((d * d) * nhl, s_tab);
-                }
+            for (int nt = 0; nt < NT; ++nt) {
+                const int p = base + col0 + nt * 8 + pq;
+                double v = (p < a.na) ? xa[p] : 0.0;
+                x[nt] = isfinite(v) ? v : 0.0;       // invalid x_a is reported by the tail (ST_XA_BAD)
             }
-        }
+            double bf[KS][NT];
+            double q0[NT], q1[NT], tm[NT];
+            int close[NT];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) { q0[nt] = 0.0; q1[nt] = 0.0; }
-        tri_pass<KS, NT, WARPS, STREAM>(s_af_l, M + lay.off_af_l_tri, s_ops, bf, q0, q1, nb, lane);
+            for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = tm[nt] = 0.0; close[nt] = 0; }
+
+            // ---- phase L: K_l cross-kernel fragments, triangular rows then the dense candidate / g rows
+            if (ALIGN) __syncthreads();                  // ... and the exp phase together (DMMA / DFMA mixing costs pipe throughput)
+            gen_fragments<KS, NT, TABN, false>(bf, x, Cl, dmax_l, nks, kq, s_xs, s_tol, s_atl, s_tab, tm, close);
+            tri_pass<KS, NT, WARPS, STREAM, ALIGN>(s_af_l, M + lay.off_af_l_tri, s_ops, bf, q0, q1, nb, lane);
 #pragma unroll
-        for (int db = 0; db < 3; ++db) {
-            if (db < ndb) {
-                const double *af;
-                if constexpr (STREAM) {
-                    __syncthreads();
-                    stage<THREADS>(s_ops, M + lay.off_af_l_dense + (db * nks) * 32, nks * 32);
-                    __syncthreads();
-                    af = s_ops + lane;
-                } else {
-                    af = s_af_d + (db * nks) * 32 + lane;
-                }
-                double c0[NT], c1[NT], e0[NT], e1[NT];
+            for (int db = 0; db < 3; ++db) {
+                if (db < ndb) {
+                    const double *af;
+                    if constexpr (STREAM) {
+                        __syncthreads();
+                        stage<THREADS>(s_ops, M + lay.off_af_l_dense + (db * nks) * 32, nks * 32);
+                        __syncthreads();
+                        af = s_ops + lane;
+                    } else {
+                        af = s_af_d + (db * nks) * 32 + lane;
+                    }
+                    double c0[NT], c1[NT], e0[NT], e1[NT];
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
+                    for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
 #pragma unroll
-                for (int ks = 0; ks < KS; ks += 2) {
-                    if (ks < nks) {                  // nks is even
-                        const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
+                    for (int ks = 0; ks < KS; ks += 2) {
+                        if (ks < nks) {                  // nks is even
+                            const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
 #pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) {
-                            dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
-                            dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);
+                            for (int nt = 0; nt < NT; ++nt) {
+                                dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
+                                dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);     // 2 chains: the dense rows are few
+                            }
                         }
                     }
-                }
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    double *d = scr_d + (nt * 24 + db * 8 + pq) * 8 + 2 * kq;
-                    d[0] = c0[nt] + e0[nt];
-                    d[1] = c1[nt] + e1[nt];
+                    for (int nt = 0; nt < NT; ++nt)
+                        *reinterpret_cast<double2 *>(scr + (4 + db * 8 + pq) * SCR_STRIDE + col0 + nt * 8 + 2 * kq) =
+                            make_double2(c0[nt] + e0[nt], c1[nt] + e1[nt]);
                 }
             }
-        }
-        // v_s . v_s : sum the 8 row slots (lanes with equal l & 3)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                q0[nt] += __shfl_xor_sync(0xffffffffu, q0[nt], o);
-                q1[nt] += __shfl_xor_sync(0xffffffffu, q1[nt], o);
-            }
-            if (pq == 0) { scr_v[nt * 32 + 2 * kq] = q0[nt]; scr_v[nt * 32 + 2 * kq + 1] = q1[nt]; }
-        }
+            park_q<NT>(q0, q1, scr, 0, col0, kq, pq);
 
-        // ================= phase TL: K_tl fragments; also gp_log_l.mean (tm) and the isclose test
-        double tm[NT];
-        int close[NT];
+            // ---- phase TL: K_tl fragments, gp_log_l.mean and the isclose test
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) { tm[nt] = 0.0; close[nt] = 0; }
+            for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
+            if (ALIGN) __syncthreads();
+            gen_fragments<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, nks, kq, s_xs, s_tol, s_atl, s_tab, tm, close);
+            tri_pass<KS, NT, WARPS, STREAM, ALIGN>(s_af_t, M + lay.off_af_tl_tri, s_ops, bf, q0, q1, nb, lane);
+            park_q<NT>(q0, q1, scr, 1, col0, kq, pq);
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            if (ks < nks) {
-                const int k = 4 * ks + kq;
-                const double xs = s_xs[k], tol = s_tol[k], at = s_atl[k];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const double d = x[nt] - xs;
-                    close[nt] |= (fabs(d) <= tol);            // np.isclose(x_a, x_s, atol=1e-4)  bq.py:456
-                    const double e = exp_neg((d * d) * nhtl, s_tab);
-                    bf[ks][nt] = e;
-                    tm[nt] = fma(at, e, tm[nt]);              // gp_log_l.mean(x_a)                bq.py:493
+            for (int nt = 0; nt < NT; ++nt) {
+                tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 1);
+                tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 2);
+                close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 1);
+                close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 2);
+                if (kq == 0) {
+                    scr[2 * SCR_STRIDE + col0 + nt * 8 + pq] = tm[nt];
+                    scr[3 * SCR_STRIDE + col0 + nt * 8 + pq] = close[nt] ? 1.0 : 0.0;
                 }
             }
-        }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) { q0[nt] = 0.0; q1[nt] = 0.0; }
-        tri_pass<KS, NT, WARPS, STREAM>(s_af_t, M + lay.off_af_tl_tri, s_ops, bf, q0, q1, nb, lane);
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                q0[nt] += __shfl_xor_sync(0xffffffffu, q0[nt], o);
-                q1[nt] += __shfl_xor_sync(0xffffffffu, q1[nt], o);
-            }
-            tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 1);
-            tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 2);
-            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 1);
-            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 2);
-            if (pq == 0) { scr_v[nt * 32 + 8 + 2 * kq] = q0[nt]; scr_v[nt * 32 + 8 + 2 * kq + 1] = q1[nt]; }
-            if (kq == 0) { scr_v[nt * 32 + 16 + pq] = tm[nt]; scr_v[nt * 32 + 24 + pq] = close[nt] ? 1.0 : 0.0; }
         }
         __syncwarp();
 
-        // ================= tail: one lane per point
-        if (lane < 8 * NT) {
-            const int nt = lane >> 3, pn = lane & 7;
-            const int p = base + lane;
-            if (p < a.na) {
-                const double xv = xa[p];
-                const double Zm = s_small[H_ZM];
-                double esm, em;
-                int st = ST_OK;
-                if (!isfinite(xv)) {
-                    esm = em = nan("");
-                    st = ST_XA_BAD;
-                } else if (scr_v[nt * 32 + 24 + pn] != 0.0) {
-                    em = Zm; esm = Zm * Zm; st = ST_SHORTCUT;
-                } else {
-                    const double qs = scr_v[nt * 32 + pn], qt = scr_v[nt * 32 + 8 + pn], tmv = scr_v[nt * 32 + 16 + pn];
-                    const double *dr = scr_d + (nt * 24) * 8 + pn;          // dense row r at dr[r * 8]
-                    const double c_l = s_small[H_CL], w_l = s_small[H_WL], thresh = s_small[H_THRESH];
-                    const double *s_xc = s_small + lay.off_xc;
-                    double w[NC_MAX], v[NC_MAX];
-                    unsigned mask = 0;
-                    for (int j = 0; j < nc; ++j) {
-                        const double dc = s_xc[j] - xv;
-                        if (fabs(dc) < thresh) mask |= 1u << j;             // bq.py:470 (strict <)
-                        w[j] = c_l * exp(-0.5 * (dc * dc) / (w_l * w_l)) + dr[j * 8];
-                    }
-                    double qc = 0, vg = 0, va = 0, bg = 0, kaa;     // bg = u_gamma_c . u_alpha_c of this pattern
-                    bool pd = true;
-                    if (mask == 0) {
-                        const double *Lc = s_small + lay.off_lcc0, *ug = s_small + lay.off_ug0, *ua = s_small + lay.off_ua0;
-                        for (int i = 0; i < nc; ++i) {
-                            double s = w[i];
-                            for (int k = 0; k < i; ++k) s -= Lc[i * NC_MAX + k] * v[k];
-                            s /= Lc[i * NC_MAX + i];
-                            v[i] = s;
-                            qc = fma(s, s, qc); vg = fma(s, ug[i], vg); va = fma(s, ua[i], va);
-                            bg = fma(ug[i], ua[i], bg);
-                        }
-                        kaa = s_small[H_KAA_E];
-                    } else {
-                        // jitter on the close candidates (bq.py:471-473): refactorise the nc x nc Schur block
-                        const double *S0 = s_small + lay.off_s0, *wb = s_small + lay.off_wb, *wa = s_small + lay.off_wa;
-                        const double j1 = s_small[H_J1];
-                        double Lc[NC_MAX * (NC_MAX + 1) / 2], ug[NC_MAX], ua[NC_MAX];
-                        for (int i = 0; i < nc && pd; ++i) {
-                            for (int j = 0; j <= i; ++j) {
-                                double s = S0[i * NC_MAX + j];
-                                if (i == j && ((mask >> i) & 1u)) s += j1;
-                                for (int k = 0; k < j; ++k) s -= Lc[i * (i + 1) / 2 + k] * Lc[j * (j + 1) / 2 + k];
-                                if (i == j) {
-                                    if (!(s > 0.0)) { pd = false; break; }
-                                    Lc[i * (i + 1) / 2 + i] = sqrt(s);
-                                } else {
-                                    Lc[i * (i + 1) / 2 + j] = s / Lc[j * (j + 1) / 2 + j];
-                                }
-                            }
-                        }
-                        if (pd) {
-                            for (int i = 0; i < nc; ++i) {
-                                double s = w[i], sg = wb[i], sa = wa[i];
-                                for (int k = 0; k < i; ++k) {
-                                    const double l = Lc[i * (i + 1) / 2 + k];
-                                    s -= l * v[k]; sg -= l * ug[k]; sa -= l * ua[k];
-                                }
-                                const double d = Lc[i * (i + 1) / 2 + i];
-                                s /= d; sg /= d; sa /= d;
-                                v[i] = s; ug[i] = sg; ua[i] = sa;
-                                qc = fma(s, s, qc); vg = fma(s, sg, vg); va = fma(s, sa, va);
-                                bg = fma(sg, sa, bg);
-                            }
-                        }
-                        kaa = s_small[H_KAA_N];
-                    }
-                    const double s_ = kaa - (qs + qc);                        // Schur pivot of the new point
-                    if (!pd || !(s_ > 0.0)) {
-                        em = Zm; esm = Zm * Zm; st = ST_NOTPD;                // bq.py:481-490
-                    } else {
-                        const double ba = s_small[H_BA_S] + bg;               // int_K(x_sc) . alpha_P
-                        const double kg = dr[nc * 8] + vg;                    // k_a . gamma_P
-                        const double ka = dr[(nc + 1) * 8] + va;              // k_a . alpha_P
-                        // int_K at the new point (gauss_c.pyx:162)
-                        const double Lb = s_small[H_LB];
-                        const double diff = xv - s_small[H_MU];
-                        const double b_a = s_small[H_HL2] *
-                            exp(-0.5 * ((1.8378770664093453 + s_small[H_LOGDETB]) + diff * ((diff / Lb) / Lb)));
-                        const double A_a = (b_a - kg) / s_;                   // last entry of K_sca^-1 int_K (bq_c.pyx:467-469)
-                        const double A_sc_l = ba - A_a * ka;                  // dot(A_sca[:-1], l_sc)       (bq_c.pyx:470)
-                        const double tC = s_small[H_KTT] - qt;                // gp_log_l.cov(x_a)            bq.py:496
-                        const double a1 = tmv + 0.5 * tC;                     // int_exp_norm(1, tm, tC)      gauss_c.pyx:87
-                        const double a2 = 2.0 * tmv + 2.0 * tC;               // int_exp_norm(2, tm, tC)
-                        if (a1 > MAX_EXPONENT) {                              // bq_c.pyx:472-475
-                            esm = em = INFINITY;
-                        } else {
-                            const double e1 = exp(a1);
-                            em = A_sc_l + A_a * e1;                           // bq_c.pyx:477
-                            if (a2 > MAX_EXPONENT) {
-                                esm = INFINITY;                               // bq_c.pyx:479-483
-                            } else {
-                                const double e2 = exp(a2);
-                                esm = (A_sc_l * A_sc_l) + (2 * A_sc_l * A_a * e1) + ((A_a * A_a) * e2);   // bq_c.pyx:485
-                            }
-                        }
-                        if (isnan(esm) || esm < 0) st |= ST_ESM_BAD;          // bq.py:514
-                        if (isnan(em)) st |= ST_EM_BAD;                       // bq.py:518
-                        if (isinf(esm)) st |= ST_ESM_INF;                     // bq.py:522
-                        if (isinf(em)) st |= ST_EM_INF;                       // bq.py:524
-                    }
+        // ================= tail: one lane per point of the super-tile
+        const int p = base + lane;
+        if (p < a.na) {
+            const double xv = xa[p];
+            const double Zm = s_small[H_ZM];
+            double esm, em;
+            int st = ST_OK;
+            if (!isfinite(xv)) {
+                esm = em = nan("");
+                st = ST_XA_BAD;
+            } else if (scr[3 * SCR_STRIDE + lane] != 0.0) {
+                em = Zm; esm = Zm * Zm; st = ST_SHORTCUT;         // bq.py:456-459
+            } else {
+                const double qs = scr[lane], qt = scr[SCR_STRIDE + lane], tmv = scr[2 * SCR_STRIDE + lane];
+                double *dr = scr + 4 * SCR_STRIDE + lane;          // dense row r at dr[r * SCR_STRIDE]; reused for v_c
+                const double c_l = s_small[H_CL], thresh = s_small[H_THRESH];
+                const double *s_xc = s_small + lay.off_xc;
+                unsigned mask = 0;
+                for (int j = 0; j < nc; ++j) {
+                    const double dc = s_xc[j] - xv;
+                    if (fabs(dc) < thresh) mask |= 1u << j;     // bq.py:470 (strict <)
+                    dr[j * SCR_STRIDE] = fma(c_l, exp_kernel<TABN>(dc * dc, Cl, dmax_l, s_tab), dr[j * SCR_STRIDE]);   // w = k_c + W k_s
                 }
-                o_esm[p] = esm;
-                if (o_em) o_em[p] = em;
-                if (o_st) o_st[p] = st;
-                if (st && a.flags) atomicOr(a.flags + inst, st);
+                double qc = 0, vg = 0, va = 0, bg = 0, kaa;     // bg = u_gamma_c . u_alpha_c of this pattern
+                bool pd = true;
+                if (mask == 0) {
+                    const double *Lc = s_small + lay.off_lcc0, *ug = s_small + lay.off_ug0, *ua = s_small + lay.off_ua0,
+                                 *rd = s_small + lay.off_rd0;
+                    for (int i = 0; i < nc; ++i) {
+                        double s = dr[i * SCR_STRIDE];
+                        for (int k = 0; k < i; ++k) s = fma(-Lc[i * NC_MAX + k], dr[k * SCR_STRIDE], s);
+                        s *= rd[i];
+                        dr[i * SCR_STRIDE] = s;
+                        qc = fma(s, s, qc); vg = fma(s, ug[i], vg); va = fma(s, ua[i], va);
+                        bg = fma(ug[i], ua[i], bg);
+                    }
+                    kaa = s_small[H_KAA_E];
+                } else {
+                    // jitter on the close candidates (bq.py:471-473): refactorise the nc x nc Schur block
+                    const double *S0 = s_small + lay.off_s0, *wb = s_small + lay.off_wb, *wa = s_small + lay.off_wa;
+                    const double j1 = s_small[H_J1];
+                    double Lc[NC_MAX * (NC_MAX + 1) / 2], ug[NC_MAX], ua[NC_MAX];
+                    for (int i = 0; i < nc && pd; ++i) {
+                        for (int j = 0; j <= i; ++j) {
+                            double s = S0[i * NC_MAX + j];
+                            if (i == j && ((mask >> i) & 1u)) s += j1;
+                            for (int k = 0; k < j; ++k) s -= Lc[i * (i + 1) / 2 + k] * Lc[j * (j + 1) / 2 + k];
+                            if (i == j) {
+                                if (!(s > 0.0)) { pd = false; break; }
+                                Lc[i * (i + 1) / 2 + i] = sqrt(s);
+                            } else {
+                                Lc[i * (i + 1) / 2 + j] = s / Lc[j * (j + 1) / 2 + j];
+                            }
+                        }
+                    }
+                    if (pd) {
+                        for (int i = 0; i < nc; ++i) {
+                            double s = dr[i * SCR_STRIDE], sg = wb[i], sa = wa[i];
+                            for (int k = 0; k < i; ++k) {
+                                const double l = Lc[i * (i + 1) / 2 + k];
+                                s -= l * dr[k * SCR_STRIDE]; sg -= l * ug[k]; sa -= l * ua[k];
+                            }
+                            const double d = Lc[i * (i + 1) / 2 + i];
+                            s /= d; sg /= d; sa /= d;
+                            dr[i * SCR_STRIDE] = s; ug[i] = sg; ua[i] = sa;
+                            qc = fma(s, s, qc); vg = fma(s, sg, vg); va = fma(s, sa, va);
+                            bg = fma(sg, sa, bg);
+                        }
+                    }
+                    kaa = s_small[H_KAA_N];
+                }
+                const double s_ = kaa - (qs + qc);                        // Schur pivot of the new point
+                if (!pd || !(s_ > 0.0)) {
+                    em = Zm; esm = Zm * Zm; st = ST_NOTPD;                // bq.py:481-490
+                } else {
+                    const double ba = s_small[H_BA_S] + bg;               // int_K(x_sc) . alpha_P
+                    const double kg = dr[nc * SCR_STRIDE] + vg;           // k_a . gamma_P
+                    const double ka = dr[(nc + 1) * SCR_STRIDE] + va;     // k_a . alpha_P
+                    // int_K at the new point (gauss_c.pyx:162): h^2 N(x_a | mu, w_l^2 + sigma^2)
+                    const double diff = xv - s_small[H_MU];
+                    const double b_a = s_small[H_CB] * exp_tab<TABN>((diff * diff) * s_small[H_NHB], s_tab);
+                    const double A_a = (b_a - kg) / s_;                   // last entry of K_sca^-1 int_K (bq_c.pyx:467-469)
+                    const double A_sc_l = ba - A_a * ka;                  // dot(A_sca[:-1], l_sc)       (bq_c.pyx:470)
+                    const double tC = s_small[H_KTT] - qt;                // gp_log_l.cov(x_a)            bq.py:496
+                    const double a1 = tmv + 0.5 * tC;                     // int_exp_norm(1, tm, tC)      gauss_c.pyx:87
+                    const double a2 = 2.0 * tmv + 2.0 * tC;               // int_exp_norm(2, tm, tC)
+                    if (a1 > MAX_EXPONENT) {                              // bq_c.pyx:472-475
+                        esm = em = INFINITY;
+                    } else {
+                        const double e1 = exp_tab<TABN>(a1, s_tab);
+                        em = A_sc_l + A_a * e1;                           // bq_c.pyx:477
+                        if (a2 > MAX_EXPONENT) {
+                            esm = INFINITY;                               // bq_c.pyx:479-483
+                        } else {
+                            const double e2 = exp_tab<TABN>(a2, s_tab);
+                            esm = (A_sc_l * A_sc_l) + (2 * A_sc_l * A_a * e1) + ((A_a * A_a) * e2);   // bq_c.pyx:485
+                        }
+                    }
+                    if (isnan(esm) || esm < 0) st |= ST_ESM_BAD;          // bq.py:514
+                    if (isnan(em)) st |= ST_EM_BAD;                       // bq.py:518
+                    if (isinf(esm)) st |= ST_ESM_INF;                     // bq.py:522
+                    if (isinf(em)) st |= ST_EM_INF;                       // bq.py:524
+                }
             }
+            o_esm[p] = esm;
+            if (o_em) o_em[p] = em;
+            if (o_st) o_st[p] = st;
+            if (st && a.flags) atomicOr(a.flags + inst, st);
         }
         __syncwarp();
     }
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN>
 static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream) {
-    using SM = ScoreSmem<KS, NT, WARPS, STREAM>;
-    const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small);
-    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM>;
+    using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
+    const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small, a.ndb_max);
+    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    const int tile_pts = WARPS * 8 * NT;
-    const int ntiles = (a.na + tile_pts - 1) / tile_pts;
+    const int nsuper = (a.na + WARPS * 32 - 1) / (WARPS * 32);
     int per_inst = (sm_count * MINB + n_inst - 1) / n_inst;      // persistent: ~MINB CTAs per SM in total
-    if (per_inst > ntiles) per_inst = ntiles;
+    if (per_inst > nsuper) per_inst = nsuper;
     if (per_inst < 1) per_inst = 1;
     dim3 grid(per_inst, n_inst);
     kern<<<grid, WARPS * 32, bytes, stream>>>(a);
@@ -418,10 +439,26 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
 // nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 256 (operands streamed)
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream) {
     switch (a.lay.nsp_cap) {
-        case 16: return launch_cfg<4, 2, 8, 2, false>(a, n_inst, sm_count, stream);
-        case 64: return launch_cfg<16, 2, 8, 2, false>(a, n_inst, sm_count, stream);
-        case 128: return launch_cfg<32, 2, 8, 1, false>(a, n_inst, sm_count, stream);
-        case 256: return launch_cfg<64, 1, 8, 1, true>(a, n_inst, sm_count, stream);
+        case 16: return launch_cfg<4, 2, 8, 2, false, 2048, false>(a, n_inst, sm_count, stream);
+        case 64: {
+            // BQB_SCORE_CFG selects an alternative tiling (tuning aid); the default is the measured best
+            static const int cfg = getenv("BQB_SCORE_CFG") ? atoi(getenv("BQB_SCORE_CFG")) : 0;
+            switch (cfg) {
+                case 1: return launch_cfg<16, 2, 8, 2, false, 2048, false>(a, n_inst, sm_count, stream);
+                case 2: return launch_cfg<16, 2, 16, 1, false, 2048, true>(a, n_inst, sm_count, stream);
+                case 3: return launch_cfg<16, 1, 12, 2, false, 2048, true>(a, n_inst, sm_count, stream);
+                default: return launch_cfg<16, 2, 8, 2, false, 2048, true>(a, n_inst, sm_count, stream);
+            }
+        }
+        case 128: {
+            static const int cfg = getenv("BQB_SCORE_CFG") ? atoi(getenv("BQB_SCORE_CFG")) : 0;
+            switch (cfg) {
+                case 1: return launch_cfg<32, 2, 8, 1, false, 512, true>(a, n_inst, sm_count, stream);
+                case 2: return launch_cfg<32, 1, 12, 1, false, 512, true>(a, n_inst, sm_count, stream);
+                default: return launch_cfg<32, 2, 8, 1, false, 512, false>(a, n_inst, sm_count, stream);
+            }
+        }
+        case 256: return launch_cfg<64, 1, 8, 1, true, 2048, false>(a, n_inst, sm_count, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) bq_setup_kernel(SetupArgs a) {
             const double d = Ll[(size_t)(ns + i) * ncap + ns + i];
             M[lay.off_ug0 + i] = s1 / d;
             M[lay.off_ua0 + i] = s2 / d;
+            M[lay.off_rd0 + i] = 1.0 / d;
         }
         // alpha_c = L_cc^-T ua0  (back substitution)
         for (int i = nc - 1; i >= 0; --i) {
@@ -436,11 +437,13 @@ __global__ void __launch_bounds__(SETUP_THREADS) bq_setup_kernel(SetupArgs a) {
         M[H_KAA_E] = c_l + fmax(EPS, c_l) * 1e-4;
         M[H_KAA_N] = c_l + fmax(EPS, c_l + j1) * 1e-4;
         M[H_KTT] = c_tl;
-        M[H_MU] = mu; M[H_HL2] = h_l * h_l; M[H_LB] = Lb; M[H_LOGDETB] = logdet_b; M[H_THRESH] = thresh; M[H_BA_S] = BA_S;
+        M[H_MU] = mu; M[H_THRESH] = thresh; M[H_BA_S] = BA_S;
+        // int_K at a new point: h^2 exp(-1/2 (log 2pi + logdet)) * exp(-1/2 diff^2 / var)  (gauss_c.pyx:110, :162)
+        M[H_CB] = (h_l * h_l) * exp(-0.5 * (LOG_2PI + logdet_b)); M[H_NHB] = -0.5 / var_b;
     }
     for (int i = tid; i < lay.nsp_cap; i += SETUP_THREADS) {
         const bool in = i < ns;
-        M[lay.off_xs + i] = in ? x_s[i] : 1e300;                         // padded: exp(-inf) = 0
+        M[lay.off_xs + i] = in ? x_s[i] : 0.0;                           // padded: finite value x zero operand columns
         M[lay.off_tol + i] = in ? 1e-4 + 1e-5 * fabs(x_s[i]) : -1.0;     // np.isclose(x_a, x_s, atol=1e-4), rtol 1e-5
         M[lay.off_atl + i] = in ? c_tl * a_tl[i] : 0.0;
     }

@@ -294,7 +294,7 @@ def run_cuda(args):
             "config": {"workload": "C2: 1-D BQ, ns=%d nc=%d, expected_Z_var over a 10^6-point grid per GPU (%d points total)"
                                    % (NS, nc, na_total),
                        "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "x_a sharded, %d rank(s)" % world},
-            "roofline": {"bound": "fp64", "kernel": "bq_score_kernel<16,2,8,2>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "fp64", "kernel": "bq_score_kernel<KS=16,NT=2,WARPS=8,MINB=2,STREAM=0,TABN=2048,ALIGN=1>", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "flop_per_eval": wf, "exp_per_eval": w_exp(NS, nc), "kernel_ms": kern_ms_avg,
                          "hbm_bytes_per_eval": 28, "hbm_gbs": 28 * NA / (kern_ms_avg * 1e-3) * 1e-9},
