@@ -158,10 +158,12 @@ class Batch(object):
                                      st.ctypes.data_as(_ip) if want_status else None), "bqb_score_host")
         return esm, em, st
 
-    def expected_var_host(self, x_a, inst=0):
-        """BQ.expected_Z_var for one instance: numpy in, numpy out, plus the OR of the status bits."""
+    def expected_var_host(self, x_a, inst=0, out=None):
+        """BQ.expected_Z_var for one instance: numpy in, numpy out, plus the OR of the status bits.
+        `out` may be a preallocated (ideally page-locked) float64 array."""
         x_a = _d(x_a)
-        out = np.empty(x_a.shape[0])
+        if out is None:
+            out = np.empty(x_a.shape[0])
         fl = ctypes.c_int(0)
         _check(load().bqb_expected_var_host(self._h, int(inst), _pd(x_a), x_a.shape[0], _pd(out), ctypes.byref(fl)),
                "bqb_expected_var_host")

@@ -62,6 +62,32 @@ class _DeviceModel(object):
         self.l_c = np.array(info["l_c"][0, :nc])
 
 
+class _PinnedPool(object):
+    """Page-locked result buffers for the host API.  A device->host copy into pageable memory is
+    staged by the driver at a fraction of PCIe speed, so results are written into pinned arrays;
+    a buffer is handed out again only after the caller has dropped every reference to the array
+    it was given (so two results never alias)."""
+
+    def __init__(self, keep=4):
+        self._bufs, self._keep = [], keep
+
+    def take(self, n):
+        import sys
+        import torch
+        for t, arr in self._bufs:
+            if arr.shape[0] >= n and sys.getrefcount(arr) <= 3:      # only the pool (tuple + loop var) holds it
+                return arr[:n]
+        t = torch.empty(max(n, 1), dtype=torch.float64).pin_memory()
+        arr = t.numpy()
+        self._bufs.append((t, arr))
+        if len(self._bufs) > self._keep:
+            self._bufs.pop(0)
+        return arr[:n]
+
+
+_POOL = _PinnedPool()
+
+
 class BQ(object):
     r"""Bayesian quadrature estimate of :math:`Z = \int \ell(x) N(x | \mu, \sigma^2) dx` with a GP
     over :math:`\log\ell` and a second GP over :math:`\exp(\log\ell)` (reference class docstring,
@@ -272,7 +298,7 @@ class BQ(object):
             warnings.warn("m_Z = %s" % model.Z_mean)
         if model.Z_var <= 0:
             warnings.warn("V_Z = %s" % model.Z_var)
-        ev, flags = model.batch.expected_var_host(x_a)
+        ev, flags = model.batch.expected_var_host(x_a, out=_POOL.take(x_a.shape[0]))
         self._last_d2h_bytes = ev.nbytes + 4
         if flags & ~(_lib.ST_SHORTCUT | _lib.ST_NOTPD):
             self._score(x_a, want_em=True)      # slow path: fetch per-point status, raise / warn like bq.py:514-525

@@ -64,6 +64,8 @@ struct bqb_batch {
     int *d_st = nullptr;
     size_t cap_xa = 0, cap_out = 0;
     int *d_flags = nullptr;
+    cudaStream_t pipe[2] = {nullptr, nullptr};
+    int *h_flags = nullptr;            // pinned
     double *d_red_val = nullptr;
     long long *d_red_idx = nullptr;
     std::vector<double> h_hdr;
@@ -133,6 +135,8 @@ void bqb_batch_destroy(bqb_batch *b) {
     void *ptrs[] = {b->d_models, b->d_tab, b->d_work, b->d_ns, b->d_nc, b->d_xs, b->d_ls, b->d_xc, b->d_hyp, b->d_prior,
                     b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags};
     for (void *p : ptrs) if (p) cudaFree(p);
+    for (cudaStream_t st : b->pipe) if (st) cudaStreamDestroy(st);
+    if (b->h_flags) cudaFreeHost(b->h_flags);
     delete b;
 }
 
@@ -272,22 +276,38 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
     rc = grow(b, (size_t)na, (size_t)b->n_inst * na);
     if (rc) return rc;
     if (!b->d_flags) CU(cudaMalloc(&b->d_flags, sizeof(int) * b->n_inst));
-    cudaStream_t s = 0;
+    if (!b->h_flags) CU(cudaMallocHost(&b->h_flags, sizeof(int)));
+    for (cudaStream_t &st : b->pipe) if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     const double *h = &b->h_hdr[(size_t)inst * H_COUNT];
-    CU(cudaMemcpyAsync(b->d_xa, x_a, sizeof(double) * na, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->n_inst, s));
+    const double msm = h[H_ZM] * h[H_ZM] + h[H_ZV];                                    // bq.py:374
+    // Chunks alternate between two streams so that the H2D copy of one chunk, the kernels of another and the
+    // D2H copy of a third overlap (fully so when the caller's buffers are page-locked).
+    const int min_chunk = 1 << 17;
+    int nchunk = na / min_chunk;
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 8) nchunk = 8;
+    int per = ((na + nchunk - 1) / nchunk + 255) & ~255;
+    CU(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->n_inst, b->pipe[0]));
+    CU(cudaStreamSynchronize(b->pipe[0]));
     ScoreArgs a;
-    a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.x_a = b->d_xa; a.xa_stride = 0; a.na = na;
-    a.esm = b->d_esm; a.em = nullptr; a.status = nullptr; a.out_stride = na; a.exp_tab = b->d_tab;
-    a.flags = b->d_flags; a.inst0 = 0; a.ndb_max = b->ndb_max;
-    CU(launch_score(a, 1, b->sm_count, s));
-    CU(launch_expected_var(b->d_esm, na, h[H_ZM] * h[H_ZM] + h[H_ZV], b->d_em, s));   // bq.py:374-377
-    b->launches += 2;
-    CU(cudaMemcpyAsync(out, b->d_em, sizeof(double) * na, cudaMemcpyDeviceToHost, s));
-    int fl = 0;
-    CU(cudaMemcpyAsync(&fl, b->d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (flags_out) *flags_out = fl;
+    a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.xa_stride = 0;
+    a.em = nullptr; a.status = nullptr; a.exp_tab = b->d_tab; a.flags = b->d_flags; a.inst0 = 0; a.ndb_max = b->ndb_max;
+    int c = 0;
+    for (int lo = 0; lo < na; lo += per, ++c) {
+        const int n = (na - lo < per) ? na - lo : per;
+        cudaStream_t s = b->pipe[c & 1];
+        CU(cudaMemcpyAsync(b->d_xa + lo, x_a + lo, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        a.x_a = b->d_xa + lo; a.na = n; a.esm = b->d_esm + lo; a.out_stride = n;
+        CU(launch_score(a, 1, b->sm_count, s));
+        CU(launch_expected_var(b->d_esm + lo, n, msm, b->d_em + lo, s));
+        b->launches += 2;
+        CU(cudaMemcpyAsync(out + lo, b->d_em + lo, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(b->pipe[0]));
+    CU(cudaStreamSynchronize(b->pipe[1]));
+    CU(cudaMemcpyAsync(b->h_flags, b->d_flags, sizeof(int), cudaMemcpyDeviceToHost, b->pipe[0]));
+    CU(cudaStreamSynchronize(b->pipe[0]));
+    if (flags_out) *flags_out = *b->h_flags;
     return 0;
 }
 

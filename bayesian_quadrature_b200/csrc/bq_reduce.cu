@@ -46,14 +46,16 @@ __global__ void argmin_kernel(const double *__restrict__ v, long long n, double 
     }
 }
 
-__global__ void argmin_final_kernel(double *bv, long long *bi, int nblocks) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double best = bv[0];
-        long long idx = bi[0];
-        for (int b = 1; b < nblocks; ++b) better(best, idx, bv[b], bi[b]);
-        bv[0] = best;
-        bi[0] = idx;
+__global__ void argmin_final_kernel(double *bv, long long *bi, int nblocks) {   // one warp
+    double best = INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    for (int b = threadIdx.x; b < nblocks; b += 32) better(best, idx, bv[b], bi[b]);
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        better(best, idx, v2, i2);
     }
+    if (threadIdx.x == 0) { bv[0] = best; bi[0] = idx; }
 }
 
 cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, long long na, double *loss, cudaStream_t s) {
@@ -70,7 +72,7 @@ cudaError_t launch_expected_var(const double *esm, long long na, double msm, dou
 
 cudaError_t launch_argmin(const double *v, long long n, double *bv, long long *bi, int sm_count, cudaStream_t s) {
     int blocks = (int)((n + 1023) / 1024);
-    if (blocks > sm_count * 4) blocks = sm_count * 4;
+    if (blocks > sm_count * 2) blocks = sm_count * 2;
     if (blocks > 4096) blocks = 4096;
     if (blocks < 1) blocks = 1;
     argmin_kernel<<<blocks, 256, 0, s>>>(v, n, bv, bi);
