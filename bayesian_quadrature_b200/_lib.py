@@ -110,7 +110,10 @@ class Batch(object):
 
     def close(self):
         if getattr(self, "_h", None):
-            load().bqb_batch_destroy(self._h)
+            try:
+                load().bqb_batch_destroy(self._h)
+            except Exception:          # interpreter shutdown: module globals may already be gone
+                pass
             self._h = None
 
     __del__ = close

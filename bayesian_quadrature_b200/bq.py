@@ -249,16 +249,24 @@ class BQ(object):
 
     # ------------------------------------------------------------------ expected variance (the hot path)
     @staticmethod
-    def _check_x_a(x_a):
+    def _check_x_a(x_a, scan=True):
+        """Input validation of bq.py:451-452.  With ``scan=False`` the NaN/inf scan is left to the
+        device (status bit ST_XA_BAD), which costs nothing; the caller then raises the same
+        ValueError from the flags."""
         if x_a is None:
             raise ValueError("invalid value for x_a: %s", x_a)       # bq.py:451-452
         x_a = np.ascontiguousarray(x_a, dtype=DTYPE)
         if x_a.ndim != 1:
             raise ValueError("x_a must be a 1-D array")
+        if scan:
+            BQ._raise_bad_x_a(x_a)
+        return x_a
+
+    @staticmethod
+    def _raise_bad_x_a(x_a):
         bad = ~np.isfinite(x_a)
         if bad.any():
             raise ValueError("invalid value for x_a: %s", x_a[np.argmax(bad)])
-        return x_a
 
     def _report(self, x_a, esm, em, status):
         """The reference's post-checks (bq.py:514-525) on a vector of results."""
@@ -292,7 +300,7 @@ class BQ(object):
     def expected_Z_var(self, x_a):
         r"""E[V(Z) | l_s, l_a] = E[Z|l_s]^2 + V(Z|l_s) - E[ E[Z|l_s,l_a]^2 ] for every point of `x_a`
         (bq.py:354-377).  One fused device pass; only the result vector crosses PCIe."""
-        x_a = self._check_x_a(x_a)
+        x_a = self._check_x_a(x_a, scan=False)
         model = self._device_model()
         if model.Z_mean <= 0:
             warnings.warn("m_Z = %s" % model.Z_mean)
@@ -300,6 +308,8 @@ class BQ(object):
             warnings.warn("V_Z = %s" % model.Z_var)
         ev, flags = model.batch.expected_var_host(x_a, out=_POOL.take(x_a.shape[0]))
         self._last_d2h_bytes = ev.nbytes + 4
+        if flags & _lib.ST_XA_BAD:
+            self._raise_bad_x_a(x_a)            # bq.py:451-452
         if flags & ~(_lib.ST_SHORTCUT | _lib.ST_NOTPD):
             self._score(x_a, want_em=True)      # slow path: fetch per-point status, raise / warn like bq.py:514-525
         return ev

@@ -282,7 +282,7 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
     const double msm = h[H_ZM] * h[H_ZM] + h[H_ZV];                                    // bq.py:374
     // Chunks alternate between two streams so that the H2D copy of one chunk, the kernels of another and the
     // D2H copy of a third overlap (fully so when the caller's buffers are page-locked).
-    const int min_chunk = 1 << 17;
+    static const int min_chunk = getenv("BQB_PIPE_CHUNK") ? atoi(getenv("BQB_PIPE_CHUNK")) : (1 << 18);
     int nchunk = na / min_chunk;
     if (nchunk < 1) nchunk = 1;
     if (nchunk > 8) nchunk = 8;
