@@ -37,6 +37,7 @@ SYMBOLS = {
     "bqb_expected_var_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _ll, _vp, _vp]),
     "bqb_mean_neg_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp]),
     "bqb_argmin_device": (ctypes.c_int, [_vp, _vp, _ll, _dp, ctypes.POINTER(_ll), _vp]),
+    "bqb_argmin_pair_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp]),
     "bqb_launch_count": (ctypes.c_ulonglong, [_vp]),
     "bqb_model_doubles": (ctypes.c_int, [_vp]),
     "bqb_model_read": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
@@ -195,6 +196,11 @@ class Batch(object):
         _check(load().bqb_argmin_device(self._h, _ptr(v), v.numel(), ctypes.byref(mn), ctypes.byref(idx),
                                         _vp(stream) if stream else None), "bqb_argmin_device")
         return mn.value, idx.value
+
+    def argmin_pair_device(self, v, offset, pair, stream=None):
+        """(min, first index + offset) of `v` written to the 2-element float64 CUDA tensor `pair`; no host sync."""
+        _check(load().bqb_argmin_pair_device(self._h, _ptr(v), v.numel(), int(offset), _ptr(pair),
+                                             _vp(stream) if stream else None), "bqb_argmin_pair_device")
 
     @property
     def launch_count(self):

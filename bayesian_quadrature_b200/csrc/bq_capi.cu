@@ -42,6 +42,7 @@ cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, lon
 cudaError_t launch_expected_var(const double *esm, long long na, double msm, double *out, cudaStream_t s);
 cudaError_t launch_argmin(const double *v, long long n, double *scratch_val, long long *scratch_idx, int sm_count,
                           cudaStream_t s);
+cudaError_t launch_argmin_pair(const double *bv, const long long *bi, long long offset, double *pair, cudaStream_t s);
 }  // namespace bqb
 
 using namespace bqb;
@@ -339,6 +340,16 @@ int bqb_argmin_device(bqb_batch *b, const double *d_v, long long n, double *min_
     CU(cudaMemcpyAsync(min_out, b->d_red_val, sizeof(double), cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(idx_out, b->d_red_idx, sizeof(long long), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int bqb_argmin_pair_device(bqb_batch *b, const double *d_v, long long n, long long offset, double *d_pair, void *stream) {
+    if (!b || !d_v || n < 1 || !d_pair) return fail(BQB_EINVAL, "bqb_argmin_pair_device: bad arguments");
+    CU(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(launch_argmin(d_v, n, b->d_red_val, b->d_red_idx, b->sm_count, s));
+    CU(launch_argmin_pair(b->d_red_val, b->d_red_idx, offset, d_pair, s));
+    b->launches += 3;
     return 0;
 }
 

@@ -58,6 +58,11 @@ __global__ void argmin_final_kernel(double *bv, long long *bi, int nblocks) {   
     if (threadIdx.x == 0) { bv[0] = best; bi[0] = idx; }
 }
 
+// (min, global index as a double) pair for the cross-rank exchange: exact for indices < 2^53
+__global__ void argmin_pair_kernel(const double *bv, const long long *bi, long long offset, double *pair) {
+    if (threadIdx.x == 0) { pair[0] = bv[0]; pair[1] = (double)(bi[0] + offset); }
+}
+
 cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, long long na, double *loss, cudaStream_t s) {
     const int blocks = (int)((na + 255) / 256 < 2368 ? (na + 255) / 256 : 2368);
     mean_neg_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(esm, stride, n_inst, na, loss);
@@ -77,6 +82,11 @@ cudaError_t launch_argmin(const double *v, long long n, double *bv, long long *b
     if (blocks < 1) blocks = 1;
     argmin_kernel<<<blocks, 256, 0, s>>>(v, n, bv, bi);
     argmin_final_kernel<<<1, 32, 0, s>>>(bv, bi, blocks);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_argmin_pair(const double *bv, const long long *bi, long long offset, double *pair, cudaStream_t s) {
+    argmin_pair_kernel<<<1, 32, 0, s>>>(bv, bi, offset, pair);
     return cudaGetLastError();
 }
 

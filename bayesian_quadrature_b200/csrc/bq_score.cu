@@ -45,25 +45,14 @@ struct ScoreArgs {
     int ndb_max;              // dense row blocks to reserve scratch for: ceil((max nc + 2) / 8)
 };
 
-constexpr int CHUNK_FRAGS = 128;   // STREAM: fragments (256 B each) per staged chunk
+constexpr int CHUNK_FRAGS = 128;   // STREAM: fragments (256 B each) per staged chunk; two chunk buffers
 
-// First row block of the chunk that contains row block rb (greedy packing of whole row blocks)
-__host__ __device__ constexpr int chunk_start_rb(int rb) {
-    int start = 0, used = 0;
-    for (int r = 0; r <= rb; ++r) {
-        const int f = 2 * r + 2;
-        if (used + f > CHUNK_FRAGS && used > 0) { start = r; used = 0; }
-        used += f;
-    }
-    return start;
+// STREAM: row blocks [rb0, end) whose fragments fit one chunk buffer (always at least one row block)
+__device__ __forceinline__ int chunk_end_rb(int rb0, int nb) {
+    int used = 0, r = rb0;
+    while (r < nb && (r == rb0 || used + 2 * r + 2 <= CHUNK_FRAGS)) { used += 2 * r + 2; ++r; }
+    return r;
 }
-__host__ __device__ constexpr int chunk_end_rb(int rb, int nb_cap) {   // one past the last row block of rb's chunk
-    const int s = chunk_start_rb(rb);
-    int r = rb;
-    while (r + 1 < nb_cap && chunk_start_rb(r + 1) == s) ++r;
-    return r + 1;
-}
-
 
 constexpr int SCR_STRIDE = 40;     // doubles per scratch row: 32 points + 8 pad (conflict-free 16 B fragment stores)
 
@@ -72,7 +61,7 @@ struct ScoreSmem {
     static constexpr int NBC = KS / 2;
     static constexpr int TRI = NBC * (NBC + 1) * 32;       // doubles per triangular operand
     static constexpr int DENSE = 3 * KS * 32;
-    static constexpr int OPERANDS = STREAM ? CHUNK_FRAGS * 32 : 2 * TRI + DENSE;
+    static constexpr int OPERANDS = STREAM ? 2 * CHUNK_FRAGS * 32 : 2 * TRI + DENSE;
     static __host__ __device__ constexpr int scr(int ndb_max) { return (4 + 8 * ndb_max) * SCR_STRIDE; }
     static __host__ __device__ constexpr int doubles(int n_small, int ndb_max) {
         return TABN + n_small + OPERANDS + WARPS * scr(ndb_max);
@@ -120,51 +109,91 @@ __device__ __forceinline__ void gen_fragments(double (&bf)[KS][NT], const double
     }
 }
 
-// Lower-triangular pass: q += (rows of (A . B))^2, A in fragment order (resident in smem or staged from gmem)
-template <int KS, int NT, int WARPS, bool STREAM, bool ALIGN>
-__device__ __forceinline__ void tri_pass(const double *af_res, const double *__restrict__ af_gmem, double *s_chunk,
-                                         const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT], int nb, int lane) {
-    if (ALIGN) __syncthreads();                                 // all warps of the CTA enter the DMMA phase together
+// Asynchronous CTA-wide copy global -> shared (cp.async, 16 B per thread per step); completion is
+// tracked with commit / wait groups so that the copy of the next operand chunk overlaps the DMMAs of this one.
+template <int THREADS>
+__device__ __forceinline__ void stage_async(double *dst, const double *__restrict__ src, int count) {
+    const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+    for (int i = threadIdx.x; i < count / 2; i += THREADS)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u * i), "l"(src + 2 * i) : "memory");
+}
+__device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One block of 8 rows: acc = A(rb, 0 .. lim-1) . B, then q += acc^2.  The k-step loop is unrolled at compile
+// time (B fragments are registers) and leaves early at the row block's diagonal, so the row-block loop
+// around it can stay rolled: the instruction footprint is KS DMMAs, not KS^2/2.
+template <int KS, int NT>
+__device__ __forceinline__ void row_block(const double *af, int lim, const double (&bf)[KS][NT], double (&q0)[NT],
+                                          double (&q1)[NT]) {
+    constexpr bool DUAL = (NT == 1);    // NT == 1: split even / odd k-steps into two chains to cover the DMMA latency
+    double c0[NT], c1[NT], e0[NT], e1[NT];
 #pragma unroll
-    for (int rb = 0; rb < KS / 2; ++rb) {
-        if (rb < nb) {
-            const double *af;
-            if constexpr (STREAM) {
-                const int cs = chunk_start_rb(rb);              // compile-time after unrolling
-                if (cs == rb) {
-                    int ce = chunk_end_rb(rb, KS / 2);
-                    if (ce > nb) ce = nb;
-                    __syncthreads();                            // everyone is done with the previous chunk
-                    stage<WARPS * 32>(s_chunk, af_gmem + tri_frags(cs) * 32, (tri_frags(ce) - tri_frags(cs)) * 32);
-                    __syncthreads();
-                }
-                af = s_chunk + (tri_frags(rb) - tri_frags(cs)) * 32 + lane;
-            } else {
-                af = af_res + tri_frags(rb) * 32 + lane;
-            }
-            // NT >= 2 gives >= 2 independent DMMA chains per warp, enough to cover the 26-cycle DMMA latency at
-            // one issue per 16 cycles; NT == 1 splits even / odd k-steps into two chains instead.
-            constexpr bool DUAL = (NT == 1);
-            double c0[NT], c1[NT], e0[NT], e1[NT];
+    for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
+    for (int ks = 0; ks < KS; ks += 2) {
+        if (ks >= lim) break;
+        const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
 #pragma unroll
-            for (int ks = 0; ks < 2 * rb + 2; ks += 2) {
-                const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
-                    if (DUAL) dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);
-                    else dmma(c0[nt], c1[nt], a1, bf[ks + 1][nt]);
-                }
-            }
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const double r0 = DUAL ? c0[nt] + e0[nt] : c0[nt], r1 = DUAL ? c1[nt] + e1[nt] : c1[nt];
-                q0[nt] = fma(r0, r0, q0[nt]);
-                q1[nt] = fma(r1, r1, q1[nt]);
-            }
+        for (int nt = 0; nt < NT; ++nt) {
+            dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
+            if (DUAL) dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);
+            else dmma(c0[nt], c1[nt], a1, bf[ks + 1][nt]);
         }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const double r0 = DUAL ? c0[nt] + e0[nt] : c0[nt], r1 = DUAL ? c1[nt] + e1[nt] : c1[nt];
+        q0[nt] = fma(r0, r0, q0[nt]);
+        q1[nt] = fma(r1, r1, q1[nt]);
+    }
+}
+
+// Lower-triangular pass with shared-memory resident operands: q += (rows of (A . B))^2.
+// ROLLED = false unrolls the row-block loop as well (exact trip counts, no early-exit branches).
+template <int KS, int NT, bool ALIGN, bool ROLLED>
+__device__ __forceinline__ void tri_pass(const double *af_res, const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT],
+                                         int nb, int lane) {
+    if (ALIGN) __syncthreads();                                 // all warps of the CTA enter the DMMA phase together
+    if constexpr (ROLLED) {
+#pragma unroll 1
+        for (int rb = 0; rb < nb; ++rb) row_block<KS, NT>(af_res + tri_frags(rb) * 32 + lane, 2 * rb + 2, bf, q0, q1);
+    } else {
+#pragma unroll
+        for (int rb = 0; rb < KS / 2; ++rb)        // lim is a compile-time constant after unrolling: the early exit folds away
+            if (rb < nb) row_block<KS, NT>(af_res + tri_frags(rb) * 32 + lane, 2 * rb + 2, bf, q0, q1);
+    }
+}
+
+// Streamed variant (operands do not fit in shared memory): chunks of whole row blocks are copied with
+// cp.async into two alternating buffers; the copy of chunk i+1 is in flight while the CTA's warps run the
+// DMMAs of chunk i.  tri_stream_begin() issues the first chunk early (before the exp phase).
+template <int THREADS>
+__device__ __forceinline__ void tri_stream_begin(const double *__restrict__ af_gmem, double *s_buf, int nb) {
+    const int r1 = chunk_end_rb(0, nb);
+    stage_async<THREADS>(s_buf, af_gmem, tri_frags(r1) * 32);
+    async_commit();
+}
+template <int KS, int NT, int THREADS>
+__device__ __forceinline__ void tri_stream_run(const double *__restrict__ af_gmem, double *s_buf, const double (&bf)[KS][NT],
+                                               double (&q0)[NT], double (&q1)[NT], int nb, int lane) {
+    int rb0 = 0, rb1 = chunk_end_rb(0, nb), cur = 0;
+    while (rb0 < nb) {
+        const int rb2 = (rb1 < nb) ? chunk_end_rb(rb1, nb) : rb1;
+        if (rb1 < nb) {
+            stage_async<THREADS>(s_buf + (cur ^ 1) * CHUNK_FRAGS * 32, af_gmem + tri_frags(rb1) * 32,
+                                 (tri_frags(rb2) - tri_frags(rb1)) * 32);
+            async_commit();
+            async_wait<1>();
+        } else {
+            async_wait<0>();
+        }
+        __syncthreads();                                        // chunk `cur` has landed for every thread
+        const double *base = s_buf + cur * CHUNK_FRAGS * 32 - tri_frags(rb0) * 32 + lane;
+#pragma unroll 1
+        for (int rb = rb0; rb < rb1; ++rb) row_block<KS, NT>(base + tri_frags(rb) * 32, 2 * rb + 2, bf, q0, q1);
+        __syncthreads();                                        // done with `cur` before the next prefetch overwrites it
+        rb0 = rb1; rb1 = rb2; cur ^= 1;
     }
 }
 
@@ -182,7 +211,7 @@ __device__ __forceinline__ void park_q(double (&q0)[NT], double (&q1)[NT], doubl
     }
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED>
 __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a) {
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     constexpr bool LOCKSTEP = STREAM || ALIGN;              // warps must keep reaching the CTA barriers
@@ -250,8 +279,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 
             // ---- phase L: K_l cross-kernel fragments, triangular rows then the dense candidate / g rows
             if (ALIGN) __syncthreads();                  // ... and the exp phase together (DMMA / DFMA mixing costs pipe throughput)
+            if constexpr (STREAM) tri_stream_begin<THREADS>(M + lay.off_af_l_tri, s_ops, nb);
             gen_fragments<KS, NT, TABN, false>(bf, x, Cl, dmax_l, nks, kq, s_xs, s_tol, s_atl, s_tab, tm, close);
-            tri_pass<KS, NT, WARPS, STREAM, ALIGN>(s_af_l, M + lay.off_af_l_tri, s_ops, bf, q0, q1, nb, lane);
+            if constexpr (STREAM) tri_stream_run<KS, NT, THREADS>(M + lay.off_af_l_tri, s_ops, bf, q0, q1, nb, lane);
+            else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_l, bf, q0, q1, nb, lane);
 #pragma unroll
             for (int db = 0; db < 3; ++db) {
                 if (db < ndb) {
@@ -278,6 +309,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                             }
                         }
                     }
+                    if constexpr (STREAM) __syncthreads();       // buffer 0 is reused by the next prefetch
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
                         *reinterpret_cast<double2 *>(scr + (4 + db * 8 + pq) * SCR_STRIDE + col0 + nt * 8 + 2 * kq) =
@@ -290,8 +322,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
             if (ALIGN) __syncthreads();
+            if constexpr (STREAM) tri_stream_begin<THREADS>(M + lay.off_af_tl_tri, s_ops, nb);
             gen_fragments<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, nks, kq, s_xs, s_tol, s_atl, s_tab, tm, close);
-            tri_pass<KS, NT, WARPS, STREAM, ALIGN>(s_af_t, M + lay.off_af_tl_tri, s_ops, bf, q0, q1, nb, lane);
+            if constexpr (STREAM) tri_stream_run<KS, NT, THREADS>(M + lay.off_af_tl_tri, s_ops, bf, q0, q1, nb, lane);
+            else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane);
             park_q<NT>(q0, q1, scr, 1, col0, kq, pq);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
@@ -420,11 +454,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     }
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED>
 static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream) {
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small, a.ndb_max);
-    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN>;
+    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     const int nsuper = (a.na + WARPS * 32 - 1) / (WARPS * 32);
@@ -436,29 +470,27 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
     return cudaGetLastError();
 }
 
-// nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 256 (operands streamed)
+// nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 256 (operands streamed).
+// BQB_SCORE_CFG selects an alternative tiling (tuning aid); the defaults are the measured best.
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream) {
+    static const int cfg = getenv("BQB_SCORE_CFG") ? atoi(getenv("BQB_SCORE_CFG")) : 0;
     switch (a.lay.nsp_cap) {
-        case 16: return launch_cfg<4, 2, 8, 2, false, 2048, false>(a, n_inst, sm_count, stream);
-        case 64: {
-            // BQB_SCORE_CFG selects an alternative tiling (tuning aid); the default is the measured best
-            static const int cfg = getenv("BQB_SCORE_CFG") ? atoi(getenv("BQB_SCORE_CFG")) : 0;
+        case 16: return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream);
+        case 64:
             switch (cfg) {
-                case 1: return launch_cfg<16, 2, 8, 2, false, 2048, false>(a, n_inst, sm_count, stream);
-                case 2: return launch_cfg<16, 2, 16, 1, false, 2048, true>(a, n_inst, sm_count, stream);
-                case 3: return launch_cfg<16, 1, 12, 2, false, 2048, true>(a, n_inst, sm_count, stream);
-                default: return launch_cfg<16, 2, 8, 2, false, 2048, true>(a, n_inst, sm_count, stream);
+                case 1: return launch_cfg<16, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream);
+                case 2: return launch_cfg<16, 2, 8, 2, false, 2048, true, true>(a, n_inst, sm_count, stream);
+                case 3: return launch_cfg<16, 1, 12, 2, false, 2048, true, true>(a, n_inst, sm_count, stream);
+                default: return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream);
             }
-        }
-        case 128: {
-            static const int cfg = getenv("BQB_SCORE_CFG") ? atoi(getenv("BQB_SCORE_CFG")) : 0;
+        case 128:
             switch (cfg) {
-                case 1: return launch_cfg<32, 2, 8, 1, false, 512, true>(a, n_inst, sm_count, stream);
-                case 2: return launch_cfg<32, 1, 12, 1, false, 512, true>(a, n_inst, sm_count, stream);
-                default: return launch_cfg<32, 2, 8, 1, false, 512, false>(a, n_inst, sm_count, stream);
+                case 1: return launch_cfg<32, 2, 8, 1, false, 512, true, false>(a, n_inst, sm_count, stream);
+                case 2: return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream);
+                case 3: return launch_cfg<32, 2, 8, 1, false, 512, true, true>(a, n_inst, sm_count, stream);
+                default: return launch_cfg<32, 2, 8, 1, false, 512, false, false>(a, n_inst, sm_count, stream);
             }
-        }
-        case 256: return launch_cfg<64, 1, 8, 1, true, 2048, false>(a, n_inst, sm_count, stream);
+        case 256: return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream);
         default: return cudaErrorInvalidValue;
     }
 }

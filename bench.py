@@ -161,6 +161,7 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
     from bayesian_quadrature_b200 import synthetic, _lib
+    from bayesian_quadrature_b200 import dist as bqdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,15 +203,12 @@ def run_cuda(args):
     def step():
         batch.score_device(x_d, esm, em, st)                       # esm, em, status for the shard
         batch.expected_var_device(0, esm, evv)                     # bq.py:374-377
-        mn, idx = batch.argmin_device(evv)                         # local (min, first index); syncs
+        batch.argmin_pair_device(evv, rank * NA, pair)             # local (min, first global index), stays on device
         if world > 1:
-            pair[0] = mn
-            pair[1] = float(idx + rank * NA)
-            dist.all_gather_into_tensor(pairs.view(-1), pair)
-            p = pairs.cpu().numpy()
-            order = np.lexsort((p[:, 1], p[:, 0]))
-            mn, idx = float(p[order[0], 0]), int(p[order[0], 1])
-        return mn, idx
+            dist.all_gather_into_tensor(pairs.view(-1), pair)      # the path's only collective: W pairs of 16 B
+            return bqdist.combine_argmin(pairs.cpu().numpy())
+        p = pair.cpu().numpy()                                     # the step's device->host read (16 B)
+        return float(p[0]), int(p[1])
 
     def barrier():
         if world > 1:

@@ -120,6 +120,12 @@ int bqb_mean_neg_device(bqb_batch *b, const double *d_esm, long long stride, lon
 int bqb_argmin_device(bqb_batch *b, const double *d_v, long long n, double *min_out, long long *idx_out,
                       void *stream);
 
+/* Same reduction, left on the device for the cross-rank exchange of sharded runs: d_pair[0] = min,
+ * d_pair[1] = (double)(first index + offset) (exact below 2^53).  Asynchronous on `stream`; the ranks
+ * all-gather their pairs (NCCL has no MINLOC) and reduce them locally. */
+int bqb_argmin_pair_device(bqb_batch *b, const double *d_v, long long n, long long offset, double *d_pair,
+                           void *stream);
+
 /* Introspection for tests and the bench harness. */
 unsigned long long bqb_launch_count(bqb_batch *b);   /* kernels launched through this batch so far */
 int bqb_model_doubles(bqb_batch *b);                  /* size of one device model block */

@@ -231,6 +231,10 @@ def test_full_size_properties_c2(lib, oracle):
     mn, idx = b.argmin_device(ev)
     ev_h = ev.cpu().numpy()
     assert idx == int(np.argmin(ev_h)) and mn == ev_h.min()
+    pair = torch.empty(2, dtype=torch.float64, device=dev)
+    b.argmin_pair_device(ev[1000:], 1000, pair)                   # sharded form: offset = start of the shard
+    pr = pair.cpu().numpy()
+    assert pr[0] == ev_h[1000:].min() and int(pr[1]) == 1000 + int(np.argmin(ev_h[1000:]))
     assert idx == int(g["grid_idx"][int(np.argmax(g["esm"][:k]))])          # same chosen point as the reference
     sub = np.random.RandomState(5).choice(grid.size, 4000, replace=False)
     m = oracle.OracleModel(g["x_s"], g["l_s"], g["x_c"], g["params_tl"], g["params_l"], float(g["x_mean"]),
