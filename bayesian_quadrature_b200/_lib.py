@@ -38,6 +38,7 @@ SYMBOLS = {
     "bqb_mean_neg_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp]),
     "bqb_argmin_device": (ctypes.c_int, [_vp, _vp, _ll, _dp, ctypes.POINTER(_ll), _vp]),
     "bqb_argmin_pair_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp]),
+    "bqb_argmin_rows_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp, _vp]),
     "bqb_launch_count": (ctypes.c_ulonglong, [_vp]),
     "bqb_model_doubles": (ctypes.c_int, [_vp]),
     "bqb_model_read": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
@@ -201,6 +202,11 @@ class Batch(object):
         """(min, first index + offset) of `v` written to the 2-element float64 CUDA tensor `pair`; no host sync."""
         _check(load().bqb_argmin_pair_device(self._h, _ptr(v), v.numel(), int(offset), _ptr(pair),
                                              _vp(stream) if stream else None), "bqb_argmin_pair_device")
+
+    def argmin_rows_device(self, v, mins, idxs, stream=None):
+        """Per-instance (min, first index) of the CUDA tensor v [n_inst, n] into mins (float64) / idxs (int64)."""
+        _check(load().bqb_argmin_rows_device(self._h, _ptr(v), v.stride(0), v.shape[1], _ptr(mins), _ptr(idxs),
+                                             _vp(stream) if stream else None), "bqb_argmin_rows_device")
 
     @property
     def launch_count(self):

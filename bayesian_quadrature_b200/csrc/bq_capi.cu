@@ -42,6 +42,8 @@ cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, lon
 cudaError_t launch_expected_var(const double *esm, long long na, double msm, double *out, cudaStream_t s);
 cudaError_t launch_argmin(const double *v, long long n, double *scratch_val, long long *scratch_idx, int sm_count,
                           cudaStream_t s);
+cudaError_t launch_argmin_rows(const double *v, long long stride, long long n, int rows, double *mins, long long *idxs,
+                               cudaStream_t s);
 cudaError_t launch_argmin_pair(const double *bv, const long long *bi, long long offset, double *pair, cudaStream_t s);
 }  // namespace bqb
 
@@ -350,6 +352,15 @@ int bqb_argmin_pair_device(bqb_batch *b, const double *d_v, long long n, long lo
     CU(launch_argmin(d_v, n, b->d_red_val, b->d_red_idx, b->sm_count, s));
     CU(launch_argmin_pair(b->d_red_val, b->d_red_idx, offset, d_pair, s));
     b->launches += 3;
+    return 0;
+}
+
+int bqb_argmin_rows_device(bqb_batch *b, const double *d_v, long long stride, long long n, double *d_min,
+                           long long *d_idx, void *stream) {
+    if (!b || !d_v || n < 1 || stride < n || !d_min || !d_idx) return fail(BQB_EINVAL, "bqb_argmin_rows_device: bad arguments");
+    CU(cudaSetDevice(b->device));
+    CU(launch_argmin_rows(d_v, stride, n, b->n_inst, d_min, d_idx, (cudaStream_t)stream));
+    b->launches++;
     return 0;
 }
 

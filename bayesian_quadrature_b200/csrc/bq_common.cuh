@@ -33,7 +33,7 @@ constexpr double EPS = 2.220446049250313e-16;        // np.finfo(float64).eps, b
 // ---- header slots of a model block (doubles)
 enum Hdr {
     H_NS = 0, H_NC, H_NSP, H_STATUS, H_CL, H_NHL, H_CTL, H_NHTL, H_KAA_E, H_KAA_N, H_J1, H_KTT, H_MU,
-    H_CB, H_NHB, H_ZM, H_ZV, H_THRESH, H_LOGLH, H_BA_S, H_NDB, H_WL, H_COUNT = 32
+    H_CB, H_NHB, H_ZM, H_ZV, H_THRESH, H_LOGLH, H_BA_S, H_NDB, H_WL, H_TOL2MAX, H_COUNT = 32
 };
 
 // Model block layout (offsets in doubles) for an instance capacity of nsp_cap observations

@@ -63,6 +63,34 @@ __global__ void argmin_pair_kernel(const double *bv, const long long *bi, long l
     if (threadIdx.x == 0) { pair[0] = bv[0]; pair[1] = (double)(bi[0] + offset); }
 }
 
+// One CTA per row: (min, first index) of every instance's score vector (C5: per-problem argmin)
+__global__ void argmin_rows_kernel(const double *__restrict__ v, long long stride, long long n, double *mins, long long *idxs) {
+    __shared__ double sv[32];
+    __shared__ long long si[32];
+    const double *row = v + (size_t)blockIdx.x * stride;
+    double best = INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    for (long long p = threadIdx.x; p < n; p += blockDim.x) better(best, idx, row[p], p);
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        better(best, idx, v2, i2);
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) better(best, idx, sv[w], si[w]);
+        mins[blockIdx.x] = best;
+        idxs[blockIdx.x] = idx;
+    }
+}
+
+cudaError_t launch_argmin_rows(const double *v, long long stride, long long n, int rows, double *mins, long long *idxs,
+                               cudaStream_t s) {
+    argmin_rows_kernel<<<rows, 256, 0, s>>>(v, stride, n, mins, idxs);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, long long na, double *loss, cudaStream_t s) {
     const int blocks = (int)((na + 255) / 256 < 2368 ? (na + 255) / 256 : 2368);
     mean_neg_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(esm, stride, n_inst, na, loss);

@@ -78,11 +78,12 @@ __device__ __forceinline__ void stage(double *dst, const double *__restrict__ sr
 
 // Cross-kernel B fragments of one sub-tile: bf[ks][nt] = exp(-(x - x_s[k])^2 / (2 w^2)), k = 4 ks + (lane & 3).
 // Groups of 4 k-steps are branch free so that the 4 NT independent exp chains interleave.  TL additionally
-// accumulates gp_log_l.mean (bq.py:493) and evaluates np.isclose(x_a, x_s, atol=1e-4) (bq.py:456) with an
-// integer compare of |d| against the precomputed tolerance (non-negative doubles order like their bits).
+// accumulates gp_log_l.mean (bq.py:493) and pre-filters np.isclose(x_a, x_s, atol=1e-4) (bq.py:456): one integer
+// compare of the high word of d^2 against an upper bound of every tolerance^2 (non-negative doubles order like
+// their bits); the exact test runs afterwards only for the rare points that pass (isclose_exact).
 template <int KS, int NT, int TABN, bool TL>
 __device__ __forceinline__ void gen_fragments(double (&bf)[KS][NT], const double (&x)[NT], double C, int d2max_hi, int nks, int kq,
-                                              const double *s_xs, const double *s_tol, const double *s_atl,
+                                              const double *s_xs, const double *s_atl, int tol2_hi,
                                               const double *s_tab, double (&tm)[NT], int (&close)[NT]) {
 #pragma unroll
     for (int g = 0; g < (KS + 3) / 4; ++g) {
@@ -96,10 +97,11 @@ __device__ __forceinline__ void gen_fragments(double (&bf)[KS][NT], const double
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
                         const double d = x[nt] - xs;
-                        const double e = exp_kernel<TABN>(d * d, C, d2max_hi, s_tab);
+                        const double d2 = d * d;
+                        const double e = exp_kernel<TABN>(d2, C, d2max_hi, s_tab);
                         bf[ks][nt] = e;
                         if (TL) {
-                            close[nt] |= ((__double_as_longlong(d) & 0x7fffffffffffffffLL) <= __double_as_longlong(s_tol[k]));
+                            close[nt] |= (__double2hiint(d2) <= tol2_hi);
                             tm[nt] = fma(s_atl[k], e, tm[nt]);
                         }
                     }
@@ -107,6 +109,14 @@ __device__ __forceinline__ void gen_fragments(double (&bf)[KS][NT], const double
             }
         }
     }
+}
+
+// Exact np.isclose(x_a, x_s, atol=1e-4): |x_a - x_s[k]| <= 1e-4 + 1e-5 |x_s[k]| for this lane's k residues (padded
+// entries carry tolerance -1).  Rolled loop: it only runs for points that passed the pre-filter.
+__device__ __forceinline__ int isclose_exact(double x, const double *s_xs, const double *s_tol, int nsp, int kq) {
+    int c = 0;
+    for (int k = kq; k < nsp; k += 4) c |= (fabs(x - s_xs[k]) <= s_tol[k]);
+    return c;
 }
 
 // Asynchronous CTA-wide copy global -> shared (cp.async, 16 B per thread per step); completion is
@@ -247,6 +257,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     const double nhl = s_small[H_NHL];
     const double Cl = nhl * ExpC<TABN>::INVN, Ctl = s_small[H_NHTL] * ExpC<TABN>::INVN;   // exponent scale in table units
     const int dmax_l = exp_d2max_hi(nhl), dmax_tl = exp_d2max_hi(s_small[H_NHTL]);
+    const int tol2_hi = __double2hiint(s_small[H_TOL2MAX]) + 1;
     double *scr = s_scr + warp * SM::scr(a.ndb_max);        // rows: 0 qs, 1 qt, 2 tm, 3 isclose, 4.. dense rows
 
     const double *xa = a.x_a + (size_t)inst * a.xa_stride;
@@ -280,7 +291,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
             // ---- phase L: K_l cross-kernel fragments, triangular rows then the dense candidate / g rows
             if (ALIGN) __syncthreads();                  // ... and the exp phase together (DMMA / DFMA mixing costs pipe throughput)
             if constexpr (STREAM) tri_stream_begin<THREADS>(M + lay.off_af_l_tri, s_ops, nb);
-            gen_fragments<KS, NT, TABN, false>(bf, x, Cl, dmax_l, nks, kq, s_xs, s_tol, s_atl, s_tab, tm, close);
+            gen_fragments<KS, NT, TABN, false>(bf, x, Cl, dmax_l, nks, kq, s_xs, s_atl, tol2_hi, s_tab, tm, close);
             if constexpr (STREAM) tri_stream_run<KS, NT, THREADS>(M + lay.off_af_l_tri, s_ops, bf, q0, q1, nb, lane);
             else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_l, bf, q0, q1, nb, lane);
 #pragma unroll
@@ -323,7 +334,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
             for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
             if (ALIGN) __syncthreads();
             if constexpr (STREAM) tri_stream_begin<THREADS>(M + lay.off_af_tl_tri, s_ops, nb);
-            gen_fragments<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, nks, kq, s_xs, s_tol, s_atl, s_tab, tm, close);
+            gen_fragments<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, nks, kq, s_xs, s_atl, tol2_hi, s_tab, tm, close);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+                if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
             if constexpr (STREAM) tri_stream_run<KS, NT, THREADS>(M + lay.off_af_tl_tri, s_ops, bf, q0, q1, nb, lane);
             else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane);
             park_q<NT>(q0, q1, scr, 1, col0, kq, pq);

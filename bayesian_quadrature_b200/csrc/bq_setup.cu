@@ -437,6 +437,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) bq_setup_kernel(SetupArgs a) {
         M[H_KAA_E] = c_l + fmax(EPS, c_l) * 1e-4;
         M[H_KAA_N] = c_l + fmax(EPS, c_l + j1) * 1e-4;
         M[H_KTT] = c_tl;
+        // isclose pre-filter of the scoring kernel: an upper bound of every tolerance squared
+        double t2 = 0;
+        for (int i = 0; i < ns; ++i) { const double t = 1e-4 + 1e-5 * fabs(x_s[i]); t2 = fmax(t2, t * t); }
+        M[H_TOL2MAX] = t2 * 1.000001;
         M[H_MU] = mu; M[H_THRESH] = thresh; M[H_BA_S] = BA_S;
         // int_K at a new point: h^2 exp(-1/2 (log 2pi + logdet)) * exp(-1/2 diff^2 / var)  (gauss_c.pyx:110, :162)
         M[H_CB] = (h_l * h_l) * exp(-0.5 * (LOG_2PI + logdet_b)); M[H_NHB] = -0.5 / var_b;

@@ -301,8 +301,11 @@ def run_cuda(args):
             if build_ref.built():
                 cores = os.cpu_count() or 1
                 v, inner, wall = reference_pass(cores, 1500)
+                v1, inner1, wall1 = reference_pass(1, 3000)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
-                                        "sample": "%d forked processes x 1500 contiguous points of the 10^6 grid, %.1f s" % (cores, wall)}
+                                        "sample": "%d forked processes x 1500 contiguous points of the 10^6 grid, %.1f s" % (cores, wall),
+                                        "single_process_value": v1,
+                                        "single_process_sample": "1 process, OPENBLAS_NUM_THREADS=1, 3000 points, %.1f s" % wall1}
             else:
                 line["cpu_baseline"] = None
         print(json.dumps(line))

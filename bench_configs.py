@@ -1,0 +1,152 @@
+#!/usr/bin/env python
+"""Device-resident timings of the five BASELINE.json configs on ONE B200 (bench.py carries the
+driver's headline line for configs[1]; this script records the others for DESIGN.md / profiles/).
+
+    python bench_configs.py [c1 c2 c3 c4 c5] > profiles/configs_rNN.jsonl
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from bayesian_quadrature_b200 import BQ, GaussianKernel, _lib, synthetic, util  # noqa: E402
+
+PEAK = 37.156
+
+
+def w_flop(ns, nc):
+    n = ns + nc
+    return n * n + ns * ns + 2 * (3 * n + 2 * ns) + 40
+
+
+def timed(fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(reps):
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.min(ts)), float(np.mean(ts))
+
+
+def single(name, ns, na):
+    dev = torch.device("cuda", 0)
+    bq = synthetic.make_bq(BQ, GaussianKernel, ns)
+    batch = bq._device_model().batch
+    x_d = torch.from_numpy(synthetic.query_grid(ns, na)).to(dev)
+    esm = torch.empty(1, na, dtype=torch.float64, device=dev)
+    ev = torch.empty(na, dtype=torch.float64, device=dev)
+    pair = torch.empty(2, dtype=torch.float64, device=dev)
+
+    def step():
+        batch.score_device(x_d, esm)
+        batch.expected_var_device(0, esm, ev)
+        batch.argmin_pair_device(ev, 0, pair)
+    best, mean = timed(step)
+    kbest, _ = timed(lambda: batch.score_device(x_d, esm))
+    wf = w_flop(ns, bq.nc)
+    p = pair.cpu().numpy()
+    return {"config": name, "ns": ns, "nc": int(bq.nc), "na": na, "step_ms": best, "score_kernel_ms": kbest,
+            "evals_per_s": na / (best * 1e-3), "tflops": wf * na / (kbest * 1e-3) * 1e-12,
+            "frac_fp64_peak": wf * na / (kbest * 1e-3) * 1e-12 / PEAK, "argmin_index": int(p[1])}
+
+
+def c4(n_hyper=1024, na=10 ** 5, ns=64):
+    dev = torch.device("cuda", 0)
+    bq = synthetic.make_bq(BQ, GaussianKernel, ns)
+    hyp4 = synthetic.hyper_sets(n_hyper)
+    hyp = np.zeros((n_hyper, 6))
+    hyp[:, 0], hyp[:, 1], hyp[:, 3], hyp[:, 4] = hyp4.T
+    opt = synthetic.options(ns)
+    prior = np.tile([opt["x_mean"], opt["x_var"], opt["candidate_thresh"]], (n_hyper, 1))
+    batch = _lib.Batch(n_hyper, ns)
+    args = (np.full(n_hyper, ns), np.full(n_hyper, bq.nc), np.tile(bq.x_s, (n_hyper, 1)), np.tile(bq.l_s, (n_hyper, 1)),
+            np.tile(bq.x_c, (n_hyper, 1)), hyp, prior)
+    t0 = time.perf_counter()
+    info = batch.setup(*args, check_max=True)
+    torch.cuda.synchronize()
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    assert (info["status"] == 0).all()
+    x_d = torch.from_numpy(synthetic.query_grid(ns, na)).to(dev)
+    esm = torch.empty(n_hyper, na, dtype=torch.float64, device=dev)
+    loss = torch.empty(na, dtype=torch.float64, device=dev)
+    pair = torch.empty(2, dtype=torch.float64, device=dev)
+
+    def step():
+        batch.score_device(x_d, esm)
+        batch.mean_neg_device(esm, loss)                 # marginal loss, sample order (bq.py:662)
+        batch.argmin_pair_device(loss, 0, pair)
+    best, mean = timed(step, reps=3, warm=1)
+    kbest, _ = timed(lambda: batch.score_device(x_d, esm), reps=3, warm=1)
+    wf = w_flop(ns, bq.nc)
+    n = n_hyper * na
+    p = pair.cpu().numpy()
+    batch.close()
+    return {"config": "C4", "ns": ns, "nc": int(bq.nc), "n_hyper": n_hyper, "na": na, "setup_ms": setup_ms, "step_ms": best,
+            "score_kernel_ms": kbest, "evals_per_s": n / (best * 1e-3), "tflops": wf * n / (kbest * 1e-3) * 1e-12,
+            "frac_fp64_peak": wf * n / (kbest * 1e-3) * 1e-12 / PEAK, "argmin_index": int(p[1])}
+
+
+def c5(n_prob=16384, ns=128, na=4096):
+    dev = torch.device("cuda", 0)
+    opt = synthetic.options(ns)
+    x_s0, _ = synthetic.observations(ns)
+    x_s, l_s, x_c = np.tile(x_s0, (n_prob, 1)), np.empty((n_prob, ns)), np.zeros((n_prob, 16))
+    nc = np.zeros(n_prob, dtype=np.int32)
+    t0 = time.perf_counter()
+    for p in range(n_prob):
+        l_s[p] = synthetic.likelihood(ns, synthetic.problem_shift(p))(x_s0)
+        rs = np.random.RandomState(synthetic.SEED + p)
+        xc = rs.uniform(x_s0.min() - 2.0, x_s0.max() + 2.0, opt["n_candidate"])     # bq.py:974-978, per-problem stream
+        util.filter_candidates(xc, x_s0, opt["candidate_thresh"])
+        xc = np.sort(xc[~np.isnan(xc)])
+        nc[p] = xc.size
+        x_c[p, :xc.size] = xc
+    host_ms = (time.perf_counter() - t0) * 1e3
+    batch = _lib.Batch(n_prob, ns)
+    hyp = np.tile(list(synthetic.PARAMS_TL) + list(synthetic.PARAMS_L), (n_prob, 1))
+    prior = np.tile([opt["x_mean"], opt["x_var"], opt["candidate_thresh"]], (n_prob, 1))
+    t0 = time.perf_counter()
+    info = batch.setup(np.full(n_prob, ns), nc, x_s, l_s, x_c, hyp, prior)
+    torch.cuda.synchronize()
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    assert (info["status"] == 0).all(), np.bincount(info["status"])
+    x_d = torch.from_numpy(synthetic.query_grid(ns, na)).to(dev)
+    esm = torch.empty(n_prob, na, dtype=torch.float64, device=dev)
+    mins = torch.empty(n_prob, dtype=torch.float64, device=dev)
+    idxs = torch.empty(n_prob, dtype=torch.int64, device=dev)
+    neg = torch.empty_like(esm)
+
+    def step():
+        batch.score_device(x_d, esm)
+        torch.neg(esm, out=neg)                          # loss = -esm (bq.py:660); plumbing, not a hot kernel
+        batch.argmin_rows_device(neg, mins, idxs)        # per-problem deterministic choose_next
+    best, mean = timed(step, reps=3, warm=1)
+    kbest, _ = timed(lambda: batch.score_device(x_d, esm), reps=3, warm=1)
+    n = n_prob * na
+    wf = float(np.mean([w_flop(ns, c) for c in nc]))
+    batch.close()
+    return {"config": "C5 (one active-sampling round)", "ns": ns, "nc_mean": float(nc.mean()), "n_problems": n_prob, "na": na,
+            "host_candidate_draw_ms": host_ms, "setup_ms": setup_ms, "step_ms": best, "score_kernel_ms": kbest,
+            "evals_per_s": n / (best * 1e-3), "tflops": wf * n / (kbest * 1e-3) * 1e-12,
+            "frac_fp64_peak": wf * n / (kbest * 1e-3) * 1e-12 / PEAK, "chosen_index_hist_head": np.bincount(idxs.cpu().numpy())[:4].tolist()}
+
+
+if __name__ == "__main__":
+    which = [a.lower() for a in sys.argv[1:]] or ["c1", "c2", "c3", "c4", "c5"]
+    runs = {"c1": lambda: single("C1", 8, 200), "c2": lambda: single("C2", 64, 10 ** 6), "c3": lambda: single("C3", 256, 10 ** 7),
+            "c4": c4, "c5": c5}
+    for k in which:
+        print(json.dumps(runs[k]()), flush=True)

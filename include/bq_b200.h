@@ -126,6 +126,11 @@ int bqb_argmin_device(bqb_batch *b, const double *d_v, long long n, double *min_
 int bqb_argmin_pair_device(bqb_batch *b, const double *d_v, long long n, long long offset, double *d_pair,
                            void *stream);
 
+/* Per-instance (min, first index) of d_v [n_inst][stride] into DEVICE arrays d_min / d_idx [n_inst]: the
+ * deterministic choose_next of a batch of independent problems (bq.py:663 per problem). */
+int bqb_argmin_rows_device(bqb_batch *b, const double *d_v, long long stride, long long n, double *d_min,
+                           long long *d_idx, void *stream);
+
 /* Introspection for tests and the bench harness. */
 unsigned long long bqb_launch_count(bqb_batch *b);   /* kernels launched through this batch so far */
 int bqb_model_doubles(bqb_batch *b);                  /* size of one device model block */

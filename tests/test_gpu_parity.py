@@ -146,8 +146,16 @@ def test_independent_problems_batch(lib, oracle):
     info = b.setup(ns, nc, x_s, l_s, x_c, hyp, prior)
     assert (info["status"] == 0).all()
     esm, em, st = b.score_host(x_a)
+    import torch
+    dev = torch.device("cuda", 0)
+    neg = torch.from_numpy(-esm).to(dev)
+    mins = torch.empty(B, dtype=torch.float64, device=dev)
+    idxs = torch.empty(B, dtype=torch.int64, device=dev)
+    b.argmin_rows_device(neg, mins, idxs)                     # per-problem deterministic choose_next
+    assert (idxs.cpu().numpy() == np.argmin(-esm, axis=1)).all() and (mins.cpu().numpy() == (-esm).min(axis=1)).all()
     for i in range(B):
         o_esm, o_em, o_st = models[i].esm_and_em(x_a[i])
+        assert int(np.argmax(o_esm)) == int(idxs[i])          # same chosen point as the oracle
         assert_close(esm[i], o_esm, "problem %d esm" % i)
         assert_close(em[i], o_em, "problem %d em" % i)
         assert_close(info["Z_mean"][i], models[i].Z_mean(), "problem %d Z_mean" % i)
