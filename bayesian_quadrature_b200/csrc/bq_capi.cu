@@ -114,7 +114,7 @@ int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     for (int j = 0; j < 2048; ++j) tab[j] = (double)exp2l((long double)j / 2048);
     for (int j = 0; j < 512; ++j) tab[2048 + j] = (double)exp2l((long double)j / 512);
     CU(cudaMemcpy(b->d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
-    b->n_cap = cap + NC_MAX;
+    b->n_cap = ((ns_max + 7) & ~7) + NC_MAX;     // leading dimension of the setup scratch matrices
     b->work_stride = 4 * (size_t)b->n_cap * b->n_cap + 32 * (size_t)b->n_cap;
     b->work_inst = n_inst < 2048 ? n_inst : 2048;
     CU(cudaMalloc(&b->d_work, sizeof(double) * b->work_stride * b->work_inst));

@@ -51,37 +51,116 @@ __device__ double block_sum(double v, double *red) {
     return s;
 }
 
-// In-place lower Cholesky of the row-major n x n matrix A (leading dimension ld).  Returns 0, or
-// j+1 when pivot j is not positive (same contract as LAPACK dpotrf's info, linalg_c.pyx:86-91).
-__device__ int chol_lower(double *A, int ld, int n) {
+constexpr int SETUP_NMAX = 256 + NC_MAX;   // largest matrix order (ns <= 256, nc <= 16)
+
+constexpr int CHB = 32;                      // Cholesky panel width
+constexpr int CH_STRIDE = CHB + 1;           // padded panel stride: conflict-free when lanes walk rows
+// dynamic shared memory (doubles) for matrices of order <= ncap: Cholesky block + panel, or 32 staged rows of L
+__host__ __device__ inline int setup_smem_doubles(int ncap) {
+    const int a = (CHB + ncap) * CH_STRIDE, b = CHB * (ncap + 1);
+    return a > b ? a : b;
+}
+
+// In-place lower Cholesky of the row-major n x n matrix A (leading dimension ld, global / L2 memory).
+// Returns 0, or j+1 when pivot j is not positive (same contract as LAPACK dpotrf's info,
+// linalg_c.pyx:86-91).  Blocked right-looking: the 32 x 32 diagonal block is factorised in shared
+// memory, the panel below it is solved one row per thread and kept in shared memory, and the trailing
+// matrix receives ONE rank-32 update per panel (contiguous row accesses) instead of one global
+// read-modify-write pass per column.
+__device__ int chol_lower(double *A, int ld, int n, double *sm) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = SETUP_THREADS / 32;
-    for (int j = 0; j < n; ++j) {
+    double *D = sm;                            // [CHB][CH_STRIDE]
+    double *P = sm + CHB * CH_STRIDE;          // [rows below][CH_STRIDE]
+    __shared__ int s_info;
+    if (tid == 0) s_info = 0;
+    for (int jb = 0; jb < n; jb += CHB) {
+        const int w = (n - jb < CHB) ? n - jb : CHB;
         __syncthreads();
-        const double d = A[(size_t)j * ld + j];
-        if (!(d > 0.0)) return j + 1;
-        const double dj = sqrt(d);
+        for (int e = tid; e < w * w; e += SETUP_THREADS) {
+            const int r = e / w, c = e - r * w;
+            D[r * CH_STRIDE + c] = (c <= r) ? A[(size_t)(jb + r) * ld + jb + c] : 0.0;
+        }
         __syncthreads();
-        for (int i = j + 1 + tid; i < n; i += SETUP_THREADS) A[(size_t)i * ld + j] /= dj;
-        if (tid == 0) A[(size_t)j * ld + j] = dj;
+        // diagonal block, unblocked, one warp (w <= 32): lane r owns row r
+        if (warp == 0) {
+            for (int j = 0; j < w; ++j) {
+                const double d = D[j * CH_STRIDE + j];
+                if (!(d > 0.0)) { if (lane == 0 && s_info == 0) s_info = jb + j + 1; break; }
+                const double dj = sqrt(d);
+                __syncwarp();
+                if (lane == j) D[j * CH_STRIDE + j] = dj;
+                if (lane > j && lane < w) D[lane * CH_STRIDE + j] /= dj;
+                __syncwarp();
+                if (lane > j && lane < w) {
+                    const double lij = D[lane * CH_STRIDE + j];
+                    for (int k = j + 1; k <= lane; ++k) D[lane * CH_STRIDE + k] -= lij * D[k * CH_STRIDE + j];
+                }
+                __syncwarp();
+            }
+        }
         __syncthreads();
-        for (int i = j + 1 + warp; i < n; i += nw) {
-            const double lij = A[(size_t)i * ld + j];
-            for (int k = j + 1 + lane; k <= i; k += 32) A[(size_t)i * ld + k] -= lij * A[(size_t)k * ld + j];
+        if (s_info) return s_info;
+        for (int e = tid; e < w * w; e += SETUP_THREADS) {
+            const int r = e / w, c = e - r * w;
+            if (c <= r) A[(size_t)(jb + r) * ld + jb + c] = D[r * CH_STRIDE + c];
+        }
+        // panel: rows below the block, P[i] = A[i][jb:jb+w] D^-T (forward substitution per row, one thread per row)
+        const int nbelow = n - jb - w;
+        for (int i = tid; i < nbelow; i += SETUP_THREADS) {
+            double *Ai = A + (size_t)(jb + w + i) * ld + jb;
+            double *Pi = P + i * CH_STRIDE;
+            for (int c = 0; c < w; ++c) {
+                double sacc = Ai[c];
+                for (int k = 0; k < c; ++k) sacc -= Pi[k] * D[c * CH_STRIDE + k];
+                sacc /= D[c * CH_STRIDE + c];
+                Pi[c] = sacc;
+                Ai[c] = sacc;
+            }
+        }
+        __syncthreads();
+        // trailing update: A[i][k] -= P[i] . P[k] for jb+w <= k <= i  (warp per row, lanes over k)
+        for (int i = warp; i < nbelow; i += nw) {
+            const double *Pi = P + i * CH_STRIDE;
+            double *Ai = A + (size_t)(jb + w + i) * ld + jb + w;
+            for (int k = lane; k <= i; k += 32) {
+                const double *Pk = P + k * CH_STRIDE;
+                double sacc = 0;
+                for (int c = 0; c < w; ++c) sacc = fma(Pi[c], Pk[c], sacc);
+                Ai[k] -= sacc;
+            }
         }
     }
     __syncthreads();
     return 0;
 }
 
-// X = L^-1 (lower, row-major, both ld); one thread per column, forward substitution.
-__device__ void tri_inverse(const double *L, double *X, int ld, int n) {
-    for (int c = threadIdx.x; c < n; c += SETUP_THREADS) {
-        for (int i = 0; i < c; ++i) X[(size_t)i * ld + c] = 0.0;
-        for (int i = c; i < n; ++i) {
-            double s = (i == c) ? 1.0 : 0.0;
-            const double *Li = L + (size_t)i * ld;
-            for (int k = c; k < i; ++k) s -= Li[k] * X[(size_t)k * ld + c];
-            X[(size_t)i * ld + c] = s / Li[i];
+// X = L^-1 (lower, row-major, both ld): X[i][c] = (delta_ic - sum_{k=c}^{i-1} L[i][k] X[k][c]) / L[i][i].
+// One thread per column c: a column only depends on itself, so rows need no barrier; blocks of 32 rows of L
+// are staged in shared memory (one barrier pair per block) and read as warp broadcasts, X[k][c] is
+// contiguous across the warp.
+__device__ void tri_inverse(const double *L, double *X, int ld, int n, double *sm) {
+    const int tid = threadIdx.x, rs = ld + 1;        // staged row stride (ld = ncap)
+    for (int ib = 0; ib < n; ib += CHB) {
+        const int h = (n - ib < CHB) ? n - ib : CHB, wdt = ib + h;       // rows ib .. ib+h-1, columns 0 .. wdt-1
+        __syncthreads();
+        for (int e = tid; e < h * wdt; e += SETUP_THREADS) {
+            const int r = e / wdt, k = e - r * wdt;
+            sm[r * rs + k] = (k <= ib + r) ? L[(size_t)(ib + r) * ld + k] : 0.0;
+        }
+        __syncthreads();
+        for (int c = tid; c < n; c += SETUP_THREADS) {
+            const int c0 = c & ~31;                     // the warp's first column keeps the k loop warp-uniform
+            for (int r = 0; r < h; ++r) {
+                const int i = ib + r;
+                const double *row = sm + r * rs;
+                double out = 0.0;
+                if (c <= i) {
+                    double sacc = (c == i) ? 1.0 : 0.0;
+                    for (int k = c0; k < i; ++k) sacc = fma(-row[k], X[(size_t)k * ld + c], sacc);   // X is 0 above the diagonal
+                    out = sacc / row[i];
+                }
+                X[(size_t)i * ld + c] = out;
+            }
         }
     }
     __syncthreads();
@@ -119,9 +198,11 @@ __device__ __forceinline__ double mvn_logpdf1(double x, double m, double L, doub
     return -0.5 * ((LOG_2PI + logdet) + diff * buf);
 }
 
-__global__ void __launch_bounds__(SETUP_THREADS) bq_setup_kernel(SetupArgs a) {
+__global__ void __launch_bounds__(SETUP_THREADS, 3) bq_setup_kernel(SetupArgs a) {
     __shared__ double red[SETUP_THREADS / 32];
     __shared__ double sm_small[4 * NC_MAX * NC_MAX];
+    extern __shared__ double s_dyn[];             // setup_smem_doubles(ncap): Cholesky block + panel / row staging of tri_inverse
+    double *s_vec = s_dyn;
     __shared__ int s_fail;
     const int inst = a.inst0 + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = SETUP_THREADS / 32;
@@ -177,9 +258,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) bq_setup_kernel(SetupArgs a) {
         Ltl[(size_t)i * ncap + j] = v;
     }
     // ---- P3: L_tl
-    if (chol_lower(Ltl, ncap, ns)) { if (tid == 0) M[H_STATUS] = SETUP_KTL_NOTPD; return; }
+    if (chol_lower(Ltl, ncap, ns, s_vec)) { if (tid == 0) M[H_STATUS] = SETUP_KTL_NOTPD; return; }
     // ---- P4: L_tl^-1
-    tri_inverse(Ltl, Xtl, ncap, ns);
+    tri_inverse(Ltl, Xtl, ncap, ns, s_vec);
     // ---- P5: a_tl = K_tl^-1 tl_s
     lower_matvec(Xtl, ncap, ns, tl_s, tmp);
     lower_matvec_t(Xtl, ncap, ns, tmp, a_tl);
@@ -223,9 +304,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) bq_setup_kernel(SetupArgs a) {
         const int i = e / nc, j = e - i * nc;
         Kcc[i * NC_MAX + j] = Ll[(size_t)(ns + i) * ncap + ns + j];
     }
-    if (chol_lower(Ll, ncap, n)) { if (tid == 0) M[H_STATUS] = SETUP_KL_NOTPD; return; }
+    if (chol_lower(Ll, ncap, n, s_vec)) { if (tid == 0) M[H_STATUS] = SETUP_KL_NOTPD; return; }
     // ---- P8: L_ss^-1
-    tri_inverse(Ll, Xl, ncap, ns);
+    tri_inverse(Ll, Xl, ncap, ns, s_vec);
     // ---- P9: b_sc = int_K (gauss_c.pyx:95-164): h^2 exp(mvn_logpdf(x; mu, w_l^2 + sigma2))
     const double var_b = sig2 + w_l * w_l;
     const double Lb = sqrt(var_b), logdet_b = 2 * log(Lb);
@@ -342,7 +423,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) bq_setup_kernel(SetupArgs a) {
             if (i == j) v += s_l * s_l;
             Kz[(size_t)i * ncap + j] = v;
         }
-        if (chol_lower(Kz, ncap, n)) { if (tid == 0) M[H_STATUS] = SETUP_KL_NOTPD; return; }
+        if (chol_lower(Kz, ncap, n, s_vec)) { if (tid == 0) M[H_STATUS] = SETUP_KL_NOTPD; return; }
         if (warp == 0) {   // forward then backward substitution, one warp
             for (int i = 0; i < n; ++i) {
                 double s = 0;
@@ -455,7 +536,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) bq_setup_kernel(SetupArgs a) {
 }
 
 void launch_setup(const SetupArgs &a, int n_inst, cudaStream_t stream) {
-    bq_setup_kernel<<<n_inst, SETUP_THREADS, 0, stream>>>(a);
+    const int bytes = (int)sizeof(double) * setup_smem_doubles(a.n_cap);
+    cudaFuncSetAttribute(bq_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    bq_setup_kernel<<<n_inst, SETUP_THREADS, bytes, stream>>>(a);
 }
 
 }  // namespace bqb
