@@ -38,6 +38,7 @@ SYMBOLS = {
     "bqb_mean_neg_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp]),
     "bqb_argmin_device": (ctypes.c_int, [_vp, _vp, _ll, _dp, ctypes.POINTER(_ll), _vp]),
     "bqb_argmin_pair_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp]),
+    "bqb_choose_step_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _ll, _vp, _vp]),
     "bqb_argmin_rows_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp, _vp]),
     "bqb_launch_count": (ctypes.c_ulonglong, [_vp]),
     "bqb_model_doubles": (ctypes.c_int, [_vp]),
@@ -202,6 +203,11 @@ class Batch(object):
         """(min, first index + offset) of `v` written to the 2-element float64 CUDA tensor `pair`; no host sync."""
         _check(load().bqb_argmin_pair_device(self._h, _ptr(v), v.numel(), int(offset), _ptr(pair),
                                              _vp(stream) if stream else None), "bqb_argmin_pair_device")
+
+    def choose_step_device(self, x_a, esm, ev, pair, offset=0, inst=0, stream=None):
+        """Fused esm + expected variance + (min, first index + offset) for one instance; CUDA tensors, no host sync."""
+        _check(load().bqb_choose_step_device(self._h, int(inst), _ptr(x_a), x_a.numel(), _ptr(esm), _ptr(ev), int(offset),
+                                             _ptr(pair), _vp(stream) if stream else None), "bqb_choose_step_device")
 
     def argmin_rows_device(self, v, mins, idxs, stream=None):
         """Per-instance (min, first index) of the CUDA tensor v [n_inst, n] into mins (float64) / idxs (int64)."""

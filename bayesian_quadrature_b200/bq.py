@@ -68,7 +68,7 @@ class _PinnedPool(object):
     a buffer is handed out again only after the caller has dropped every reference to the array
     it was given (so two results never alias)."""
 
-    def __init__(self, keep=4):
+    def __init__(self, keep=6):
         self._bufs, self._keep = [], keep
 
     def take(self, n):

@@ -35,9 +35,13 @@ struct ScoreArgs {
     int *flags;
     int inst0;
     int ndb_max;
+    double *ev = nullptr;
+    double *part_val = nullptr;
+    long long *part_idx = nullptr;
 };
 void launch_setup(const SetupArgs &a, int n_inst, cudaStream_t stream);
-cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream);
+cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x = nullptr);
+cudaError_t launch_argmin_partials(double *bv, long long *bi, int nblocks, long long offset, double *pair, cudaStream_t s);
 cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, long long na, double *loss, cudaStream_t s);
 cudaError_t launch_expected_var(const double *esm, long long na, double msm, double *out, cudaStream_t s);
 cudaError_t launch_argmin(const double *v, long long n, double *scratch_val, long long *scratch_idx, int sm_count,
@@ -352,6 +356,26 @@ int bqb_argmin_pair_device(bqb_batch *b, const double *d_v, long long n, long lo
     CU(launch_argmin(d_v, n, b->d_red_val, b->d_red_idx, b->sm_count, s));
     CU(launch_argmin_pair(b->d_red_val, b->d_red_idx, offset, d_pair, s));
     b->launches += 3;
+    return 0;
+}
+
+int bqb_choose_step_device(bqb_batch *b, int inst, const double *d_x_a, int na, double *d_esm, double *d_ev, long long offset,
+                           double *d_pair, void *stream) {
+    int rc = check_ready(b, "bqb_choose_step_device");
+    if (rc) return rc;
+    if (inst < 0 || inst >= b->n_inst || !d_x_a || !d_esm || !d_ev || !d_pair || na < 1)
+        return fail(BQB_EINVAL, "bqb_choose_step_device: bad arguments");
+    CU(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    ScoreArgs a;
+    a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = 0; a.na = na;
+    a.esm = d_esm; a.em = nullptr; a.status = nullptr; a.out_stride = na; a.exp_tab = b->d_tab; a.flags = nullptr;
+    a.inst0 = 0; a.ndb_max = b->ndb_max;
+    a.ev = d_ev; a.part_val = b->d_red_val; a.part_idx = b->d_red_idx;
+    int grid_x = 0;
+    CU(launch_score(a, 1, b->sm_count, s, &grid_x));
+    CU(launch_argmin_partials(b->d_red_val, b->d_red_idx, grid_x, offset, d_pair, s));
+    b->launches += 2;
     return 0;
 }
 

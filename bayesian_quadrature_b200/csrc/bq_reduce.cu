@@ -113,6 +113,24 @@ cudaError_t launch_argmin(const double *v, long long n, double *bv, long long *b
     return cudaGetLastError();
 }
 
+// final step of the fused scoring epilogue: reduce the per-CTA partials and emit the (min, index + offset) pair
+__global__ void argmin_partials_kernel(double *bv, long long *bi, int nblocks, long long offset, double *pair) {
+    double best = INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    for (int b = threadIdx.x; b < nblocks; b += 32) better(best, idx, bv[b], bi[b]);
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        better(best, idx, v2, i2);
+    }
+    if (threadIdx.x == 0) { pair[0] = best; pair[1] = (double)(idx + offset); }
+}
+
+cudaError_t launch_argmin_partials(double *bv, long long *bi, int nblocks, long long offset, double *pair, cudaStream_t s) {
+    argmin_partials_kernel<<<1, 32, 0, s>>>(bv, bi, nblocks, offset, pair);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_argmin_pair(const double *bv, const long long *bi, long long offset, double *pair, cudaStream_t s) {
     argmin_pair_kernel<<<1, 32, 0, s>>>(bv, bi, offset, pair);
     return cudaGetLastError();

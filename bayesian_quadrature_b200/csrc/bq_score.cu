@@ -43,6 +43,10 @@ struct ScoreArgs {
     int *flags;               // [B] OR of every point's status bits (may be null)
     int inst0;
     int ndb_max;              // dense row blocks to reserve scratch for: ceil((max nc + 2) / 8)
+    // optional fused epilogue of choose_next / expected_Z_var (single-instance launches only):
+    double *ev;               // [na] expected variance Zm^2 + Zv - esm (bq.py:374-377); may be null
+    double *part_val;         // [gridDim.x] per-CTA minimum of ev ...
+    long long *part_idx;      // ... and the first index attaining it (np.argmin semantics); may be null
 };
 
 constexpr int CHUNK_FRAGS = 128;   // STREAM: fragments (256 B each) per staged chunk; two chunk buffers
@@ -221,7 +225,7 @@ __device__ __forceinline__ void park_q(double (&q0)[NT], double (&q1)[NT], doubl
     }
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, bool EPI>
 __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a) {
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     constexpr bool LOCKSTEP = STREAM || ALIGN;              // warps must keep reaching the CTA barriers
@@ -267,6 +271,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 
     const int kq = lane & 3, pq = lane >> 2;
     const int nsuper = (a.na + WARPS * 32 - 1) / (WARPS * 32);
+    double best_v = INFINITY;                               // fused argmin of ev: this lane's running (min, first index)
+    long long best_i = 0x7fffffffffffffffLL;
 
     for (int st_i = blockIdx.x; st_i < nsuper; st_i += gridDim.x) {
         const int base = (st_i * WARPS + warp) * 32;
@@ -460,19 +466,46 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                 }
             }
             o_esm[p] = esm;
+            if (EPI) {
+                const double evv = __dsub_rn(__dadd_rn(__dmul_rn(Zm, Zm), s_small[H_ZV]), esm);   // no FMA contraction: matches the host
+                a.ev[p] = evv;
+                if (evv < best_v) { best_v = evv; best_i = p; }   // p increases per lane: ties keep the first index
+            }
             if (o_em) o_em[p] = em;
             if (o_st) o_st[p] = st;
             if (st && a.flags) atomicOr(a.flags + inst, st);
         }
         __syncwarp();
     }
+    if (EPI) {                                              // (min, first index) of this CTA's points
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double v2 = __shfl_xor_sync(0xffffffffu, best_v, o);
+            const long long i2 = __shfl_xor_sync(0xffffffffu, best_i, o);
+            if (v2 < best_v || (v2 == best_v && i2 < best_i)) { best_v = v2; best_i = i2; }
+        }
+        __syncthreads();                                    // scratch is free: every warp has left the tile loop
+        double *rv = s_scr;
+        long long *ri = reinterpret_cast<long long *>(s_scr + WARPS);
+        if (lane == 0) { rv[warp] = best_v; ri[warp] = best_i; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < WARPS; ++w)
+                if (rv[w] < best_v || (rv[w] == best_v && ri[w] < best_i)) { best_v = rv[w]; best_i = ri[w]; }
+            a.part_val[blockIdx.x] = best_v;
+            a.part_idx[blockIdx.x] = best_i;
+        }
+    }
 }
 
 template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED>
-static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream) {
+static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x);
+
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, bool EPI>
+static cudaError_t launch_cfg2(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small, a.ndb_max);
-    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED>;
+    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, EPI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     const int nsuper = (a.na + WARPS * 32 - 1) / (WARPS * 32);
@@ -480,31 +513,39 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
     if (per_inst > nsuper) per_inst = nsuper;
     if (per_inst < 1) per_inst = 1;
     dim3 grid(per_inst, n_inst);
+    if (grid_x) *grid_x = per_inst;
     kern<<<grid, WARPS * 32, bytes, stream>>>(a);
     return cudaGetLastError();
 }
 
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED>
+static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
+    // the fused expected-variance / argmin epilogue is a separate instantiation so that plain scoring keeps its registers
+    if (a.ev) return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, true>(a, n_inst, sm_count, stream, grid_x);
+    return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, false>(a, n_inst, sm_count, stream, grid_x);
+}
+
 // nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 256 (operands streamed).
 // BQB_SCORE_CFG selects an alternative tiling (tuning aid); the defaults are the measured best.
-cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream) {
+cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     static const int cfg = getenv("BQB_SCORE_CFG") ? atoi(getenv("BQB_SCORE_CFG")) : 0;
     switch (a.lay.nsp_cap) {
-        case 16: return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream);
+        case 16: return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream, grid_x);
         case 64:
             switch (cfg) {
-                case 1: return launch_cfg<16, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream);
-                case 2: return launch_cfg<16, 2, 8, 2, false, 2048, true, true>(a, n_inst, sm_count, stream);
-                case 3: return launch_cfg<16, 1, 12, 2, false, 2048, true, true>(a, n_inst, sm_count, stream);
-                default: return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream);
+                case 1: return launch_cfg<16, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream, grid_x);
+                case 2: return launch_cfg<16, 2, 8, 2, false, 2048, true, true>(a, n_inst, sm_count, stream, grid_x);
+                case 3: return launch_cfg<16, 1, 12, 2, false, 2048, true, true>(a, n_inst, sm_count, stream, grid_x);
+                default: return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
             }
         case 128:
             switch (cfg) {
-                case 1: return launch_cfg<32, 2, 8, 1, false, 512, true, false>(a, n_inst, sm_count, stream);
-                case 2: return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream);
-                case 3: return launch_cfg<32, 2, 8, 1, false, 512, true, true>(a, n_inst, sm_count, stream);
-                default: return launch_cfg<32, 2, 8, 1, false, 512, false, false>(a, n_inst, sm_count, stream);
+                case 1: return launch_cfg<32, 2, 8, 1, false, 512, true, false>(a, n_inst, sm_count, stream, grid_x);
+                case 2: return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
+                case 3: return launch_cfg<32, 2, 8, 1, false, 512, true, true>(a, n_inst, sm_count, stream, grid_x);
+                default: return launch_cfg<32, 2, 8, 1, false, 512, false, false>(a, n_inst, sm_count, stream, grid_x);
             }
-        case 256: return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream);
+        case 256: return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -20,7 +20,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -57,33 +56,50 @@ def fp64_peak_tflops():
         return 37.2, "nominal:148 SM x 64 DFMA/clk x 1.965 GHz"
 
 
-class ClockSampler(threading.Thread):
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+class ClockSampler(object):
+    """`nvidia-smi -lms 200` in its own process for the duration of the timed regions (the profiling
+    recipe's clocks line); parsed when stopped.  A separate process, so it never holds this process's GIL."""
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+
+    def __init__(self, index):
+        self.path = "/tmp/bq_b200_clocks_%d_%d.csv" % (os.getpid(), index)
+        self.fh = open(self.path, "w")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def start(self):
+        return self
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        self.fh.close()
+        rows = [[c.strip() for c in line.split(",")] for line in open(self.path) if line.strip()]
+        os.unlink(self.path)
+
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in rows if num(r[0]) is not None]
+        mx = [num(r[1]) for r in rows if len(r) > 1 and num(r[1]) is not None]
+        pw = [num(r[2]) for r in rows if len(r) > 2 and num(r[2]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower() == "active"})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) > 3 + i and r[3 + i].lower() == "active"})
+        # "under load": samples at or above half the maximum clock (idle samples between phases are dropped)
+        load = [v for v in sm if mx and v >= 0.5 * max(mx)] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": reasons, "samples": len(rows)}
 
 
 def build_problem():
@@ -201,9 +217,9 @@ def run_cuda(args):
     pairs = torch.empty(world, 2, dtype=torch.float64, device=dev) if world > 1 else None
 
     def step():
-        batch.score_device(x_d, esm, em, st)                       # esm, em, status for the shard
-        batch.expected_var_device(0, esm, evv)                     # bq.py:374-377
-        batch.argmin_pair_device(evv, rank * NA, pair)             # local (min, first global index), stays on device
+        # esm (bq.py:379-402), expected variance (bq.py:374-377) and the local (min, first global index) of the shard:
+        # the scoring kernel with its fused epilogue + one tiny reduction launch; the result stays on the device
+        batch.choose_step_device(x_d, esm, evv, pair, offset=rank * NA)
         if world > 1:
             dist.all_gather_into_tensor(pairs.view(-1), pair)      # the path's only collective: W pairs of 16 B
             return bqdist.combine_argmin(pairs.cpu().numpy())
@@ -260,8 +276,8 @@ def run_cuda(args):
     # ---- end to end through the public host API: numpy in (pinned), numpy out
     x_pin = torch.from_numpy(shard).pin_memory()
     x_host = x_pin.numpy()
-    for _ in range(2):
-        bq.expected_Z_var(x_host)
+    keep = [bq.expected_Z_var(x_host) for _ in range(3)]     # steady state: the caller still holds the previous result
+    del keep
     barrier()
     e2e_ms = []
     for _ in range(args.steps):

@@ -126,6 +126,13 @@ int bqb_argmin_device(bqb_batch *b, const double *d_v, long long n, double *min_
 int bqb_argmin_pair_device(bqb_batch *b, const double *d_v, long long n, long long offset, double *d_pair,
                            void *stream);
 
+/* One fused step of expected-variance active sampling for instance `inst` over a (shard of a) query vector:
+ * d_esm[p] (bq.py:379-402), d_ev[p] = Z_mean^2 + Z_var - esm[p] (bq.py:374-377) and the deterministic
+ * (min of ev, first index + offset) pair (bq.py:663) in d_pair, in two launches (the scoring kernel carries
+ * the reduction in its epilogue).  DEVICE pointers, asynchronous on `stream`. */
+int bqb_choose_step_device(bqb_batch *b, int inst, const double *d_x_a, int na, double *d_esm, double *d_ev,
+                           long long offset, double *d_pair, void *stream);
+
 /* Per-instance (min, first index) of d_v [n_inst][stride] into DEVICE arrays d_min / d_idx [n_inst]: the
  * deterministic choose_next of a batch of independent problems (bq.py:663 per problem). */
 int bqb_argmin_rows_device(bqb_batch *b, const double *d_v, long long stride, long long n, double *d_min,

@@ -243,6 +243,12 @@ def test_full_size_properties_c2(lib, oracle):
     b.argmin_pair_device(ev[1000:], 1000, pair)                   # sharded form: offset = start of the shard
     pr = pair.cpu().numpy()
     assert pr[0] == ev_h[1000:].min() and int(pr[1]) == 1000 + int(np.argmin(ev_h[1000:]))
+    # fused step: same esm / ev bit for bit, same (min, index)
+    esm_f, ev_f = torch.empty(grid.size, dtype=torch.float64, device=dev), torch.empty(grid.size, dtype=torch.float64, device=dev)
+    b.choose_step_device(x_d, esm_f, ev_f, pair, offset=7)
+    pr = pair.cpu().numpy()
+    assert torch.equal(esm_f, esm[0]) and torch.equal(ev_f, ev)
+    assert pr[0] == ev_h.min() and int(pr[1]) == 7 + int(np.argmin(ev_h))
     assert idx == int(g["grid_idx"][int(np.argmax(g["esm"][:k]))])          # same chosen point as the reference
     sub = np.random.RandomState(5).choice(grid.size, 4000, replace=False)
     m = oracle.OracleModel(g["x_s"], g["l_s"], g["x_c"], g["params_tl"], g["params_l"], float(g["x_mean"]),
