@@ -8,5 +8,6 @@ logger = logging.getLogger("bayesian_quadrature")
 
 from .bq import BQ                                   # noqa: E402
 from .gp import GP, GaussianKernel, PeriodicKernel   # noqa: E402
+from .batch import BatchBQ                           # noqa: E402
 
-__all__ = ["BQ", "GP", "GaussianKernel", "PeriodicKernel"]
+__all__ = ["BQ", "BatchBQ", "GP", "GaussianKernel", "PeriodicKernel"]

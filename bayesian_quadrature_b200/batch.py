@@ -1,0 +1,156 @@
+"""``BatchBQ`` — P independent 1-D BQ problems advanced in lock-step on one GPU (BASELINE config C5:
+a batch of problems doing rounds of expected-variance active sampling, problems sharded across
+GPUs with no collective).
+
+Per problem the semantics are those of the reference's ``BQ`` object under fixed hyper-parameters:
+``init`` draws and filters candidates (bq.py:967-991), a round scores a query grid with
+``expected_squared_mean`` (bq.py:379-402), picks the first minimiser of ``-esm`` (bq.py:660-663,
+deterministic mode), and ``add_observation`` merges or appends the new point and re-initialises
+(bq.py:683-701).  Differences forced by batching, both documented in SURVEY appendix A.4: every
+problem has its own ``RandomState(seed + p)`` candidate stream (the reference uses one global
+RNG), and device arrays are padded to the batch's largest ``ns`` / ``nc``.
+
+All per-problem bookkeeping is numpy-vectorised over the batch; scoring, the per-problem argmin
+and the model setup run on the device through the C-ABI.
+"""
+import numpy as np
+
+from . import _lib
+
+
+def filter_candidates_batch(x_c, x_s, ns, thresh):
+    """Vectorised ``bq_c.filter_candidates`` (bq_c.pyx:601-650) over a batch: x_c [P, m] is modified
+    in place (NaN = removed), x_s [P, cap] holds ns[p] valid observations per row."""
+    P, m = x_c.shape
+    changed = np.ones(P, dtype=bool)
+    while changed.any():                     # the reference repeats the pair sweep while anything merged
+        changed[:] = False
+        for i in range(m):
+            for j in range(i + 1, m):
+                xi, xj = x_c[:, i], x_c[:, j]
+                hit = ~np.isnan(xi) & ~np.isnan(xj)
+                hit[hit] = np.abs(xi[hit] - xj[hit]) < thresh
+                if hit.any():
+                    x_c[hit, i] = (xi[hit] + xj[hit]) / 2.0
+                    x_c[hit, j] = np.nan
+                    changed |= hit
+    valid = np.arange(x_s.shape[1])[None, :] < ns[:, None]
+    for i in range(m):
+        d = np.abs(x_c[:, i, None] - x_s)
+        d[~valid] = np.inf
+        close = (d < thresh).any(axis=1)          # NaN candidates compare False
+        x_c[close, i] = np.nan
+
+
+class BatchBQ(object):
+    def __init__(self, x_s, l_s, params_tl, params_l, n_candidate, candidate_thresh, x_mean, x_var, seed=0,
+                 device=0, ns_reserve=0):
+        """x_s, l_s: [P, ns0] initial observations; params_*: (h, w, s) shared by all problems or [P, 3];
+        x_mean / x_var scalars or [P].  ``ns_reserve`` extra observation slots are pre-allocated."""
+        x_s, l_s = np.asarray(x_s, dtype=np.float64), np.asarray(l_s, dtype=np.float64)
+        if x_s.ndim != 2 or x_s.shape != l_s.shape:
+            raise ValueError("x_s and l_s must be [P, ns] arrays of the same shape")
+        if (l_s <= 0).any():
+            raise ValueError("l_s contains zero or negative values")
+        self.P, ns0 = x_s.shape
+        self.cap = ns0 + int(ns_reserve)
+        self.x_s = np.zeros((self.P, self.cap)); self.x_s[:, :ns0] = x_s
+        self.l_s = np.ones((self.P, self.cap)); self.l_s[:, :ns0] = l_s
+        self.ns = np.full(self.P, ns0, dtype=np.int32)
+        bc = lambda v, k: np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.float64), (self.P, k)))
+        self.hyp = np.concatenate([bc(params_tl, 3), bc(params_l, 3)], axis=1)
+        self.prior = np.stack([bc(x_mean, 1)[:, 0], bc(x_var, 1)[:, 0], np.full(self.P, float(candidate_thresh))], axis=1)
+        self.n_candidate, self.thresh = int(n_candidate), float(candidate_thresh)
+        if self.n_candidate > _lib.NC_MAX:
+            raise NotImplementedError("n_candidate > %d" % _lib.NC_MAX)
+        self.rngs = [np.random.RandomState(seed + p) for p in range(self.P)]
+        self.device = int(device)
+        self.batch = None
+        self.x_c = np.zeros((self.P, _lib.NC_MAX))
+        self.nc = np.zeros(self.P, dtype=np.int32)
+        self.init()
+
+    def close(self):
+        if self.batch is not None:
+            self.batch.close()
+            self.batch = None
+
+    # ---------------------------------------------------------------- bq.py:132-171 / :967-991 per problem
+    def init(self):
+        w_tl = self.hyp[:, 1]
+        idx = np.arange(self.cap)[None, :] < self.ns[:, None]
+        lo = np.where(idx, self.x_s, np.inf).min(axis=1) - w_tl
+        hi = np.where(idx, self.x_s, -np.inf).max(axis=1) + w_tl
+        xc = np.stack([self.rngs[p].uniform(lo[p], hi[p], self.n_candidate) for p in range(self.P)])
+        filter_candidates_batch(xc, self.x_s, self.ns, self.thresh)
+        xc.sort(axis=1)                                   # NaNs sort last
+        self.nc = (~np.isnan(xc)).sum(axis=1).astype(np.int32)
+        self.x_c[:] = 0.0
+        self.x_c[:, :self.n_candidate] = np.nan_to_num(xc, nan=0.0)
+        cap_class = _lib.load().bqb_ns_capacity(int(self.ns.max()))
+        if cap_class < 0:
+            raise NotImplementedError("more than 256 observations per problem")
+        if self.batch is None or self._cap_class != cap_class:       # crossed a kernel capacity class: new device batch
+            self.close()
+            self.batch = _lib.Batch(self.P, cap_class, device=self.device)
+            self._cap_class = cap_class
+        stride = min(self.cap, cap_class)
+        info = self.batch.setup(self.ns, self.nc, self.x_s[:, :stride], self.l_s[:, :stride], self.x_c, self.hyp, self.prior)
+        bad = np.nonzero(info["status"])[0]
+        if bad.size:
+            raise np.linalg.LinAlgError("problem %d failed device setup with status %d" % (bad[0], info["status"][bad[0]]))
+        self.info = info
+        return info
+
+    def Z_mean(self):
+        return self.info["Z_mean"]
+
+    def Z_var(self):
+        return self.info["Z_var"]
+
+    # ---------------------------------------------------------------- one active-sampling round
+    def choose_next(self, x_a):
+        """Deterministic choose_next of every problem over a shared grid ``x_a`` [na] or per-problem grids
+        [P, na]: index and location of the first maximiser of expected_squared_mean."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        x_a = np.ascontiguousarray(x_a, dtype=np.float64)
+        na = x_a.shape[-1]
+        x_d = torch.from_numpy(x_a).to(dev)
+        if getattr(self, "_esm", None) is None or self._esm.shape != (self.P, na):
+            self._esm = torch.empty(self.P, na, dtype=torch.float64, device=dev)
+            self._mins = torch.empty(self.P, dtype=torch.float64, device=dev)
+            self._idxs = torch.empty(self.P, dtype=torch.int64, device=dev)
+            self._flags = torch.zeros(self.P, dtype=torch.int32, device=dev)
+        self.batch.score_device(x_d, self._esm, None, None, self._flags)
+        self._esm.neg_()                                  # loss = -esm (bq.py:660)
+        self.batch.argmin_rows_device(self._esm, self._mins, self._idxs)
+        idx = self._idxs.cpu().numpy()
+        fl = self._flags.cpu().numpy()
+        if (fl & (_lib.ST_ESM_BAD | _lib.ST_EM_BAD | _lib.ST_XA_BAD)).any():
+            raise RuntimeError("invalid expected squared mean in problem %d" % int(np.argmax(fl & 112 != 0)))
+        x_next = x_a[idx] if x_a.ndim == 1 else x_a[np.arange(self.P), idx]
+        return idx, x_next
+
+    def add_observations(self, x_new, l_new):
+        """Vectorised ``add_observation`` (bq.py:683-701): average into the nearest observation when it is
+        closer than candidate_thresh, append otherwise; then re-initialise every problem."""
+        x_new, l_new = np.asarray(x_new, dtype=np.float64), np.asarray(l_new, dtype=np.float64)
+        valid = np.arange(self.cap)[None, :] < self.ns[:, None]
+        d = np.abs(x_new[:, None] - self.x_s)
+        d[~valid] = np.inf
+        c = d.argmin(axis=1)
+        merge = d[np.arange(self.P), c] < self.thresh
+        rows = np.nonzero(merge)[0]
+        self.x_s[rows, c[rows]] = (self.x_s[rows, c[rows]] + x_new[rows]) / 2.0
+        self.l_s[rows, c[rows]] = (self.l_s[rows, c[rows]] + l_new[rows]) / 2.0
+        rows = np.nonzero(~merge)[0]
+        if rows.size and self.ns[rows].max() >= self.cap:
+            grow = max(16, self.cap // 4)
+            self.x_s = np.concatenate([self.x_s, np.zeros((self.P, grow))], axis=1)
+            self.l_s = np.concatenate([self.l_s, np.ones((self.P, grow))], axis=1)
+            self.cap += grow
+        self.x_s[rows, self.ns[rows]] = x_new[rows]
+        self.l_s[rows, self.ns[rows]] = l_new[rows]
+        self.ns[rows] += 1
+        return self.init()

@@ -97,6 +97,7 @@ int bqb_ns_capacity(int ns) {
     if (ns <= 16) return 16;
     if (ns <= 64) return 64;
     if (ns <= 128) return 128;
+    if (ns <= 160) return 160;
     if (ns <= 256) return 256;
     return BQB_EUNSUPPORTED;
 }

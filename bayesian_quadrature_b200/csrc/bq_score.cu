@@ -525,7 +525,7 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
     return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, false>(a, n_inst, sm_count, stream, grid_x);
 }
 
-// nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 256 (operands streamed).
+// nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 160 and 256 (operands streamed).
 // BQB_SCORE_CFG selects an alternative tiling (tuning aid); the defaults are the measured best.
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     static const int cfg = getenv("BQB_SCORE_CFG") ? atoi(getenv("BQB_SCORE_CFG")) : 0;
@@ -535,7 +535,11 @@ cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStrea
             switch (cfg) {
                 case 1: return launch_cfg<16, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream, grid_x);
                 case 2: return launch_cfg<16, 2, 8, 2, false, 2048, true, true>(a, n_inst, sm_count, stream, grid_x);
-                case 3: return launch_cfg<16, 1, 12, 2, false, 2048, true, true>(a, n_inst, sm_count, stream, grid_x);
+                case 3: return launch_cfg<16, 1, 12, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
+                case 4: return launch_cfg<16, 4, 8, 1, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
+                case 5: return launch_cfg<16, 1, 16, 1, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
+                case 6: return launch_cfg<16, 2, 4, 4, false, 512, true, false>(a, n_inst, sm_count, stream, grid_x);
+                case 7: return launch_cfg<16, 2, 4, 3, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
                 default: return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
             }
         case 128:
@@ -545,6 +549,7 @@ cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStrea
                 case 3: return launch_cfg<32, 2, 8, 1, false, 512, true, true>(a, n_inst, sm_count, stream, grid_x);
                 default: return launch_cfg<32, 2, 8, 1, false, 512, false, false>(a, n_inst, sm_count, stream, grid_x);
             }
+        case 160: return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
         case 256: return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
         default: return cudaErrorInvalidValue;
     }

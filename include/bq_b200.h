@@ -54,7 +54,7 @@ const char *bqb_last_error(void);
 int bqb_version(void);
 int bqb_device_count(int *count);
 
-/* Padded observation capacity the library would use for `ns` observations (16, 64, 128 or 256), or
+/* Padded observation capacity the library would use for `ns` observations (16, 64, 128, 160 or 256), or
  * BQB_EUNSUPPORTED. */
 int bqb_ns_capacity(int ns);
 

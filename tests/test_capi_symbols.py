@@ -39,7 +39,8 @@ def test_capacity_and_argument_errors_without_gpu():
     L = _lib.load()
     assert L.bqb_ns_capacity(1) == 16 and L.bqb_ns_capacity(16) == 16
     assert L.bqb_ns_capacity(17) == 64 and L.bqb_ns_capacity(64) == 64
-    assert L.bqb_ns_capacity(65) == 128 and L.bqb_ns_capacity(129) == 256 and L.bqb_ns_capacity(256) == 256
+    assert L.bqb_ns_capacity(65) == 128 and L.bqb_ns_capacity(129) == 160 and L.bqb_ns_capacity(161) == 256
+    assert L.bqb_ns_capacity(256) == 256
     assert L.bqb_ns_capacity(257) == _lib.EUNSUPPORTED
     assert L.bqb_ns_capacity(0) == _lib.EINVAL
     assert L.bqb_batch_create(None, 0, 1, 8) == _lib.EINVAL

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import scipy.stats
 
-from conftest import assert_close, load_golden
+from conftest import assert_close, load_golden  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 
@@ -163,3 +163,31 @@ def test_marginalize_shapes_and_choose_next():
         rows.append(-bq.expected_squared_mean(x_a))
     bq.__setstate__(saved)
     assert_close(loss_d.cpu().numpy(), np.mean(rows, axis=0), "marginal loss")
+
+
+def test_batch_of_problems_rounds_match_the_oracle(oracle):
+    """C5 semantics: independent problems advanced in lock-step; after every round each problem's scores and
+    chosen point equal the oracle's for that problem's current observations and candidates."""
+    from bayesian_quadrature_b200 import BatchBQ, synthetic
+    P, ns0 = 5, 30
+    x0, _ = synthetic.observations(ns0)
+    fl = [synthetic.likelihood(ns0, synthetic.problem_shift(p)) for p in range(P)]
+    opt = synthetic.options(ns0)
+    bb = BatchBQ(np.tile(x0, (P, 1)), np.stack([f(x0) for f in fl]), synthetic.PARAMS_TL, synthetic.PARAMS_L,
+                 opt["n_candidate"], opt["candidate_thresh"], opt["x_mean"], opt["x_var"], seed=77, ns_reserve=8)
+    grid = synthetic.query_grid(ns0, 901)
+    for rnd in range(4):
+        idx, x_next = bb.choose_next(grid)
+        esm = -bb._esm.cpu().numpy()
+        for p in range(P):
+            n, c = bb.ns[p], bb.nc[p]
+            m = oracle.OracleModel(bb.x_s[p, :n], bb.l_s[p, :n], bb.x_c[p, :c], synthetic.PARAMS_TL, synthetic.PARAMS_L,
+                                   opt["x_mean"], opt["x_var"], opt["candidate_thresh"])
+            o_esm, _, _ = m.esm_and_em(grid)
+            assert_close(esm[p], o_esm, "round %d problem %d esm" % (rnd, p))
+            assert int(np.argmax(o_esm)) == int(idx[p])
+            assert_close(bb.Z_mean()[p], m.Z_mean(), "Z_mean")
+        ns_before = bb.ns.copy()
+        bb.add_observations(x_next, np.array([fl[p](x_next[p]) for p in range(P)]))
+        assert ((bb.ns == ns_before) | (bb.ns == ns_before + 1)).all()
+    bb.close()

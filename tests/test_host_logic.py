@@ -111,3 +111,20 @@ def test_synthetic_workload_matches_survey_generator():
     assert g[0] == -2 * synthetic.span(64) and g[-1] == 2 * synthetic.span(64)
     h = synthetic.hyper_sets(1024)
     assert h.shape == (1024, 4) and (h[:, 1] >= 1.6).all() and (h[:, 1] <= 2.2).all()
+
+
+def test_batched_candidate_filter_equals_the_scalar_one():
+    from bayesian_quadrature_b200.batch import filter_candidates_batch
+    rs = np.random.RandomState(0)
+    P = 300
+    ns = rs.randint(5, 10, P)
+    x_s = np.zeros((P, 9))
+    for p in range(P):
+        x_s[p, :ns[p]] = np.sort(rs.uniform(-5, 5, ns[p]))
+    xc = rs.uniform(-7, 7, (P, 10))
+    ref = xc.copy()
+    for p in range(P):
+        util.filter_candidates(ref[p], x_s[p, :ns[p]], 0.5)
+    filter_candidates_batch(xc, x_s, ns, 0.5)
+    assert np.array_equal(np.isnan(xc), np.isnan(ref))
+    assert np.array_equal(np.nan_to_num(xc), np.nan_to_num(ref))
