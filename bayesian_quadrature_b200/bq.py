@@ -453,6 +453,34 @@ class BQ(object):
             batch.close()
             raise
 
+    def log_lh_batch(self, hypers_tl, hypers_l, params):
+        """Joint log marginal likelihood ``gp_log_l.log_lh + gp_l.log_lh`` (bq.py:546) of MANY hyper-parameter
+        proposals in one device batch: entry i is what ``_make_llh_params(params)`` would return
+        for ``concatenate([hypers_tl[i], hypers_l[i]])`` — including -inf for invalid values, a non-PD Gram matrix
+        or the "GP mean is too large" guard (bq.py:536-548) — without touching this object's state."""
+        hypers_tl, hypers_l = np.atleast_2d(hypers_tl), np.atleast_2d(hypers_l)
+        n = hypers_tl.shape[0]
+        names = list(self.gp_log_l.K.names) + ["s"]
+        hyp = np.empty((n, 6))
+        hyp[:, :3], hyp[:, 3:] = self.gp_log_l.params, self.gp_l.params
+        for j, name in enumerate(params):
+            hyp[:, names.index(name)] = hypers_tl[:, j]
+            hyp[:, 3 + names.index(name)] = hypers_l[:, j]
+        ok = np.isfinite(hyp).all(axis=1) & (hyp[:, [0, 1, 3, 4]] > 0).all(axis=1) & (hyp[:, [2, 5]] >= 0).all(axis=1)
+        out = np.full(n, -np.inf)
+        if ok.any():
+            m = int(ok.sum())
+            batch = _lib.Batch(m, self.ns, device=self.device)
+            try:
+                prior = np.tile([float(self.options["x_mean"][0]), float(self.options["x_cov"][0, 0]),
+                                 self.options["candidate_thresh"]], (m, 1))
+                info = batch.setup(np.full(m, self.ns), np.full(m, self.nc), np.tile(self.x_s, (m, 1)),
+                                   np.tile(self.l_s, (m, 1)), np.tile(self.x_c, (m, 1)), hyp[ok], prior, check_max=True)
+            finally:
+                batch.close()
+            out[ok] = np.where(info["status"] == _lib.SETUP_OK, info["log_lh"], -np.inf)
+        return out
+
     def choose_next(self, x_a, n, params, plot=False, deterministic=False):
         """Pick the next query location: argmin over `x_a` of the marginal negative expected squared
         mean (bq.py:659-681).  Like the reference, ties within ``np.isclose`` of the minimum are

@@ -68,3 +68,64 @@ def all_reduce_loss(partial_sum, n_samples_total):
     if W > 1:
         dist.all_reduce(partial_sum, op=dist.ReduceOp.SUM)
     return partial_sum / n_samples_total
+
+
+# --------------------------------------------------------------------------------------------------
+# Sharded forms of the BQ scoring calls (one process per GPU; every rank holds the same BQ object)
+
+def expected_Z_var_sharded(bq, x_a):
+    """``bq.expected_Z_var(x_a)`` with the query points sharded across ranks (C2 / C3): each rank scores its
+    contiguous shard on its GPU, the shards are all-gathered, every rank returns the full vector."""
+    W, rank = world()
+    x_a = np.ascontiguousarray(x_a, dtype=np.float64)
+    lo, hi = shard_bounds(x_a.shape[0], W, rank)
+    dev = torch.device("cuda", bq.device)
+    model = bq._device_model()
+    x_d = torch.from_numpy(x_a[lo:hi]).to(dev)
+    esm = torch.empty(max(hi - lo, 1), dtype=torch.float64, device=dev)
+    ev = torch.empty_like(esm)
+    pair = torch.empty(2, dtype=torch.float64, device=dev)
+    if hi > lo:
+        model.batch.choose_step_device(x_d, esm[: hi - lo], ev[: hi - lo], pair, offset=lo)
+    return all_gather_scores(ev[: hi - lo], x_a.shape[0]).cpu().numpy()
+
+
+def choose_next_sharded(bq, x_a, hypers_tl, hypers_l, params, shard="points"):
+    """Deterministic ``choose_next`` (first minimiser of the marginal loss, bq.py:660-663) over the hyper-parameter
+    samples ``hypers_tl`` / ``hypers_l`` (as returned by ``bq.sample_hypers``; identical on every rank).
+
+    shard="points"  (C2/C3/C4-by-points): every rank scores its shard of ``x_a`` under ALL samples; the mean over
+                    samples is taken in sample order on the device (bit-identical to one GPU); the ranks exchange one
+                    (min, first global index) pair each.
+    shard="samples" (C4-by-samples): every rank scores ALL points under its contiguous subset of samples; the partial
+                    sums are all-reduced (summation order differs from one GPU by ~1e-16 relative), then argmin.
+    Returns (x_next, global index, minimal loss)."""
+    W, rank = world()
+    x_a = np.ascontiguousarray(x_a, dtype=np.float64)
+    n = len(hypers_tl)
+    dev = torch.device("cuda", bq.device)
+    if shard == "points":
+        lo, hi = shard_bounds(x_a.shape[0], W, rank)
+        if hi > lo:
+            loss, batch = bq.marginal_loss(x_a[lo:hi], hypers_tl, hypers_l, params)
+            mn, idx = batch.argmin_device(loss)
+            batch.close()
+        else:
+            mn, idx = float("inf"), 0
+        mn, idx = all_argmin(mn, idx, lo, device=dev)
+    elif shard == "samples":
+        lo, hi = shard_bounds(n, W, rank)
+        total = torch.zeros(x_a.shape[0], dtype=torch.float64, device=dev)
+        batch = None
+        if hi > lo:
+            loss, batch = bq.marginal_loss(x_a, hypers_tl[lo:hi], hypers_l[lo:hi], params)
+            total += loss * (hi - lo)
+        loss = all_reduce_loss(total, n)
+        if batch is None:
+            from . import _lib
+            batch = _lib.Batch(1, 1, device=bq.device)
+        mn, idx = batch.argmin_device(loss)
+        batch.close()
+    else:
+        raise ValueError("shard must be 'points' or 'samples'")
+    return x_a[idx], idx, mn

@@ -1,0 +1,42 @@
+"""Run under torchrun on >= 2 GPUs (tests/test_gpu_dist.py launches it): the sharded scoring calls must return
+what one GPU returns — bit-identical scores and argmin for points-sharding, 1e-12-close loss for samples-sharding."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bayesian_quadrature_b200 import BQ, GaussianKernel, synthetic  # noqa: E402
+from bayesian_quadrature_b200 import dist as bqdist                  # noqa: E402
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, W = dist.get_rank(), dist.get_world_size()
+    bq = synthetic.make_bq(BQ, GaussianKernel, 64)           # same seed on every rank: identical candidates
+    assert bq.device == local
+    x_a = synthetic.query_grid(64, 100003)
+    ev = bqdist.expected_Z_var_sharded(bq, x_a)
+    ref = bq.expected_Z_var(x_a)                             # the whole vector on this rank's GPU
+    assert np.array_equal(ev, ref), "sharded expected_Z_var differs from the single-GPU result"
+    hyp = synthetic.hyper_sets(6)
+    htl, hl = hyp[:, :2], hyp[:, 2:]
+    loss, batch = bq.marginal_loss(x_a, htl, hl, ["h", "w"])
+    mn1, idx1 = batch.argmin_device(loss)
+    batch.close()
+    xp, idx_p, mn_p = bqdist.choose_next_sharded(bq, x_a, htl, hl, ["h", "w"], shard="points")
+    assert idx_p == idx1 and mn_p == mn1 and xp == x_a[idx1], (idx_p, idx1, mn_p, mn1)
+    xs, idx_s, mn_s = bqdist.choose_next_sharded(bq, x_a, htl, hl, ["h", "w"], shard="samples")
+    assert idx_s == idx1 and abs(mn_s - mn1) <= 1e-12 * abs(mn1), (idx_s, idx1, mn_s, mn1)
+    if rank == 0:
+        print("DIST_GPU_CHECK_OK world=%d argmin=%d" % (W, idx1))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -191,3 +191,24 @@ def test_batch_of_problems_rounds_match_the_oracle(oracle):
         bb.add_observations(x_next, np.array([fl[p](x_next[p]) for p in range(P)]))
         assert ((bb.ns == ns_before) | (bb.ns == ns_before + 1)).all()
     bb.close()
+
+
+def test_log_lh_batch_matches_the_host_gps():
+    # many hyper-parameter proposals per launch; equals gp_log_l.log_lh + gp_l.log_lh (bq.py:546)
+    bq = make_bq()
+    rs = np.random.RandomState(4)
+    htl = np.stack([rs.uniform(10, 16, 12), rs.uniform(1.5, 2.5, 12)], axis=1)
+    hl = np.stack([rs.uniform(0.15, 0.6, 12), rs.uniform(1.0, 1.5, 12)], axis=1)
+    htl[3, 1] = -1.0                                    # invalid -> -inf (bq.py:536-543)
+    htl[5, 0] = 1e6                                     # "GP mean is too large" -> -inf
+    got = bq.log_lh_batch(htl, hl, ["h", "w"])
+    f = bq._make_llh_params(["h", "w"])
+    state = bq.__getstate__()
+    import copy
+    saved = copy.deepcopy(state)
+    want = np.array([f(np.concatenate([htl[i], hl[i]])) for i in range(12)])
+    bq.__setstate__(saved)
+    assert np.isneginf(got[3]) and np.isneginf(got[5]) and np.isneginf(want[3]) and np.isneginf(want[5])
+    fin = np.isfinite(want)
+    assert (np.isfinite(got) == fin).all()
+    assert np.allclose(got[fin], want[fin], rtol=1e-9, atol=1e-9)
