@@ -22,23 +22,38 @@ def filter_candidates_batch(x_c, x_s, ns, thresh):
     """Vectorised ``bq_c.filter_candidates`` (bq_c.pyx:601-650) over a batch: x_c [P, m] is modified
     in place (NaN = removed), x_s [P, cap] holds ns[p] valid observations per row."""
     P, m = x_c.shape
-    changed = np.ones(P, dtype=bool)
-    while changed.any():                     # the reference repeats the pair sweep while anything merged
-        changed[:] = False
-        for i in range(m):
-            for j in range(i + 1, m):
-                xi, xj = x_c[:, i], x_c[:, j]
-                hit = ~np.isnan(xi) & ~np.isnan(xj)
-                hit[hit] = np.abs(xi[hit] - xj[hit]) < thresh
-                if hit.any():
-                    x_c[hit, i] = (xi[hit] + xj[hit]) / 2.0
-                    x_c[hit, j] = np.nan
-                    changed |= hit
-    valid = np.arange(x_s.shape[1])[None, :] < ns[:, None]
+    xt = np.ascontiguousarray(x_c.T)         # [m, P]: contiguous per-candidate vectors
+    changed = True
+    with np.errstate(invalid="ignore"):
+        while changed:                       # the reference repeats the pair sweep while anything merged
+            changed = False
+            for i in range(m):
+                for j in range(i + 1, m):
+                    hit = np.abs(xt[i] - xt[j]) < thresh          # NaN (removed) compares False
+                    if hit.any():
+                        xt[i] = np.where(hit, (xt[i] + xt[j]) / 2.0, xt[i])
+                        xt[j] = np.where(hit, np.nan, xt[j])
+                        changed = True
+    x_c[:] = xt.T
+    # drop candidates closer than thresh to an observation: the nearest observation is one of the two
+    # neighbours in sorted order, found with a vectorised binary search (same |x_c - x_s| < thresh test)
+    cap = x_s.shape[1]
+    valid = np.arange(cap)[None, :] < ns[:, None]
+    xs = np.sort(np.where(valid, x_s, np.inf), axis=1)
+    xs = np.concatenate([np.full((P, 1), -np.inf), xs, np.full((P, 1), np.inf)], axis=1)    # sentinels at both ends
+    rows = np.arange(P)
+    steps = int(np.ceil(np.log2(cap + 2))) + 1
     for i in range(m):
-        d = np.abs(x_c[:, i, None] - x_s)
-        d[~valid] = np.inf
-        close = (d < thresh).any(axis=1)          # NaN candidates compare False
+        q = x_c[:, i]
+        lo = np.zeros(P, dtype=np.int64)                 # invariant: xs[lo] < q <= xs[hi] (NaN q: comparisons False)
+        hi = np.full(P, cap + 1, dtype=np.int64)
+        for _ in range(steps):
+            mid = (lo + hi) >> 1
+            go = xs[rows, mid] < q
+            lo = np.where(go, mid, lo)
+            hi = np.where(go, hi, mid)
+        with np.errstate(invalid="ignore"):
+            close = (np.abs(q - xs[rows, lo]) < thresh) | (np.abs(q - xs[rows, hi]) < thresh)
         x_c[close, i] = np.nan
 
 

@@ -137,7 +137,7 @@ __device__ __forceinline__ double exp_kernel(double d2, double C, int d2max_hi, 
     const double T = tab[ki & (N - 1)];
     const double y = fma(T * r, q, T);
     // scale by 2^(k >> log2 N): add to the exponent field; (ki & ~(N-1)) << (20 - log2 N) == (ki >> log2 N) << 20
-    return __hiloint2double(__double2hiint(y) + ((ki & ~(N - 1)) << (20 - ExpC<N>::SHIFT)), __double2loint(y));
+    return __hiloint2double(__double2hiint(y) + (ki & ~(N - 1)) * (1 << (20 - ExpC<N>::SHIFT)), __double2loint(y));   // LOP3 + IMAD
 }
 
 // high word of the largest d2 the kernel exponent may see: 700 / |nh| (exp(-700) ~ 1e-304)
