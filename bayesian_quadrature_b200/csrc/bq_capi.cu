@@ -275,28 +275,45 @@ int bqb_score_host(bqb_batch *b, const double *x_a, long long xa_stride, int na,
     return 0;
 }
 
+// Page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor) is mapped into the device
+// address space under unified addressing: the scoring kernel can read its query points from it and write its
+// results to it directly, so the transfer overlaps the arithmetic point by point instead of chunk by chunk.
+static bool mapped_host(const void *p, void **dev) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+    *dev = at.devicePointer;
+    return true;
+}
+
 int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, double *out, int *flags_out) {
     int rc = check_ready(b, "bqb_expected_var_host");
     if (rc) return rc;
     if (inst < 0 || inst >= b->n_inst || !x_a || !out || na < 0) return fail(BQB_EINVAL, "bqb_expected_var_host: bad arguments");
     if (na == 0) { if (flags_out) *flags_out = 0; return 0; }
     CU(cudaSetDevice(b->device));
-    rc = grow(b, (size_t)na, (size_t)b->n_inst * na);
-    if (rc) return rc;
+    static const int zero_copy = getenv("BQB_ZERO_COPY") ? atoi(getenv("BQB_ZERO_COPY")) : 1;
+    void *dx = nullptr, *dout = nullptr;
+    const bool in_mapped = zero_copy && mapped_host(x_a, &dx);
+    const bool out_mapped = zero_copy && mapped_host(out, &dout);
+    if (!in_mapped || !out_mapped) {
+        rc = grow(b, (size_t)na, (size_t)b->n_inst * na);
+        if (rc) return rc;
+    }
     if (!b->d_flags) CU(cudaMalloc(&b->d_flags, sizeof(int) * b->n_inst));
     if (!b->h_flags) CU(cudaMallocHost(&b->h_flags, sizeof(int)));
     for (cudaStream_t &st : b->pipe) if (!st) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     const double *h = &b->h_hdr[(size_t)inst * H_COUNT];
     const double msm = h[H_ZM] * h[H_ZM] + h[H_ZV];                                    // bq.py:374
-    // Chunks alternate between two streams so that the H2D copy of one chunk, the kernels of another and the
-    // D2H copy of a third overlap (fully so when the caller's buffers are page-locked).
+    // Buffers that are not page-locked go through device staging in chunks that alternate between two streams, so
+    // that the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap.
     static const int min_chunk = getenv("BQB_PIPE_CHUNK") ? atoi(getenv("BQB_PIPE_CHUNK")) : (1 << 18);
-    int nchunk = na / min_chunk;
+    int nchunk = (in_mapped && out_mapped) ? 1 : na / min_chunk;
     if (nchunk < 1) nchunk = 1;
     if (nchunk > 8) nchunk = 8;
     int per = ((na + nchunk - 1) / nchunk + 255) & ~255;
     CU(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->n_inst, b->pipe[0]));
-    CU(cudaStreamSynchronize(b->pipe[0]));
+    if (nchunk > 1) CU(cudaStreamSynchronize(b->pipe[0]));
     ScoreArgs a;
     a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.xa_stride = 0;
     a.em = nullptr; a.status = nullptr; a.exp_tab = b->d_tab; a.flags = b->d_flags; a.inst0 = 0; a.ndb_max = b->ndb_max;
@@ -304,15 +321,28 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
     for (int lo = 0; lo < na; lo += per, ++c) {
         const int n = (na - lo < per) ? na - lo : per;
         cudaStream_t s = b->pipe[c & 1];
-        CU(cudaMemcpyAsync(b->d_xa + lo, x_a + lo, sizeof(double) * n, cudaMemcpyHostToDevice, s));
-        a.x_a = b->d_xa + lo; a.na = n; a.esm = b->d_esm + lo; a.out_stride = n;
-        CU(launch_score(a, 1, b->sm_count, s));
-        CU(launch_expected_var(b->d_esm + lo, n, msm, b->d_em + lo, s));
-        b->launches += 2;
-        CU(cudaMemcpyAsync(out + lo, b->d_em + lo, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+        if (in_mapped) {
+            a.x_a = (const double *)dx + lo;
+        } else {
+            CU(cudaMemcpyAsync(b->d_xa + lo, x_a + lo, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+            a.x_a = b->d_xa + lo;
+        }
+        a.na = n; a.out_stride = n;
+        if (out_mapped) {
+            // fused epilogue: Zm^2 + Zv - esm written straight into the caller's page-locked array
+            a.esm = nullptr; a.ev = (double *)dout + lo;
+            a.part_val = b->d_red_val + 2048 * (c & 1); a.part_idx = b->d_red_idx + 2048 * (c & 1);
+            CU(launch_score(a, 1, b->sm_count, s));
+            b->launches += 1;
+        } else {
+            a.esm = b->d_esm + lo; a.ev = nullptr;
+            CU(launch_score(a, 1, b->sm_count, s));
+            CU(launch_expected_var(b->d_esm + lo, n, msm, b->d_em + lo, s));
+            b->launches += 2;
+            CU(cudaMemcpyAsync(out + lo, b->d_em + lo, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+        }
     }
-    CU(cudaStreamSynchronize(b->pipe[0]));
-    CU(cudaStreamSynchronize(b->pipe[1]));
+    if (nchunk > 1) CU(cudaStreamSynchronize(b->pipe[1]));
     CU(cudaMemcpyAsync(b->h_flags, b->d_flags, sizeof(int), cudaMemcpyDeviceToHost, b->pipe[0]));
     CU(cudaStreamSynchronize(b->pipe[0]));
     if (flags_out) *flags_out = *b->h_flags;

@@ -59,6 +59,20 @@ __device__ __forceinline__ int chunk_end_rb(int rb0, int nb) {
 }
 
 constexpr int SCR_STRIDE = 40;     // doubles per scratch row: 32 points + 8 pad (conflict-free 16 B fragment stores)
+constexpr int SCR_X = 4;           // scratch rows 4, 5: query points of the current / next super-tile
+constexpr int SCR_DENSE = 6;       // first dense row
+
+// Asynchronous fetch of the 32 query points of the super-tile starting at `base` into a scratch row: one coalesced
+// 256 B read per warp, global (or page-locked host memory mapped into the device address space) -> shared with no
+// register staging, issued one whole super-tile ahead of its use so that even a PCIe round trip is hidden.
+__device__ __forceinline__ void fetch_points(double *row, const double *__restrict__ xa, long long base, int na, int lane) {
+    if (base + lane < na) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(row + lane);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(xa + base + lane) : "memory");
+    } else {
+        row[lane] = 0.0;
+    }
+}
 
 template <int KS, int NT, int WARPS, bool STREAM, int TABN>
 struct ScoreSmem {
@@ -66,7 +80,9 @@ struct ScoreSmem {
     static constexpr int TRI = NBC * (NBC + 1) * 32;       // doubles per triangular operand
     static constexpr int DENSE = 3 * KS * 32;
     static constexpr int OPERANDS = STREAM ? 2 * CHUNK_FRAGS * 32 : 2 * TRI + DENSE;
-    static __host__ __device__ constexpr int scr(int ndb_max) { return (4 + 8 * ndb_max) * SCR_STRIDE; }
+    // scratch rows per warp: 0 qs, 1 qt, 2 tm, 3 isclose, 4 / 5 the query points of this / the next super-tile
+    // (double buffer filled by cp.async), 6.. the dense rows
+    static __host__ __device__ constexpr int scr(int ndb_max) { return (SCR_DENSE + 8 * ndb_max) * SCR_STRIDE; }
     static __host__ __device__ constexpr int doubles(int n_small, int ndb_max) {
         return TABN + n_small + OPERANDS + WARPS * scr(ndb_max);
     }
@@ -262,10 +278,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     const double Cl = nhl * ExpC<TABN>::INVN, Ctl = s_small[H_NHTL] * ExpC<TABN>::INVN;   // exponent scale in table units
     const int dmax_l = exp_d2max_hi(nhl), dmax_tl = exp_d2max_hi(s_small[H_NHTL]);
     const int tol2_hi = __double2hiint(s_small[H_TOL2MAX]) + 1;
-    double *scr = s_scr + warp * SM::scr(a.ndb_max);        // rows: 0 qs, 1 qt, 2 tm, 3 isclose, 4.. dense rows
+    double *scr = s_scr + warp * SM::scr(a.ndb_max);        // rows: 0 qs, 1 qt, 2 tm, 3 isclose, 4 / 5 x_a, 6.. dense rows
 
     const double *xa = a.x_a + (size_t)inst * a.xa_stride;
-    double *o_esm = a.esm + (size_t)inst * a.out_stride;
+    double *o_esm = a.esm ? a.esm + (size_t)inst * a.out_stride : nullptr;   // optional when the fused epilogue writes ev
     double *o_em = a.em ? a.em + (size_t)inst * a.out_stride : nullptr;
     int *o_st = a.status ? a.status + (size_t)inst * a.out_stride : nullptr;
 
@@ -274,8 +290,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     double best_v = INFINITY;                               // fused argmin of ev: this lane's running (min, first index)
     long long best_i = 0x7fffffffffffffffLL;
 
+    int xb = 0;                                             // scratch row (SCR_X + xb) holds this super-tile's points
+    if ((int)blockIdx.x < nsuper) fetch_points(scr + SCR_X * SCR_STRIDE, xa, (long long)(blockIdx.x * WARPS + warp) * 32, a.na, lane);
+    async_commit();
+
     for (int st_i = blockIdx.x; st_i < nsuper; st_i += gridDim.x) {
         const int base = (st_i * WARPS + warp) * 32;
+        const double *xrow = scr + (SCR_X + xb) * SCR_STRIDE;
+        async_wait<0>();                             // this super-tile's points have landed (fetched one tile ago) ...
+        __syncwarp();                                // ... for every lane of the warp
+        xb ^= 1;
+        if (st_i + (int)gridDim.x < nsuper)
+            fetch_points(scr + (SCR_X + xb) * SCR_STRIDE, xa, (long long)((st_i + gridDim.x) * WARPS + warp) * 32, a.na, lane);
+        async_commit();
         if (!LOCKSTEP && base >= a.na) continue;     // warp-uniform; lock-step warps must keep hitting the barriers
 
 #pragma unroll 1
@@ -284,8 +311,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
             double x[NT];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const int p = base + col0 + nt * 8 + pq;
-                double v = (p < a.na) ? xa[p] : 0.0;
+                const double v = xrow[col0 + nt * 8 + pq];      // points past na were filled with 0
                 x[nt] = isfinite(v) ? v : 0.0;       // invalid x_a is reported by the tail (ST_XA_BAD)
             }
             double bf[KS][NT];
@@ -329,7 +355,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                     if constexpr (STREAM) __syncthreads();       // buffer 0 is reused by the next prefetch
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
-                        *reinterpret_cast<double2 *>(scr + (4 + db * 8 + pq) * SCR_STRIDE + col0 + nt * 8 + 2 * kq) =
+                        *reinterpret_cast<double2 *>(scr + (SCR_DENSE + db * 8 + pq) * SCR_STRIDE + col0 + nt * 8 + 2 * kq) =
                             make_double2(c0[nt] + e0[nt], c1[nt] + e1[nt]);
                 }
             }
@@ -364,7 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
         // ================= tail: one lane per point of the super-tile
         const int p = base + lane;
         if (p < a.na) {
-            const double xv = xa[p];
+            const double xv = xrow[lane];
             const double Zm = s_small[H_ZM];
             double esm, em;
             int st = ST_OK;
@@ -375,7 +401,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                 em = Zm; esm = Zm * Zm; st = ST_SHORTCUT;         // bq.py:456-459
             } else {
                 const double qs = scr[lane], qt = scr[SCR_STRIDE + lane], tmv = scr[2 * SCR_STRIDE + lane];
-                double *dr = scr + 4 * SCR_STRIDE + lane;          // dense row r at dr[r * SCR_STRIDE]; reused for v_c
+                double *dr = scr + SCR_DENSE * SCR_STRIDE + lane;          // dense row r at dr[r * SCR_STRIDE]; reused for v_c
                 const double c_l = s_small[H_CL], thresh = s_small[H_THRESH];
                 const double *s_xc = s_small + lay.off_xc;
                 unsigned mask = 0;
@@ -465,7 +491,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                     if (isinf(em)) st |= ST_EM_INF;                       // bq.py:524
                 }
             }
-            o_esm[p] = esm;
+            if (o_esm) o_esm[p] = esm;
             if (EPI) {
                 const double evv = __dsub_rn(__dadd_rn(__dmul_rn(Zm, Zm), s_small[H_ZV]), esm);   // no FMA contraction: matches the host
                 a.ev[p] = evv;

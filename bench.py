@@ -56,6 +56,17 @@ def fp64_peak_tflops():
         return 37.2, "nominal:148 SM x 64 DFMA/clk x 1.965 GHz"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the scoring kernel on the bench workload, from the
+    committed `ncu --set full` capture (profiles/ncu_score_traffic.json, written by profiles/summarize.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_score_traffic.json")) as fh:
+            d = json.load(fh)
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 class ClockSampler(object):
     """`nvidia-smi -lms 200` in its own process for the duration of the timed regions (the profiling
     recipe's clocks line); parsed when stopped.  A separate process, so it never holds this process's GIL."""
@@ -305,7 +316,8 @@ def run_cuda(args):
                                    % (NS, nc, na_total),
                        "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "x_a sharded, %d rank(s)" % world},
             "roofline": {"bound": "fp64", "kernel": "bq_score_kernel<KS=16,NT=2,WARPS=8,MINB=2,STREAM=0,TABN=2048,ALIGN=1>", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(), "traffic_unit": "bytes per launch (ncu dram read + write)",
+                         "peak_source": peak_src,
                          "flop_per_eval": wf, "exp_per_eval": w_exp(NS, nc), "kernel_ms": kern_ms_avg,
                          "hbm_bytes_per_eval": 28, "hbm_gbs": 28 * NA / (kern_ms_avg * 1e-3) * 1e-9},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * NA, "d2h_bytes_per_step": bq._last_d2h_bytes},
@@ -316,12 +328,14 @@ def run_cuda(args):
             from oracle import build_ref
             if build_ref.built():
                 cores = os.cpu_count() or 1
-                v, inner, wall = reference_pass(cores, 1500)
-                v1, inner1, wall1 = reference_pass(1, 3000)
+                pts = args.cpu_points
+                v, inner, wall = reference_pass(cores, pts)
+                v1, inner1, wall1 = reference_pass(1, 12000)
                 line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
-                                        "sample": "%d forked processes x 1500 contiguous points of the 10^6 grid, %.1f s" % (cores, wall),
+                                        "sample": "%d forked processes x %d contiguous points of the 10^6 grid, %.1f s (%.1f s scoring)"
+                                                  % (cores, pts, wall, inner),
                                         "single_process_value": v1,
-                                        "single_process_sample": "1 process, OPENBLAS_NUM_THREADS=1, 3000 points, %.1f s" % wall1}
+                                        "single_process_sample": "1 process, OPENBLAS_NUM_THREADS=1, 12000 points, %.1f s" % wall1}
             else:
                 line["cpu_baseline"] = None
         print(json.dumps(line))
@@ -337,6 +351,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-points", type=int, default=40000,
+                    help="points per host core of the cpu_baseline sample (default: ~10 s of CPU work per core)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -50,6 +50,17 @@ def raw(path):
                 st[h.replace("smsp__pcsamp_warps_issue_stalled_", "")] = float(vals[i])
             except ValueError:
                 pass
+    try:        # the bench's roofline.traffic reads this
+        import json
+        import os
+        rd, wr = float(vals[hdr.index("dram__bytes_read.sum")]), float(vals[hdr.index("dram__bytes_write.sum")])
+        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd *= mult[units[hdr.index("dram__bytes_read.sum")]]
+        wr *= mult[units[hdr.index("dram__bytes_write.sum")]]
+        json.dump({"kernel": vals[hdr.index("Kernel Name")], "dram_bytes_read": rd, "dram_bytes_write": wr, "source": path},
+                  open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_score_traffic.json"), "w"))
+    except Exception as e:
+        print("traffic json not written:", e)
     tot = sum(st.values()) or 1
     out += ["", "warp stall sampling: " + ", ".join("%s %.1f %%" % (k, 100 * v / tot)
                                                     for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:8])]
