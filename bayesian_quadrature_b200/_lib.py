@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbq_b200.so")
+LIB_PATH = os.environ.get("BQB200_LIB") or os.path.join(HERE, "libbq_b200.so")     # override: A/B of kernel variants
 NC_MAX = 16
 
 ST_OK, ST_SHORTCUT, ST_NOTPD, ST_ESM_INF, ST_EM_INF, ST_ESM_BAD, ST_EM_BAD, ST_XA_BAD = 0, 1, 2, 4, 8, 16, 32, 64

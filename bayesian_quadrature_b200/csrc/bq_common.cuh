@@ -98,14 +98,14 @@ template <> struct ExpC<2048> {
     static constexpr double INVN = 0x1.71547652b82fep+11;          // N / ln 2
     static constexpr double HI = 0x1.62e42fec00000p-12;            // ln2 / N, top 31 bits
     static constexpr double LO = 0x1.d1cf79abc9e3bp-43;
-    static constexpr long long T_MIN = 0x4337ffffffe015b0LL;       // bits(1.5 * 2^52 - 4 * 522900): arg >= -708
+    static constexpr double MAGIC_B = 6755399443150848.0;          // 1.5 * 2^52 + 1023 * N
 };
 template <> struct ExpC<512> {
     static constexpr int SHIFT = 9;
     static constexpr double INVN = 0x1.71547652b82fep+9;
     static constexpr double HI = 0x1.62e42fef00000p-10;            // top 33 bits
     static constexpr double LO = 0x1.473de6af278edp-43;
-    static constexpr long long T_MIN = 0x4337fffffff8056cLL;       // bits(1.5 * 2^52 - 522900)
+    static constexpr double MAGIC_B = 6755399441579520.0;          // 1.5 * 2^52 + 1023 * N
 };
 constexpr double EXP_MAGIC = 6755399441055744.0;                   // 1.5 * 2^52
 
@@ -118,12 +118,16 @@ constexpr double EXP_MAGIC = 6755399441055744.0;                   // 1.5 * 2^52
 // like their bit patterns), so far-away points give ~1e-304 instead of an exact 0 and the result is always a
 // normal number; it also maps d2 = +inf to a finite value.  All of this keeps work off the FP64 pipe, which a
 // warp instruction occupies for 2 issue cycles (DSETP / DMNMX would cost as much as a DFMA).
+// The exp phase is issue bound (ncu: 9 FP64 + 11 other instructions per element), so the integer side is kept
+// minimal: the rounding constant carries the exponent bias (k + 1023 N in the low word of t), hence the scale
+// 2^(k >> log2 N) is merged into the table value by ONE shift and ONE bit-select (LOP3) *before* the final FMAs
+// -- no mask, no add, and nothing integer at the end of the dependency chain.
 template <int N>
 __device__ __forceinline__ double exp_kernel(double d2, double C, int d2max_hi, const double *__restrict__ tab) {
     d2 = __hiloint2double(min(__double2hiint(d2), d2max_hi), __double2loint(d2));
-    const double t = fma(d2, C, EXP_MAGIC);
-    const int ki = __double2loint(t);
-    const double kf = t - EXP_MAGIC;
+    const double t = fma(d2, C, ExpC<N>::MAGIC_B);
+    const int ki = __double2loint(t);                      // round(u) + 1023 N  (> 0: the clamp keeps u >= -1010 N)
+    const double kf = t - ExpC<N>::MAGIC_B;
     const double r = fma(d2, C, -kf);
     double q;
     if (N == 2048) {
@@ -134,10 +138,12 @@ __device__ __forceinline__ double exp_kernel(double d2, double C, int d2max_hi, 
         q = fma(q, r, 0x1.ebfbdff82c58fp-21);
         q = fma(q, r, 0x1.62e42fefa39efp-10);
     }
-    const double T = tab[ki & (N - 1)];
-    const double y = fma(T * r, q, T);
-    // scale by 2^(k >> log2 N): add to the exponent field; (ki & ~(N-1)) << (20 - log2 N) == (ki >> log2 N) << 20
-    return __hiloint2double(__double2hiint(y) + (ki & ~(N - 1)) * (1 << (20 - ExpC<N>::SHIFT)), __double2loint(y));   // LOP3 + IMAD
+    const double T = tab[ki & (N - 1)];                    // in [1, 2): exponent field 0x3ff, replaced below
+    // biased exponent (ki >> log2 N) into bits 20..30, mantissa bits of T kept: (T_hi & 0xfffff) | ((ki << s) & ~0xfffff)
+    int hs;                                                // bit-select: one LOP3 (the compiler emits two for the C form)
+    asm("lop3.b32 %0, %1, %2, 0x000fffff, 0xE4;" : "=r"(hs) : "r"(__double2hiint(T)), "r"(ki << (20 - ExpC<N>::SHIFT)));
+    const double Ts = __hiloint2double(hs, __double2loint(T));
+    return fma(Ts * r, q, Ts);
 }
 
 // high word of the largest d2 the kernel exponent may see: 700 / |nh| (exp(-700) ~ 1e-304)

@@ -24,8 +24,6 @@
 //
 // Grid: persistent CTAs (a multiple of the SM count) striding over point tiles; gridDim.y = model
 // instances (hyper-parameter sets or independent problems).
-#include <cstdlib>
-
 #include "bq_common.cuh"
 
 namespace bqb {
@@ -59,8 +57,7 @@ __device__ __forceinline__ int chunk_end_rb(int rb0, int nb) {
 }
 
 constexpr int SCR_STRIDE = 40;     // doubles per scratch row: 32 points + 8 pad (conflict-free 16 B fragment stores)
-constexpr int SCR_X = 4;           // scratch rows 4, 5: query points of the current / next super-tile
-constexpr int SCR_DENSE = 6;       // first dense row
+constexpr int SCR_DENSE = 4;       // first dense row
 
 // Asynchronous fetch of the 32 query points of the super-tile starting at `base` into a scratch row: one coalesced
 // 256 B read per warp, global (or page-locked host memory mapped into the device address space) -> shared with no
@@ -80,11 +77,11 @@ struct ScoreSmem {
     static constexpr int TRI = NBC * (NBC + 1) * 32;       // doubles per triangular operand
     static constexpr int DENSE = 3 * KS * 32;
     static constexpr int OPERANDS = STREAM ? 2 * CHUNK_FRAGS * 32 : 2 * TRI + DENSE;
-    // scratch rows per warp: 0 qs, 1 qt, 2 tm, 3 isclose, 4 / 5 the query points of this / the next super-tile
-    // (double buffer filled by cp.async), 6.. the dense rows
-    static __host__ __device__ constexpr int scr(int ndb_max) { return (SCR_DENSE + 8 * ndb_max) * SCR_STRIDE; }
+    // scratch per warp: padded rows 0 qs, 1 qt, 2 tm, 3 isclose, 4.. the dense rows; then two unpadded 32-point rows
+    // holding the query points of this / the next super-tile (double buffer filled by cp.async)
+    static __host__ __device__ constexpr int scr(int ndb_max) { return (SCR_DENSE + 8 * ndb_max) * SCR_STRIDE + 64; }
     static __host__ __device__ constexpr int doubles(int n_small, int ndb_max) {
-        return TABN + n_small + OPERANDS + WARPS * scr(ndb_max);
+        return n_small + OPERANDS + WARPS * scr(ndb_max);     // dynamic part; the exp table is static shared memory
     }
 };
 
@@ -249,8 +246,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     constexpr int SUB = 4 / NT;                             // sub-tiles of 8 NT points per 32-point super-tile
     extern __shared__ __align__(16) double smem[];
     const Layout lay = a.lay;
-    double *s_tab = smem;
-    double *s_small = s_tab + TABN;
+    __shared__ __align__(16) double s_tab[TABN];            // static: its address is an immediate of every table LDS
+    double *s_small = smem;
     double *s_ops = s_small + lay.n_small;                  // resident operands, or the staging chunk
     double *s_af_l = s_ops;
     double *s_af_d = s_af_l + SM::TRI;
@@ -278,7 +275,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     const double Cl = nhl * ExpC<TABN>::INVN, Ctl = s_small[H_NHTL] * ExpC<TABN>::INVN;   // exponent scale in table units
     const int dmax_l = exp_d2max_hi(nhl), dmax_tl = exp_d2max_hi(s_small[H_NHTL]);
     const int tol2_hi = __double2hiint(s_small[H_TOL2MAX]) + 1;
-    double *scr = s_scr + warp * SM::scr(a.ndb_max);        // rows: 0 qs, 1 qt, 2 tm, 3 isclose, 4 / 5 x_a, 6.. dense rows
+    double *scr = s_scr + warp * SM::scr(a.ndb_max);        // rows: 0 qs, 1 qt, 2 tm, 3 isclose, 4.. dense rows, then x_a
 
     const double *xa = a.x_a + (size_t)inst * a.xa_stride;
     double *o_esm = a.esm ? a.esm + (size_t)inst * a.out_stride : nullptr;   // optional when the fused epilogue writes ev
@@ -286,27 +283,45 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     int *o_st = a.status ? a.status + (size_t)inst * a.out_stride : nullptr;
 
     const int kq = lane & 3, pq = lane >> 2;
-    const int nsuper = (a.na + WARPS * 32 - 1) / (WARPS * 32);
+    // Work distribution.  A UNIT is 8 NT WARPS points (one sub-tile per warp), a super-tile SUB units (32 points per
+    // warp).  Whole super-tiles are dealt round-robin (tile it * G + c to CTA c: expensive neighbourhoods -- points
+    // close to a candidate refactorise the Schur block in the tail -- are spread over all CTAs; contiguous runs per CTA
+    // measured 12 % slower on C2), every CTA taking the same number `full` of them; the remaining R < G SUB units are
+    // split evenly at unit granularity, so a CTA ends with one partial super-tile of r_n < SUB units (8 NT r_n points
+    // per warp).  With whole super-tiles only, the last of the ~14 rounds of a 10^6-point launch was 80 % idle.
+    constexpr int UNIT = 8 * NT * WARPS;
+    const int n_units = (a.na + UNIT - 1) / UNIT;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int full = n_units / (G * SUB);
+    const int R = n_units - full * G * SUB;
+    const int r_lo = full * G * SUB + (int)(((long long)cta * R) / G);
+    const int r_n = (int)(((long long)(cta + 1) * R) / G) - (int)(((long long)cta * R) / G);
+    const int n_it = full + (r_n > 0 ? 1 : 0);
+    auto tile_u = [&](int it) { return it < full ? (it * G + cta) * SUB : r_lo; };       // first unit of tile `it`
+    auto tile_n = [&](int it) { return it < full ? SUB : r_n; };                         // its units
     double best_v = INFINITY;                               // fused argmin of ev: this lane's running (min, first index)
     long long best_i = 0x7fffffffffffffffLL;
 
-    int xb = 0;                                             // scratch row (SCR_X + xb) holds this super-tile's points
-    if ((int)blockIdx.x < nsuper) fetch_points(scr + SCR_X * SCR_STRIDE, xa, (long long)(blockIdx.x * WARPS + warp) * 32, a.na, lane);
+    int xb = 0;                                             // xrows + 32 xb holds this super-tile's points
+    double *xrows = scr + (SCR_DENSE + 8 * a.ndb_max) * SCR_STRIDE;   // two 32-point rows
+    if (n_it > 0) fetch_points(xrows, xa, (long long)tile_u(0) * UNIT + warp * (8 * NT * tile_n(0)), a.na, lane);
     async_commit();
 
-    for (int st_i = blockIdx.x; st_i < nsuper; st_i += gridDim.x) {
-        const int base = (st_i * WARPS + warp) * 32;
-        const double *xrow = scr + (SCR_X + xb) * SCR_STRIDE;
+    for (int it = 0; it < n_it; ++it) {
+        const int nsub = tile_n(it);                 // units (= sub-tiles per warp) of this super-tile
+        const int npw = 8 * NT * nsub;               // points per warp
+        const int base = tile_u(it) * UNIT + warp * npw;
+        const double *xrow = xrows + 32 * xb;
         async_wait<0>();                             // this super-tile's points have landed (fetched one tile ago) ...
         __syncwarp();                                // ... for every lane of the warp
         xb ^= 1;
-        if (st_i + (int)gridDim.x < nsuper)
-            fetch_points(scr + (SCR_X + xb) * SCR_STRIDE, xa, (long long)((st_i + gridDim.x) * WARPS + warp) * 32, a.na, lane);
+        if (it + 1 < n_it)
+            fetch_points(xrows + 32 * xb, xa, (long long)tile_u(it + 1) * UNIT + warp * (8 * NT * tile_n(it + 1)), a.na, lane);
         async_commit();
         if (!LOCKSTEP && base >= a.na) continue;     // warp-uniform; lock-step warps must keep hitting the barriers
 
 #pragma unroll 1
-        for (int sub = 0; sub < SUB; ++sub) {
+        for (int sub = 0; sub < nsub; ++sub) {
             const int col0 = sub * 8 * NT;
             double x[NT];
 #pragma unroll
@@ -389,7 +404,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 
         // ================= tail: one lane per point of the super-tile
         const int p = base + lane;
-        if (p < a.na) {
+        if (lane < npw && p < a.na) {
             const double xv = xrow[lane];
             const double Zm = s_small[H_ZM];
             double esm, em;
@@ -534,9 +549,9 @@ static cudaError_t launch_cfg2(const ScoreArgs &a, int n_inst, int sm_count, cud
     auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, EPI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    const int nsuper = (a.na + WARPS * 32 - 1) / (WARPS * 32);
+    const int n_units = (a.na + 8 * NT * WARPS - 1) / (8 * NT * WARPS);
     int per_inst = (sm_count * MINB + n_inst - 1) / n_inst;      // persistent: ~MINB CTAs per SM in total
-    if (per_inst > nsuper) per_inst = nsuper;
+    if (per_inst > n_units) per_inst = n_units;
     if (per_inst < 1) per_inst = 1;
     dim3 grid(per_inst, n_inst);
     if (grid_x) *grid_x = per_inst;
@@ -551,30 +566,24 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
     return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, false>(a, n_inst, sm_count, stream, grid_x);
 }
 
-// nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 160 and 256 (operands streamed).
-// BQB_SCORE_CFG selects an alternative tiling (tuning aid); the defaults are the measured best.
+// Bytes of shared memory (static table + dynamic) an instantiation needs for this launch
+template <int KS, int NT, int WARPS, bool STREAM, int TABN>
+static size_t smem_need(const ScoreArgs &a) {
+    return sizeof(double) * (TABN + ScoreSmem<KS, NT, WARPS, STREAM, TABN>::doubles(a.lay.n_small, a.ndb_max));
+}
+constexpr size_t SMEM_LIMIT = 227 * 1024;      // per-CTA opt-in maximum on sm_100
+
+// nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 160 and 256 (operands streamed).  The tilings
+// are the measured best of the round-1 sweep (profiles/ncu_score_r01.md); a resident instantiation falls back to the
+// streamed one when many candidates (scratch rows) push it over the shared-memory limit.
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
-    static const int cfg = getenv("BQB_SCORE_CFG") ? atoi(getenv("BQB_SCORE_CFG")) : 0;
     switch (a.lay.nsp_cap) {
         case 16: return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream, grid_x);
-        case 64:
-            switch (cfg) {
-                case 1: return launch_cfg<16, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream, grid_x);
-                case 2: return launch_cfg<16, 2, 8, 2, false, 2048, true, true>(a, n_inst, sm_count, stream, grid_x);
-                case 3: return launch_cfg<16, 1, 12, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
-                case 4: return launch_cfg<16, 4, 8, 1, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
-                case 5: return launch_cfg<16, 1, 16, 1, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
-                case 6: return launch_cfg<16, 2, 4, 4, false, 512, true, false>(a, n_inst, sm_count, stream, grid_x);
-                case 7: return launch_cfg<16, 2, 4, 3, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
-                default: return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
-            }
+        case 64: return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
         case 128:
-            switch (cfg) {
-                case 1: return launch_cfg<32, 2, 8, 1, false, 512, true, false>(a, n_inst, sm_count, stream, grid_x);
-                case 2: return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
-                case 3: return launch_cfg<32, 2, 8, 1, false, 512, true, true>(a, n_inst, sm_count, stream, grid_x);
-                default: return launch_cfg<32, 2, 8, 1, false, 512, false, false>(a, n_inst, sm_count, stream, grid_x);
-            }
+            if (smem_need<32, 2, 8, false, 512>(a) <= SMEM_LIMIT)
+                return launch_cfg<32, 2, 8, 1, false, 512, false, false>(a, n_inst, sm_count, stream, grid_x);
+            return launch_cfg<32, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
         case 160: return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
         case 256: return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
         default: return cudaErrorInvalidValue;
