@@ -22,23 +22,6 @@ struct SetupArgs {
     size_t work_stride;
     int n_cap, inst0;
 };
-struct ScoreArgs {
-    const double *models;
-    Layout lay;
-    const double *x_a;
-    long long xa_stride;
-    int na;
-    double *esm, *em;
-    int *status;
-    long long out_stride;
-    const double *exp_tab;
-    int *flags;
-    int inst0;
-    int ndb_max;
-    double *ev = nullptr;
-    double *part_val = nullptr;
-    long long *part_idx = nullptr;
-};
 void launch_setup(const SetupArgs &a, int n_inst, cudaStream_t stream);
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x = nullptr);
 cudaError_t launch_argmin_partials(double *bv, long long *bi, int nblocks, long long offset, double *pair, cudaStream_t s);

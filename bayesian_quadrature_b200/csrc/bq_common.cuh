@@ -78,6 +78,27 @@ __host__ __device__ inline Layout make_layout(int nsp_cap) {
     return L;
 }
 
+// Arguments of one scoring launch (bq_score.cu); shared with the C-ABI layer (bq_capi.cu)
+struct ScoreArgs {
+    const double *models = nullptr;     // [B][lay.total]
+    Layout lay;
+    const double *x_a = nullptr;        // [na] (xa_stride = 0) or [B][xa_stride]
+    long long xa_stride = 0;
+    int na = 0;
+    double *esm = nullptr, *em = nullptr;   // [B][out_stride]; em may be null (esm too when ev is given)
+    int *status = nullptr;              // [B][out_stride]; may be null
+    long long out_stride = 0;
+    const double *exp_tab = nullptr;    // [EXP_TAB]
+    int *flags = nullptr;               // [B] OR of every point's status bits (may be null)
+    int inst0 = 0;
+    int ndb_max = 1;                    // dense row blocks to reserve scratch for: ceil((max nc + 2) / 8)
+    // optional fused epilogue of choose_next / expected_Z_var (single-instance launches only):
+    double *ev = nullptr;               // [na] expected variance Zm^2 + Zv - esm (bq.py:374-377); may be null
+    double *part_val = nullptr;         // [gridDim.x] per-CTA minimum of ev ...
+    long long *part_idx = nullptr;      // ... and the first index attaining it (np.argmin semantics); may be null
+    int chunk_frags = 0;                // streamed kernels: fragments per operand chunk (set by launch_score)
+};
+
 #ifdef __CUDACC__
 
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor path (SASS: DMMA.8x8x4).  Lane l holds

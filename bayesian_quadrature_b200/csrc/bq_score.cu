@@ -28,32 +28,42 @@
 
 namespace bqb {
 
-struct ScoreArgs {
-    const double *models;     // [B][lay.total]
-    Layout lay;
-    const double *x_a;        // [na] (xa_stride = 0) or [B][xa_stride]
-    long long xa_stride;
-    int na;
-    double *esm, *em;         // [B][out_stride]; em may be null
-    int *status;              // [B][out_stride]; may be null
-    long long out_stride;
-    const double *exp_tab;    // [EXP_TAB]
-    int *flags;               // [B] OR of every point's status bits (may be null)
-    int inst0;
-    int ndb_max;              // dense row blocks to reserve scratch for: ceil((max nc + 2) / 8)
-    // optional fused epilogue of choose_next / expected_Z_var (single-instance launches only):
-    double *ev;               // [na] expected variance Zm^2 + Zv - esm (bq.py:374-377); may be null
-    double *part_val;         // [gridDim.x] per-CTA minimum of ev ...
-    long long *part_idx;      // ... and the first index attaining it (np.argmin semantics); may be null
-};
 
-constexpr int CHUNK_FRAGS = 128;   // STREAM: fragments (256 B each) per staged chunk; two chunk buffers
+// STREAM: the triangular operands are streamed through two chunk buffers of `chunk_frags` fragments (256 B each);
+// launch_score picks the largest size (<= CHUNK_FRAGS_MAX) that fits next to the resident pieces.
+constexpr int CHUNK_FRAGS_MAX = 256;
 
 // STREAM: row blocks [rb0, end) whose fragments fit one chunk buffer (always at least one row block)
-__device__ __forceinline__ int chunk_end_rb(int rb0, int nb) {
+__device__ __forceinline__ int chunk_end_rb(int rb0, int nb, int chunk_frags) {
     int used = 0, r = rb0;
-    while (r < nb && (r == rb0 || used + 2 * r + 2 <= CHUNK_FRAGS)) { used += 2 * r + 2; ++r; }
+    while (r < nb && (r == rb0 || used + 2 * r + 2 <= chunk_frags)) { used += 2 * r + 2; ++r; }
     return r;
+}
+
+// ---- mbarrier + bulk-copy (TMA) primitives of the operand stream
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one thread: global -> shared bulk copy (multiple of 16 B) whose completion is counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 constexpr int SCR_STRIDE = 40;     // doubles per scratch row: 32 points + 8 pad (conflict-free 16 B fragment stores)
@@ -76,12 +86,15 @@ struct ScoreSmem {
     static constexpr int NBC = KS / 2;
     static constexpr int TRI = NBC * (NBC + 1) * 32;       // doubles per triangular operand
     static constexpr int DENSE = 3 * KS * 32;
-    static constexpr int OPERANDS = STREAM ? 2 * CHUNK_FRAGS * 32 : 2 * TRI + DENSE;
+    // resident: both triangles + the dense rows; streamed: two chunk buffers + the dense rows actually used
+    static __host__ __device__ constexpr int operands(int ndb_max, int chunk_frags) {
+        return STREAM ? 2 * chunk_frags * 32 + ndb_max * KS * 32 : 2 * TRI + DENSE;
+    }
     // scratch per warp: padded rows 0 qs, 1 qt, 2 tm, 3 isclose, 4.. the dense rows; then two unpadded 32-point rows
     // holding the query points of this / the next super-tile (double buffer filled by cp.async)
     static __host__ __device__ constexpr int scr(int ndb_max) { return (SCR_DENSE + 8 * ndb_max) * SCR_STRIDE + 64; }
-    static __host__ __device__ constexpr int doubles(int n_small, int ndb_max) {
-        return n_small + OPERANDS + WARPS * scr(ndb_max);     // dynamic part; the exp table is static shared memory
+    static __host__ __device__ constexpr int doubles(int n_small, int ndb_max, int chunk_frags) {
+        return n_small + operands(ndb_max, chunk_frags) + WARPS * scr(ndb_max);     // dynamic part; the exp table is static
     }
 };
 
@@ -102,12 +115,15 @@ template <int KS, int NT, int TABN, bool TL>
 __device__ __forceinline__ void gen_fragments(double (&bf)[KS][NT], const double (&x)[NT], double C, int d2max_hi, int nks, int kq,
                                               const double *s_xs, const double *s_atl, int tol2_hi,
                                               const double *s_tab, double (&tm)[NT], int (&close)[NT]) {
+    // 8 independent exp chains per branch-free group: with one CTA of 8 warps per SM (two warps per scheduler) the
+    // NT = 1 exp phase was latency bound at 4 (ncu: 47 % of its stalls on fixed-latency dependencies)
+    constexpr int GK = (NT == 1) ? 8 : 4;
 #pragma unroll
-    for (int g = 0; g < (KS + 3) / 4; ++g) {
-        if (4 * g < nks) {
+    for (int g = 0; g < (KS + GK - 1) / GK; ++g) {
+        if (GK * g < nks) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ks = 4 * g + j;
+            for (int j = 0; j < GK; ++j) {
+                const int ks = GK * g + j;
                 if (ks < KS) {
                     const int k = 4 * ks + kq;
                     const double xs = s_xs[k];
@@ -136,14 +152,7 @@ __device__ __forceinline__ int isclose_exact(double x, const double *s_xs, const
     return c;
 }
 
-// Asynchronous CTA-wide copy global -> shared (cp.async, 16 B per thread per step); completion is
-// tracked with commit / wait groups so that the copy of the next operand chunk overlaps the DMMAs of this one.
-template <int THREADS>
-__device__ __forceinline__ void stage_async(double *dst, const double *__restrict__ src, int count) {
-    const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
-    for (int i = threadIdx.x; i < count / 2; i += THREADS)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u * i), "l"(src + 2 * i) : "memory");
-}
+// cp.async group bookkeeping of the query-point prefetch (fetch_points)
 __device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -176,6 +185,80 @@ __device__ __forceinline__ void row_block(const double *af, int lim, const doubl
     }
 }
 
+// Two consecutive row blocks at once (rolled loops): the B fragment of a k-step feeds both, which doubles the number
+// of independent DMMA chains per warp, and the k loop advances four k-steps per (branch-free) group so that the eight
+// A-fragment loads of a group are issued ahead of its DMMAs.  ncu on the ns = 256 kernel had 42 % of the DMMA-phase
+// stalls on the LDS -> DMMA scoreboard and one ISETP + BRA per two DMMAs with the one-block-at-a-time loop.
+// limA = k-steps of the first row block (2 rb + 2); the second one has two more.
+template <int KS, int NT>
+__device__ __forceinline__ void row_block_pair(const double *afA, const double *afB, int limA, const double (&bf)[KS][NT],
+                                               double (&q0)[NT], double (&q1)[NT]) {
+    static_assert(KS % 4 == 0, "k-steps come in groups of 4");
+    double a0[NT], a1[NT], b0[NT], b1[NT], c0[NT], c1[NT], d0[NT], d1[NT];   // (a, b): block A even / odd k; (c, d): block B
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { a0[nt] = a1[nt] = b0[nt] = b1[nt] = c0[nt] = c1[nt] = d0[nt] = d1[nt] = 0.0; }
+#pragma unroll
+    for (int ks = 0; ks < KS; ks += 4) {
+        if (ks >= limA + 2) break;           // both row blocks are complete
+        if (ks + 4 <= limA) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { fa[j] = afA[(ks + j) * 32]; fb[j] = afB[(ks + j) * 32]; }
+#pragma unroll
+            for (int j = 0; j < 4; j += 2)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    dmma(a0[nt], a1[nt], fa[j], bf[ks + j][nt]);
+                    dmma(c0[nt], c1[nt], fb[j], bf[ks + j][nt]);
+                    dmma(b0[nt], b1[nt], fa[j + 1], bf[ks + j + 1][nt]);
+                    dmma(d0[nt], d1[nt], fb[j + 1], bf[ks + j + 1][nt]);
+                }
+        } else {
+            if (ks + 2 <= limA) {            // limA == ks + 2: two more k-steps for both, then B's last two
+                const double fa0 = afA[ks * 32], fa1 = afA[(ks + 1) * 32];
+                double fb[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) fb[j] = afB[(ks + j) * 32];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    dmma(a0[nt], a1[nt], fa0, bf[ks][nt]);
+                    dmma(c0[nt], c1[nt], fb[0], bf[ks][nt]);
+                    dmma(b0[nt], b1[nt], fa1, bf[ks + 1][nt]);
+                    dmma(d0[nt], d1[nt], fb[1], bf[ks + 1][nt]);
+                    dmma(c0[nt], c1[nt], fb[2], bf[ks + 2][nt]);
+                    dmma(d0[nt], d1[nt], fb[3], bf[ks + 3][nt]);
+                }
+            } else {                         // limA == ks: only B's last two k-steps remain
+                const double fb0 = afB[ks * 32], fb1 = afB[(ks + 1) * 32];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    dmma(c0[nt], c1[nt], fb0, bf[ks][nt]);
+                    dmma(d0[nt], d1[nt], fb1, bf[ks + 1][nt]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const double rA0 = a0[nt] + b0[nt], rA1 = a1[nt] + b1[nt], rB0 = c0[nt] + d0[nt], rB1 = c1[nt] + d1[nt];
+        q0[nt] = fma(rA0, rA0, q0[nt]);
+        q1[nt] = fma(rA1, rA1, q1[nt]);
+        q0[nt] = fma(rB0, rB0, q0[nt]);
+        q1[nt] = fma(rB1, rB1, q1[nt]);
+    }
+}
+
+// Row blocks [rb0, rb1) of a triangular operand whose fragment (rb, ks) sits at base[(tri_frags(rb) + ks) * 32]
+template <int KS, int NT>
+__device__ __forceinline__ void row_blocks_rolled(const double *base, int rb0, int rb1, const double (&bf)[KS][NT],
+                                                  double (&q0)[NT], double (&q1)[NT]) {
+    int rb = rb0;
+#pragma unroll 1
+    for (; rb + 1 < rb1; rb += 2)
+        row_block_pair<KS, NT>(base + tri_frags(rb) * 32, base + tri_frags(rb + 1) * 32, 2 * rb + 2, bf, q0, q1);
+    if (rb < rb1) row_block<KS, NT>(base + tri_frags(rb) * 32, 2 * rb + 2, bf, q0, q1);
+}
+
 // Lower-triangular pass with shared-memory resident operands: q += (rows of (A . B))^2.
 // ROLLED = false unrolls the row-block loop as well (exact trip counts, no early-exit branches).
 template <int KS, int NT, bool ALIGN, bool ROLLED>
@@ -183,8 +266,7 @@ __device__ __forceinline__ void tri_pass(const double *af_res, const double (&bf
                                          int nb, int lane) {
     if (ALIGN) __syncthreads();                                 // all warps of the CTA enter the DMMA phase together
     if constexpr (ROLLED) {
-#pragma unroll 1
-        for (int rb = 0; rb < nb; ++rb) row_block<KS, NT>(af_res + tri_frags(rb) * 32 + lane, 2 * rb + 2, bf, q0, q1);
+        row_blocks_rolled<KS, NT>(af_res + lane, 0, nb, bf, q0, q1);
     } else {
 #pragma unroll
         for (int rb = 0; rb < KS / 2; ++rb)        // lim is a compile-time constant after unrolling: the early exit folds away
@@ -192,36 +274,49 @@ __device__ __forceinline__ void tri_pass(const double *af_res, const double (&bf
     }
 }
 
-// Streamed variant (operands do not fit in shared memory): chunks of whole row blocks are copied with
-// cp.async into two alternating buffers; the copy of chunk i+1 is in flight while the CTA's warps run the
-// DMMAs of chunk i.  tri_stream_begin() issues the first chunk early (before the exp phase).
-template <int THREADS>
-__device__ __forceinline__ void tri_stream_begin(const double *__restrict__ af_gmem, double *s_buf, int nb) {
-    const int r1 = chunk_end_rb(0, nb);
-    stage_async<THREADS>(s_buf, af_gmem, tri_frags(r1) * 32);
-    async_commit();
-}
-template <int KS, int NT, int THREADS>
-__device__ __forceinline__ void tri_stream_run(const double *__restrict__ af_gmem, double *s_buf, const double (&bf)[KS][NT],
-                                               double (&q0)[NT], double (&q1)[NT], int nb, int lane) {
-    int rb0 = 0, rb1 = chunk_end_rb(0, nb), cur = 0;
-    while (rb0 < nb) {
-        const int rb2 = (rb1 < nb) ? chunk_end_rb(rb1, nb) : rb1;
-        if (rb1 < nb) {
-            stage_async<THREADS>(s_buf + (cur ^ 1) * CHUNK_FRAGS * 32, af_gmem + tri_frags(rb1) * 32,
-                                 (tri_frags(rb2) - tri_frags(rb1)) * 32);
-            async_commit();
-            async_wait<1>();
-        } else {
-            async_wait<0>();
-        }
-        __syncthreads();                                        // chunk `cur` has landed for every thread
-        const double *base = s_buf + cur * CHUNK_FRAGS * 32 - tri_frags(rb0) * 32 + lane;
-#pragma unroll 1
-        for (int rb = rb0; rb < rb1; ++rb) row_block<KS, NT>(base + tri_frags(rb) * 32, 2 * rb + 2, bf, q0, q1);
-        __syncthreads();                                        // done with `cur` before the next prefetch overwrites it
-        rb0 = rb1; rb1 = rb2; cur ^= 1;
+// Streamed variant (operands do not fit in shared memory): chunks of whole row blocks move global (L2) -> shared
+// with ONE bulk-copy (TMA) instruction issued by one thread and completing on an mbarrier, into two alternating
+// buffers; the copy of chunk i+1 is in flight while the CTA's warps run the DMMAs of chunk i.  (The first version
+// staged chunks with per-thread cp.async: ~16 LDGSTS + address arithmetic per thread and chunk, each LDGSTS batch
+// preceded by three dummy LDS in the SASS, and two CTA barriers per chunk.)
+// The chunk boundaries depend only on nb: s_chk[i] = first row block of chunk i (padded with nb), tabulated once per
+// CTA -- recomputing them in every pass cost as many instructions as the exponentials.
+constexpr int CHUNK_TAB = 40;
+struct Stream {
+    unsigned long long *bar;      // [2] "chunk landed" barriers, one per buffer
+    const int *chk;               // chunk table
+    double *buf;                  // two buffers of `stride` doubles
+    int stride;
+    unsigned phase;               // bit b: parity to wait for on buffer b
+};
+// first chunk of a pass into buffer 0; called before the exp phase so that it lands underneath it.  Every thread has
+// left the previous pass (CTA barrier at the end of tri_stream_run), so buffer 0 is free.
+__device__ __forceinline__ void tri_stream_begin(const double *__restrict__ af_gmem, const Stream &st) {
+    if (threadIdx.x == 0) {
+        const unsigned bytes = tri_frags(st.chk[1]) * 256;
+        mbar_expect_tx(st.bar, bytes);
+        bulk_g2s(st.buf, af_gmem, bytes, st.bar);
     }
+}
+template <int KS, int NT>
+__device__ __forceinline__ void tri_stream_run(const double *__restrict__ af_gmem, Stream &st, const double (&bf)[KS][NT],
+                                               double (&q0)[NT], double (&q1)[NT], int nb, int lane) {
+    int rb0 = 0, rb1 = st.chk[1], cur = 0, ci = 0;
+    while (rb0 < nb) {
+        const int rb2 = st.chk[ci + 2];
+        mbar_wait(st.bar + cur, (st.phase >> cur) & 1u);        // chunk `cur` has landed
+        st.phase ^= 1u << cur;
+        __syncthreads();                                        // everybody is done with chunk cur ^ 1 ...
+        if (rb1 < nb && threadIdx.x == 0) {                     // ... so its buffer takes the next chunk while this one is consumed
+            const unsigned bytes = (tri_frags(rb2) - tri_frags(rb1)) * 256;
+            mbar_expect_tx(st.bar + (cur ^ 1), bytes);
+            bulk_g2s(st.buf + (cur ^ 1) * st.stride, af_gmem + tri_frags(rb1) * 32, bytes, st.bar + (cur ^ 1));
+        }
+        const double *base = st.buf + cur * st.stride - tri_frags(rb0) * 32 + lane;
+        row_blocks_rolled<KS, NT>(base, rb0, rb1, bf, q0, q1);
+        rb0 = rb1; rb1 = rb2; cur ^= 1; ++ci;
+    }
+    __syncthreads();                                            // both buffers are free again (next pass)
 }
 
 // Sum the 8 row slots of the squared accumulators (lanes with equal lane & 3) and park them in scratch row `row`
@@ -248,11 +343,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     const Layout lay = a.lay;
     __shared__ __align__(16) double s_tab[TABN];            // static: its address is an immediate of every table LDS
     double *s_small = smem;
-    double *s_ops = s_small + lay.n_small;                  // resident operands, or the staging chunk
+    double *s_ops = s_small + lay.n_small;                  // resident operands, or the two chunk buffers + dense rows
     double *s_af_l = s_ops;
-    double *s_af_d = s_af_l + SM::TRI;
-    double *s_af_t = s_af_d + SM::DENSE;
-    double *s_scr = s_ops + SM::OPERANDS;
+    double *s_af_d = STREAM ? s_ops + 2 * a.chunk_frags * 32 : s_af_l + SM::TRI;
+    double *s_af_t = s_af_d + SM::DENSE;                    // (resident only)
+    double *s_scr = s_ops + SM::operands(a.ndb_max, a.chunk_frags);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int inst = a.inst0 + blockIdx.y;
@@ -263,12 +358,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     __syncthreads();
     const int nc = (int)s_small[H_NC], nsp = (int)s_small[H_NSP], ndb = (int)s_small[H_NDB];
     const int nb = nsp >> 3, nks = nsp >> 2;
-    if constexpr (!STREAM) {
+    __shared__ int s_chk[STREAM ? CHUNK_TAB : 1];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    Stream strm{s_bar, s_chk, s_ops, a.chunk_frags * 32, 0u};
+    if constexpr (STREAM) {
+        if (tid == 0) {
+            int r = 0;
+            for (int i = 0; i < CHUNK_TAB; ++i) { s_chk[i] = r; if (r < nb) r = chunk_end_rb(r, nb, a.chunk_frags); }
+            mbar_init(s_bar, 1);
+            mbar_init(s_bar + 1, 1);
+            mbar_init_fence();
+        }
+    } else {
         stage<THREADS>(s_af_l, M + lay.off_af_l_tri, tri_frags(nb) * 32);
         stage<THREADS>(s_af_t, M + lay.off_af_tl_tri, tri_frags(nb) * 32);
-        stage<THREADS>(s_af_d, M + lay.off_af_l_dense, ndb * nks * 32);
-        __syncthreads();
     }
+    stage<THREADS>(s_af_d, M + lay.off_af_l_dense, ndb * nks * 32);     // the dense rows are resident in both variants
+    __syncthreads();
 
     const double *s_xs = s_small + lay.off_xs, *s_tol = s_small + lay.off_tol, *s_atl = s_small + lay.off_atl;
     const double nhl = s_small[H_NHL];
@@ -337,22 +443,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 
             // ---- phase L: K_l cross-kernel fragments, triangular rows then the dense candidate / g rows
             if (ALIGN) __syncthreads();                  // ... and the exp phase together (DMMA / DFMA mixing costs pipe throughput)
-            if constexpr (STREAM) tri_stream_begin<THREADS>(M + lay.off_af_l_tri, s_ops, nb);
+            if constexpr (STREAM) tri_stream_begin(M + lay.off_af_l_tri, strm);
             gen_fragments<KS, NT, TABN, false>(bf, x, Cl, dmax_l, nks, kq, s_xs, s_atl, tol2_hi, s_tab, tm, close);
-            if constexpr (STREAM) tri_stream_run<KS, NT, THREADS>(M + lay.off_af_l_tri, s_ops, bf, q0, q1, nb, lane);
+            if constexpr (STREAM) tri_stream_run<KS, NT>(M + lay.off_af_l_tri, strm, bf, q0, q1, nb, lane);
             else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_l, bf, q0, q1, nb, lane);
 #pragma unroll
             for (int db = 0; db < 3; ++db) {
                 if (db < ndb) {
-                    const double *af;
-                    if constexpr (STREAM) {
-                        __syncthreads();
-                        stage<THREADS>(s_ops, M + lay.off_af_l_dense + (db * nks) * 32, nks * 32);
-                        __syncthreads();
-                        af = s_ops + lane;
-                    } else {
-                        af = s_af_d + (db * nks) * 32 + lane;
-                    }
+                    const double *af = s_af_d + (db * nks) * 32 + lane;
                     double c0[NT], c1[NT], e0[NT], e1[NT];
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
@@ -367,7 +465,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                             }
                         }
                     }
-                    if constexpr (STREAM) __syncthreads();       // buffer 0 is reused by the next prefetch
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
                         *reinterpret_cast<double2 *>(scr + (SCR_DENSE + db * 8 + pq) * SCR_STRIDE + col0 + nt * 8 + 2 * kq) =
@@ -380,12 +477,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
             if (ALIGN) __syncthreads();
-            if constexpr (STREAM) tri_stream_begin<THREADS>(M + lay.off_af_tl_tri, s_ops, nb);
+            if constexpr (STREAM) tri_stream_begin(M + lay.off_af_tl_tri, strm);
             gen_fragments<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, nks, kq, s_xs, s_atl, tol2_hi, s_tab, tm, close);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
                 if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
-            if constexpr (STREAM) tri_stream_run<KS, NT, THREADS>(M + lay.off_af_tl_tri, s_ops, bf, q0, q1, nb, lane);
+            if constexpr (STREAM) tri_stream_run<KS, NT>(M + lay.off_af_tl_tri, strm, bf, q0, q1, nb, lane);
             else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane);
             park_q<NT>(q0, q1, scr, 1, col0, kq, pq);
 #pragma unroll
@@ -539,13 +636,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     }
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED>
-static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x);
+constexpr size_t SMEM_LIMIT = 227 * 1024;      // per-CTA opt-in maximum on sm_100 (static + dynamic)
+constexpr size_t SMEM_STATIC_MISC = 256;       // chunk table, mbarriers
+
+// Bytes of shared memory (static + dynamic) an instantiation needs for this launch
+template <int KS, int NT, int WARPS, bool STREAM, int TABN>
+static size_t smem_need(const ScoreArgs &a, int chunk_frags) {
+    return sizeof(double) * (TABN + ScoreSmem<KS, NT, WARPS, STREAM, TABN>::doubles(a.lay.n_small, a.ndb_max, chunk_frags)) +
+           SMEM_STATIC_MISC;
+}
 
 template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, bool EPI>
-static cudaError_t launch_cfg2(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
+static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
-    const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small, a.ndb_max);
+    a.chunk_frags = 0;
+    if (STREAM) {       // the largest chunk that fits; a chunk must hold the longest row block (KS fragments)
+        int cf = CHUNK_FRAGS_MAX;
+        while (cf >= KS && smem_need<KS, NT, WARPS, STREAM, TABN>(a, cf) > SMEM_LIMIT) cf -= 16;
+        if (cf < KS) return cudaErrorInvalidConfiguration;
+        a.chunk_frags = cf;
+    }
+    const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small, a.ndb_max, a.chunk_frags);
     auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, EPI>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
@@ -566,22 +677,15 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
     return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, false>(a, n_inst, sm_count, stream, grid_x);
 }
 
-// Bytes of shared memory (static table + dynamic) an instantiation needs for this launch
-template <int KS, int NT, int WARPS, bool STREAM, int TABN>
-static size_t smem_need(const ScoreArgs &a) {
-    return sizeof(double) * (TABN + ScoreSmem<KS, NT, WARPS, STREAM, TABN>::doubles(a.lay.n_small, a.ndb_max));
-}
-constexpr size_t SMEM_LIMIT = 227 * 1024;      // per-CTA opt-in maximum on sm_100
-
 // nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 160 and 256 (operands streamed).  The tilings
-// are the measured best of the round-1 sweep (profiles/ncu_score_r01.md); a resident instantiation falls back to the
+// are the measured best of the round-1 sweeps (profiles/ncu_score_r01.md); a resident instantiation falls back to the
 // streamed one when many candidates (scratch rows) push it over the shared-memory limit.
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     switch (a.lay.nsp_cap) {
         case 16: return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream, grid_x);
         case 64: return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
         case 128:
-            if (smem_need<32, 2, 8, false, 512>(a) <= SMEM_LIMIT)
+            if (smem_need<32, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
                 return launch_cfg<32, 2, 8, 1, false, 512, false, false>(a, n_inst, sm_count, stream, grid_x);
             return launch_cfg<32, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
         case 160: return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
