@@ -30,6 +30,15 @@ SYMBOLS = {
     "bqb_batch_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "bqb_batch_destroy": (None, [_vp]),
     "bqb_batch_setup": (ctypes.c_int, [_vp, _ip, _ip, _dp, _dp, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, _vp]),
+    "bqb_batch_stage": (ctypes.c_int, [_vp, _ip, _dp, _dp, ctypes.c_int, _dp, _dp, _vp]),
+    "bqb_batch_setup_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "bqb_batch_seed_candidates": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint), _vp]),
+    "bqb_batch_rng_get": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint), _ip]),
+    "bqb_batch_rng_set": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint), _ip]),
+    "bqb_batch_draw_candidates": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    "bqb_batch_add_observations": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "bqb_batch_get_staged": (ctypes.c_int, [_vp, _ip, _ip, _dp, _dp, _dp]),
+    "bqb_batch_capacity": (ctypes.c_int, [_vp]),
     "bqb_batch_info": (ctypes.c_int, [_vp, _dp, _dp, _dp, _ip, _dp]),
     "bqb_score_device": (ctypes.c_int, [_vp, _vp, _ll, ctypes.c_int, _vp, _vp, _vp, _ll, _vp, _vp]),
     "bqb_expected_var_host": (ctypes.c_int, [_vp, ctypes.c_int, _dp, ctypes.c_int, _dp, _ip]),
@@ -146,6 +155,63 @@ class Batch(object):
         l_c = np.empty((B, NC_MAX))
         _check(load().bqb_batch_info(self._h, _pd(Zm), _pd(Zv), _pd(llh), st.ctypes.data_as(_ip), _pd(l_c)), "bqb_batch_info")
         return {"Z_mean": Zm, "Z_var": Zv, "log_lh": llh, "status": st, "l_c": l_c}
+
+    # ---- device-resident active sampling (include/bq_b200.h, "device-resident active sampling")
+    @property
+    def capacity(self):
+        return int(load().bqb_batch_capacity(self._h))
+
+    def stage(self, ns, x_s, l_s, hyp, prior, stream=None):
+        B = self.n_inst
+        ns = np.ascontiguousarray(np.broadcast_to(np.asarray(ns, dtype=np.int32), (B,)))
+        x_s, l_s = _d(x_s).reshape(B, -1), _d(l_s).reshape(B, -1)
+        hyp, prior = _d(hyp).reshape(B, 6), _d(prior).reshape(B, 3)
+        _check(load().bqb_batch_stage(self._h, ns.ctypes.data_as(_ip), _pd(x_s), _pd(l_s), x_s.shape[1], _pd(hyp), _pd(prior),
+                                      _vp(stream) if stream else None), "bqb_batch_stage")
+
+    def setup_device(self, check_max=False, stream=None):
+        _check(load().bqb_batch_setup_device(self._h, int(check_max), _vp(stream) if stream else None), "bqb_batch_setup_device")
+        return self.info()
+
+    def seed_candidates(self, seeds, stream=None):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        if seeds.shape != (self.n_inst,):
+            raise ValueError("one 32-bit seed per instance")
+        _check(load().bqb_batch_seed_candidates(self._h, seeds.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)),
+                                                _vp(stream) if stream else None), "bqb_batch_seed_candidates")
+
+    def rng_get(self):
+        """(words [624, n_inst] uint32, positions [n_inst] int32) of the per-instance MT19937 generators."""
+        mt = np.empty((624, self.n_inst), dtype=np.uint32)
+        pos = np.empty(self.n_inst, dtype=np.int32)
+        _check(load().bqb_batch_rng_get(self._h, mt.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), pos.ctypes.data_as(_ip)),
+               "bqb_batch_rng_get")
+        return mt, pos
+
+    def rng_set(self, mt, pos):
+        mt = np.ascontiguousarray(mt, dtype=np.uint32)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        if mt.shape != (624, self.n_inst) or pos.shape != (self.n_inst,):
+            raise ValueError("mt must be [624, n_inst], pos [n_inst]")
+        _check(load().bqb_batch_rng_set(self._h, mt.ctypes.data_as(ctypes.POINTER(ctypes.c_uint)), pos.ctypes.data_as(_ip)),
+               "bqb_batch_rng_set")
+
+    def draw_candidates(self, n_candidate, stream=None):
+        _check(load().bqb_batch_draw_candidates(self._h, int(n_candidate), _vp(stream) if stream else None),
+               "bqb_batch_draw_candidates")
+
+    def add_observations(self, x_new, l_new, stream=None):
+        """x_new, l_new: float64 CUDA tensors [n_inst]."""
+        _check(load().bqb_batch_add_observations(self._h, _ptr(x_new), _ptr(l_new), _vp(stream) if stream else None),
+               "bqb_batch_add_observations")
+
+    def get_staged(self):
+        B, cap = self.n_inst, self.capacity
+        ns, nc = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
+        x_s, l_s, x_c = np.empty((B, cap)), np.empty((B, cap)), np.empty((B, NC_MAX))
+        _check(load().bqb_batch_get_staged(self._h, ns.ctypes.data_as(_ip), nc.ctypes.data_as(_ip), _pd(x_s), _pd(l_s), _pd(x_c)),
+               "bqb_batch_get_staged")
+        return {"ns": ns, "nc": nc, "x_s": x_s, "l_s": l_s, "x_c": x_c}
 
     def score_host(self, x_a, want_em=True, want_status=True):
         """x_a: [na] shared by all instances, or [B, na].  Returns (esm, em, status) as [B, na] numpy arrays."""

@@ -32,6 +32,11 @@ cudaError_t launch_argmin(const double *v, long long n, double *scratch_val, lon
 cudaError_t launch_argmin_rows(const double *v, long long stride, long long n, int rows, double *mins, long long *idxs,
                                cudaStream_t s);
 cudaError_t launch_argmin_pair(const double *bv, const long long *bi, long long offset, double *pair, cudaStream_t s);
+cudaError_t launch_mt_seed(const unsigned *seeds, unsigned *mt, int *mti, int P, cudaStream_t s);
+cudaError_t launch_add_observations(double *x_s, double *l_s, int *ns, int stride, const double *prior, const double *x_new,
+                                    const double *l_new, int P, int *overflow, cudaStream_t s);
+cudaError_t launch_draw_candidates(const double *x_s, const int *ns, int stride, const double *hyp, const double *prior,
+                                   unsigned *mt, int *mti, int n_candidate, double *x_c, int *nc, int P, cudaStream_t s);
 }  // namespace bqb
 
 using namespace bqb;
@@ -46,8 +51,13 @@ struct bqb_batch {
     double *d_models = nullptr, *d_tab = nullptr, *d_work = nullptr;
     int work_inst = 0, n_cap = 0;
     size_t work_stride = 0;
-    // staged inputs
+    // staged inputs: x_s / l_s rows have the device stride ns_cap, so that observations can be appended in place
     int *d_ns = nullptr, *d_nc = nullptr;
+    bool staged = false;
+    // device-resident active sampling (bq_round.cu)
+    unsigned *d_mt = nullptr;          // [624][n_inst] Mersenne-Twister words
+    int *d_mti = nullptr, *d_overflow = nullptr;
+    std::vector<int> h_ns, h_nc;
     double *d_xs = nullptr, *d_ls = nullptr, *d_xc = nullptr, *d_hyp = nullptr, *d_prior = nullptr;
     // host-buffer scoring staging (grown on demand)
     double *d_xa = nullptr, *d_esm = nullptr, *d_em = nullptr;
@@ -116,6 +126,8 @@ int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     CU(cudaMalloc(&b->d_red_val, sizeof(double) * 4096));
     CU(cudaMalloc(&b->d_red_idx, sizeof(long long) * 4096));
     b->h_hdr.resize((size_t)n_inst * H_COUNT);
+    b->h_ns.resize(n_inst);
+    b->h_nc.resize(n_inst);
     *out = b;
     return 0;
 }
@@ -124,35 +136,19 @@ void bqb_batch_destroy(bqb_batch *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     void *ptrs[] = {b->d_models, b->d_tab, b->d_work, b->d_ns, b->d_nc, b->d_xs, b->d_ls, b->d_xc, b->d_hyp, b->d_prior,
-                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags};
+                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags, b->d_mt, b->d_mti, b->d_overflow};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaStream_t st : b->pipe) if (st) cudaStreamDestroy(st);
     if (b->h_flags) cudaFreeHost(b->h_flags);
     delete b;
 }
 
-int bqb_batch_setup(bqb_batch *b, const int *ns, const int *nc, const double *x_s, const double *l_s, int in_stride,
-                    const double *x_c, const double *hyp, const double *prior, int check_max, void *stream) {
-    if (!b || !ns || !nc || !x_s || !l_s || !hyp || !prior) return fail(BQB_EINVAL, "bqb_batch_setup: null argument");
-    if (in_stride < 1 || in_stride > b->ns_cap) return fail(BQB_EINVAL, "bqb_batch_setup: in_stride exceeds the batch capacity");
-    for (int i = 0; i < b->n_inst; ++i) {
-        if (ns[i] < 1 || ns[i] > in_stride) return fail(BQB_EINVAL, "bqb_batch_setup: ns out of range");
-        if (nc[i] < 0 || nc[i] > NC_MAX) return fail(BQB_EUNSUPPORTED, "bqb_batch_setup: more than 16 candidates");
-        if (nc[i] > 0 && !x_c) return fail(BQB_EINVAL, "bqb_batch_setup: x_c is null");
-    }
-    cudaStream_t s = (cudaStream_t)stream;
-    CU(cudaSetDevice(b->device));
+// Runs the setup kernel on the staged device inputs and fetches the per-instance headers and counts.
+static int run_setup(bqb_batch *b, int check_max, cudaStream_t s) {
     const int B = b->n_inst;
-    CU(cudaMemcpyAsync(b->d_ns, ns, sizeof(int) * B, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(b->d_nc, nc, sizeof(int) * B, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(b->d_xs, x_s, sizeof(double) * (size_t)B * in_stride, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(b->d_ls, l_s, sizeof(double) * (size_t)B * in_stride, cudaMemcpyHostToDevice, s));
-    if (x_c) CU(cudaMemcpyAsync(b->d_xc, x_c, sizeof(double) * (size_t)B * NC_MAX, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(b->d_hyp, hyp, sizeof(double) * (size_t)B * 6, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(b->d_prior, prior, sizeof(double) * (size_t)B * 3, cudaMemcpyHostToDevice, s));
     SetupArgs a;
     a.ns = b->d_ns; a.nc = b->d_nc; a.x_s = b->d_xs; a.l_s = b->d_ls; a.x_c = b->d_xc; a.hyp = b->d_hyp; a.prior = b->d_prior;
-    a.in_stride = in_stride; a.check_max = check_max; a.models = b->d_models; a.lay = b->lay;
+    a.in_stride = b->ns_cap; a.check_max = check_max; a.models = b->d_models; a.lay = b->lay;
     a.work = b->d_work; a.work_stride = b->work_stride; a.n_cap = b->n_cap;
     for (int i0 = 0; i0 < B; i0 += b->work_inst) {
         const int cnt = (B - i0 < b->work_inst) ? B - i0 : b->work_inst;
@@ -164,12 +160,137 @@ int bqb_batch_setup(bqb_batch *b, const int *ns, const int *nc, const double *x_
     // headers back to the host (Z_mean, Z_var, log_lh, status)
     CU(cudaMemcpy2DAsync(b->h_hdr.data(), sizeof(double) * H_COUNT, b->d_models, sizeof(double) * b->lay.total,
                          sizeof(double) * H_COUNT, B, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(b->h_ns.data(), b->d_ns, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(b->h_nc.data(), b->d_nc, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     b->ndb_max = 1;
-    for (int i = 0; i < B; ++i) { const int d = (nc[i] + 2 + 7) / 8; if (d > b->ndb_max) b->ndb_max = d; }
+    for (int i = 0; i < B; ++i) { const int d = (b->h_nc[i] + 2 + 7) / 8; if (d > b->ndb_max) b->ndb_max = d; }
     b->ready = true;
     return 0;
 }
+
+int bqb_batch_stage(bqb_batch *b, const int *ns, const double *x_s, const double *l_s, int in_stride, const double *hyp,
+                    const double *prior, void *stream) {
+    if (!b || !ns || !x_s || !l_s || !hyp || !prior) return fail(BQB_EINVAL, "bqb_batch_stage: null argument");
+    if (in_stride < 1 || in_stride > b->ns_cap) return fail(BQB_EINVAL, "bqb_batch_stage: in_stride exceeds the batch capacity");
+    for (int i = 0; i < b->n_inst; ++i)
+        if (ns[i] < 1 || ns[i] > in_stride) return fail(BQB_EINVAL, "bqb_batch_stage: ns out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaSetDevice(b->device));
+    const int B = b->n_inst;
+    CU(cudaMemcpyAsync(b->d_ns, ns, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync(b->d_xs, sizeof(double) * b->ns_cap, x_s, sizeof(double) * in_stride, sizeof(double) * in_stride, B,
+                         cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync(b->d_ls, sizeof(double) * b->ns_cap, l_s, sizeof(double) * in_stride, sizeof(double) * in_stride, B,
+                         cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->d_hyp, hyp, sizeof(double) * (size_t)B * 6, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(b->d_prior, prior, sizeof(double) * (size_t)B * 3, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));          // the host arrays may be pageable and are free to change after this call
+    b->staged = true;
+    b->ready = false;
+    return 0;
+}
+
+int bqb_batch_setup(bqb_batch *b, const int *ns, const int *nc, const double *x_s, const double *l_s, int in_stride,
+                    const double *x_c, const double *hyp, const double *prior, int check_max, void *stream) {
+    if (!b || !nc) return fail(BQB_EINVAL, "bqb_batch_setup: null argument");
+    int rc = bqb_batch_stage(b, ns, x_s, l_s, in_stride, hyp, prior, stream);
+    if (rc) return rc;
+    for (int i = 0; i < b->n_inst; ++i) {
+        if (nc[i] < 0 || nc[i] > NC_MAX) return fail(BQB_EUNSUPPORTED, "bqb_batch_setup: more than 16 candidates");
+        if (nc[i] > 0 && !x_c) return fail(BQB_EINVAL, "bqb_batch_setup: x_c is null");
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = b->n_inst;
+    CU(cudaMemcpyAsync(b->d_nc, nc, sizeof(int) * B, cudaMemcpyHostToDevice, s));
+    if (x_c) CU(cudaMemcpyAsync(b->d_xc, x_c, sizeof(double) * (size_t)B * NC_MAX, cudaMemcpyHostToDevice, s));
+    return run_setup(b, check_max, s);
+}
+
+int bqb_batch_setup_device(bqb_batch *b, int check_max, void *stream) {
+    if (!b || !b->staged) return fail(BQB_ESTATE, "bqb_batch_setup_device: nothing staged (bqb_batch_stage / bqb_batch_setup first)");
+    CU(cudaSetDevice(b->device));
+    return run_setup(b, check_max, (cudaStream_t)stream);
+}
+
+int bqb_batch_seed_candidates(bqb_batch *b, const unsigned *seeds, void *stream) {
+    if (!b || !seeds) return fail(BQB_EINVAL, "bqb_batch_seed_candidates: null argument");
+    CU(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int B = b->n_inst;
+    if (!b->d_mt) CU(cudaMalloc(&b->d_mt, sizeof(unsigned) * 624 * (size_t)B));
+    if (!b->d_mti) CU(cudaMalloc(&b->d_mti, sizeof(int) * B));
+    unsigned *d_seeds = nullptr;
+    CU(cudaMalloc(&d_seeds, sizeof(unsigned) * B));
+    CU(cudaMemcpyAsync(d_seeds, seeds, sizeof(unsigned) * B, cudaMemcpyHostToDevice, s));
+    cudaError_t e = launch_mt_seed(d_seeds, b->d_mt, b->d_mti, B, s);
+    b->launches++;
+    cudaStreamSynchronize(s);
+    cudaFree(d_seeds);
+    CU(e);
+    return 0;
+}
+
+int bqb_batch_rng_get(bqb_batch *b, unsigned *mt_out, int *pos_out) {
+    if (!b || !b->d_mt || !mt_out || !pos_out) return fail(BQB_ESTATE, "bqb_batch_rng_get: generators were not seeded");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpy(mt_out, b->d_mt, sizeof(unsigned) * 624 * (size_t)b->n_inst, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(pos_out, b->d_mti, sizeof(int) * b->n_inst, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int bqb_batch_rng_set(bqb_batch *b, const unsigned *mt, const int *pos) {
+    if (!b || !mt || !pos) return fail(BQB_EINVAL, "bqb_batch_rng_set: null argument");
+    CU(cudaSetDevice(b->device));
+    if (!b->d_mt) CU(cudaMalloc(&b->d_mt, sizeof(unsigned) * 624 * (size_t)b->n_inst));
+    if (!b->d_mti) CU(cudaMalloc(&b->d_mti, sizeof(int) * b->n_inst));
+    CU(cudaMemcpy(b->d_mt, mt, sizeof(unsigned) * 624 * (size_t)b->n_inst, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(b->d_mti, pos, sizeof(int) * b->n_inst, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int bqb_batch_draw_candidates(bqb_batch *b, int n_candidate, void *stream) {
+    if (!b || !b->staged) return fail(BQB_ESTATE, "bqb_batch_draw_candidates: nothing staged");
+    if (!b->d_mt) return fail(BQB_ESTATE, "bqb_batch_draw_candidates: generators were not seeded");
+    if (n_candidate < 0 || n_candidate > NC_MAX) return fail(BQB_EUNSUPPORTED, "bqb_batch_draw_candidates: more than 16 candidates");
+    CU(cudaSetDevice(b->device));
+    CU(launch_draw_candidates(b->d_xs, b->d_ns, b->ns_cap, b->d_hyp, b->d_prior, b->d_mt, b->d_mti, n_candidate, b->d_xc,
+                              b->d_nc, b->n_inst, (cudaStream_t)stream));
+    b->launches++;
+    b->ready = false;
+    return 0;
+}
+
+int bqb_batch_add_observations(bqb_batch *b, const double *d_x_new, const double *d_l_new, void *stream) {
+    if (!b || !b->staged) return fail(BQB_ESTATE, "bqb_batch_add_observations: nothing staged");
+    if (!d_x_new || !d_l_new) return fail(BQB_EINVAL, "bqb_batch_add_observations: null argument");
+    CU(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!b->d_overflow) CU(cudaMalloc(&b->d_overflow, sizeof(int)));
+    CU(cudaMemsetAsync(b->d_overflow, 0, sizeof(int), s));
+    CU(launch_add_observations(b->d_xs, b->d_ls, b->d_ns, b->ns_cap, b->d_prior, d_x_new, d_l_new, b->n_inst, b->d_overflow, s));
+    b->launches++;
+    b->ready = false;
+    int ov = 0;
+    CU(cudaMemcpyAsync(&ov, b->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (ov) return fail(BQB_EUNSUPPORTED, "bqb_batch_add_observations: an instance is at the batch's observation capacity");
+    return 0;
+}
+
+int bqb_batch_get_staged(bqb_batch *b, int *ns, int *nc, double *x_s, double *l_s, double *x_c) {
+    if (!b || !b->staged) return fail(BQB_ESTATE, "bqb_batch_get_staged: nothing staged");
+    CU(cudaSetDevice(b->device));
+    const size_t B = b->n_inst;
+    if (ns) CU(cudaMemcpy(ns, b->d_ns, sizeof(int) * B, cudaMemcpyDeviceToHost));
+    if (nc) CU(cudaMemcpy(nc, b->d_nc, sizeof(int) * B, cudaMemcpyDeviceToHost));
+    if (x_s) CU(cudaMemcpy(x_s, b->d_xs, sizeof(double) * B * b->ns_cap, cudaMemcpyDeviceToHost));
+    if (l_s) CU(cudaMemcpy(l_s, b->d_ls, sizeof(double) * B * b->ns_cap, cudaMemcpyDeviceToHost));
+    if (x_c) CU(cudaMemcpy(x_c, b->d_xc, sizeof(double) * B * NC_MAX, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int bqb_batch_capacity(bqb_batch *b) { return b ? b->ns_cap : BQB_EINVAL; }
 
 int bqb_batch_info(bqb_batch *b, double *Z_mean, double *Z_var, double *log_lh, int *status, double *l_c) {
     if (!b || !b->ready) return fail(BQB_ESTATE, "bqb_batch_info: batch was not set up");

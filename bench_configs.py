@@ -144,9 +144,11 @@ def c5(n_prob=16384, ns=128, na=4096):
             "frac_fp64_peak": wf * n / (kbest * 1e-3) * 1e-12 / PEAK, "chosen_index_hist_head": np.bincount(idxs.cpu().numpy())[:4].tolist()}
 
 
-def c5_rounds(n_prob=16384, ns=128, na=4096, rounds=20):
+def c5_rounds(n_prob=16384, ns=128, na=4096, rounds=20, device_resident=True):
     """C5 as BASELINE.json states it: 16384 independent problems, 128 observations each, 20 rounds of
-    score -> deterministic argmin -> add_observation -> re-init, all problems on this GPU."""
+    score -> deterministic argmin -> add_observation -> re-init, all problems on this GPU.  device_resident=True keeps
+    the observations, candidate generators and candidate filter on the GPU (the likelihood is still evaluated by the
+    caller on the host: it is the user's black box); False drives every round from host arrays."""
     from bayesian_quadrature_b200 import BatchBQ
     opt = synthetic.options(ns)
     x0, _ = synthetic.observations(ns)
@@ -160,25 +162,33 @@ def c5_rounds(n_prob=16384, ns=128, na=4096, rounds=20):
     l0 = np.stack([lik(np.full(n_prob, x), shifts) for x in x0], axis=1)
     t0 = time.perf_counter()
     bb = BatchBQ(np.tile(x0, (n_prob, 1)), l0, synthetic.PARAMS_TL, synthetic.PARAMS_L, opt["n_candidate"],
-                 opt["candidate_thresh"], opt["x_mean"], opt["x_var"], seed=synthetic.SEED, ns_reserve=rounds)
+                 opt["candidate_thresh"], opt["x_mean"], opt["x_var"], seed=synthetic.SEED, ns_reserve=rounds,
+                 device_resident=device_resident)
     init_s = time.perf_counter() - t0
     grid = synthetic.query_grid(ns, na)
+    if device_resident:
+        grid = torch.from_numpy(grid).cuda()
     score_ms, host_ms = [], []
     torch.cuda.synchronize()
     t_all = time.perf_counter()
     for r in range(rounds):
         t0 = time.perf_counter()
-        idx, x_next = bb.choose_next(grid)
+        idx, x_next = bb.choose_next(grid, on_device=device_resident)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        bb.add_observations(x_next, lik(x_next, shifts))
+        if device_resident:      # only the chosen points go to the host likelihood and its values come back
+            l_next = torch.from_numpy(lik(x_next.cpu().numpy(), shifts)).cuda()
+            bb.add_observations(x_next, l_next)
+        else:
+            bb.add_observations(x_next, lik(x_next, shifts))
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         score_ms.append((t1 - t0) * 1e3)
         host_ms.append((t2 - t1) * 1e3)
     total_s = time.perf_counter() - t_all
     evals = n_prob * na * rounds
-    out = {"config": "C5 (20 rounds)", "n_problems": n_prob, "ns_start": ns, "ns_end_min": int(bb.ns.min()),
+    bb.sync_host()
+    out = {"config": "C5 (20 rounds, %s)" % ("device-resident" if device_resident else "host-driven"), "n_problems": n_prob, "ns_start": ns, "ns_end_min": int(bb.ns.min()),
            "ns_end_max": int(bb.ns.max()), "na": na, "rounds": rounds, "init_s": init_s, "total_s": total_s,
            "score_ms_per_round_first": score_ms[0], "score_ms_per_round_last": score_ms[-1],
            "update_ms_per_round_mean": float(np.mean(host_ms)), "evals_per_s_whole_loop": evals / total_s,
@@ -190,6 +200,6 @@ def c5_rounds(n_prob=16384, ns=128, na=4096, rounds=20):
 if __name__ == "__main__":
     which = [a.lower() for a in sys.argv[1:]] or ["c1", "c2", "c3", "c4", "c5", "c5r"]
     runs = {"c1": lambda: single("C1", 8, 200), "c2": lambda: single("C2", 64, 10 ** 6), "c3": lambda: single("C3", 256, 10 ** 7),
-            "c4": c4, "c5": c5, "c5r": c5_rounds}
+            "c4": c4, "c5": c5, "c5r": c5_rounds, "c5rh": lambda: c5_rounds(device_resident=False)}
     for k in which:
         print(json.dumps(runs[k]()), flush=True)

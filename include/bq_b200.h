@@ -81,6 +81,38 @@ int bqb_batch_setup(bqb_batch *b, const int *ns, const int *nc, const double *x_
                     int in_stride, const double *x_c, const double *hyp, const double *prior,
                     int check_max, void *stream);
 
+/* ---- device-resident active sampling over a batch of independent problems ----------------
+ * The observations of every instance stay in HBM between rounds: a round is
+ *   bqb_score_device -> bqb_argmin_rows_device -> (caller evaluates the likelihood at the chosen points)
+ *   -> bqb_batch_add_observations -> bqb_batch_draw_candidates -> bqb_batch_setup_device.
+ *
+ * bqb_batch_stage: the upload half of bqb_batch_setup (HOST pointers; x_s / l_s rows of in_stride doubles are
+ * stored with the batch's own row stride bqb_batch_capacity(), so observations can be appended in place). */
+int bqb_batch_stage(bqb_batch *b, const int *ns, const double *x_s, const double *l_s, int in_stride,
+                    const double *hyp, const double *prior, void *stream);
+/* The setup half: runs the setup kernel on whatever is staged on the device (after bqb_batch_stage /
+ * bqb_batch_add_observations / bqb_batch_draw_candidates).  Stands in for BQ.init (bq.py:132-171) of every
+ * instance.  Synchronises `stream`. */
+int bqb_batch_setup_device(bqb_batch *b, int check_max, void *stream);
+/* One numpy.random.RandomState(seeds[i]) per instance (MT19937 seeded like numpy's legacy integer seeding),
+ * resident on the device; bqb_batch_rng_get / _set copy the generator states ([624][n_inst] words, word-major, and
+ * the n_inst positions) to / from HOST arrays, e.g. to continue a stream that the host started. */
+int bqb_batch_seed_candidates(bqb_batch *b, const unsigned *seeds, void *stream);
+int bqb_batch_rng_get(bqb_batch *b, unsigned *mt_out, int *pos_out);
+int bqb_batch_rng_set(bqb_batch *b, const unsigned *mt, const int *pos);
+/* BQ._choose_candidates (bq.py:967-991) for every instance on the device: n_candidate draws of
+ * np.random.uniform(x_s.min() - w_tl, x_s.max() + w_tl) from the instance's generator (bit-identical to numpy),
+ * bq_c.filter_candidates (bq_c.pyx:601-650) with the instance's candidate_thresh, np.sort of the survivors. */
+int bqb_batch_draw_candidates(bqb_batch *b, int n_candidate, void *stream);
+/* BQ.add_observation (bq.py:683-701) for every instance: DEVICE arrays d_x_new / d_l_new [n_inst]; the new point
+ * is averaged into the nearest observation when closer than candidate_thresh, appended otherwise.  Returns
+ * BQB_EUNSUPPORTED if an instance is already at bqb_batch_capacity() observations.  Synchronises `stream`. */
+int bqb_batch_add_observations(bqb_batch *b, const double *d_x_new, const double *d_l_new, void *stream);
+/* Copies the staged state to HOST arrays (any may be NULL): ns, nc [n_inst]; x_s, l_s [n_inst][capacity];
+ * x_c [n_inst][BQB_NC_MAX]. */
+int bqb_batch_get_staged(bqb_batch *b, int *ns, int *nc, double *x_s, double *l_s, double *x_c);
+int bqb_batch_capacity(bqb_batch *b);
+
 /* Per-instance results of the setup (HOST output arrays of n_inst entries, any may be NULL;
  * l_c is [n_inst][BQB_NC_MAX]).  Z_mean / Z_var replace BQ._exact_Z_mean (bq.py:268-291) and
  * BQ._exact_Z_var (bq.py:329-348). */

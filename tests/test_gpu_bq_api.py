@@ -193,6 +193,63 @@ def test_batch_of_problems_rounds_match_the_oracle(oracle):
     bb.close()
 
 
+def test_device_resident_rounds_equal_the_host_rounds():
+    """with the observations, the per-problem numpy-compatible MT19937 candidate streams, the candidate
+    filter and add_observation on the GPU, every round gives bit-identical candidates, observations, chosen points
+    and Z estimates to the host-driven rounds -- including across a capacity-class change (ns 62 -> 66 crosses 64)."""
+    import torch
+    from bayesian_quadrature_b200 import BatchBQ, synthetic
+    P, ns0 = 7, 62
+    x0, _ = synthetic.observations(ns0)
+    fl = [synthetic.likelihood(ns0, synthetic.problem_shift(p)) for p in range(P)]
+    opt = synthetic.options(ns0)
+    args = (np.tile(x0, (P, 1)), np.stack([f(x0) for f in fl]), synthetic.PARAMS_TL, synthetic.PARAMS_L,
+            opt["n_candidate"], opt["candidate_thresh"], opt["x_mean"], opt["x_var"])
+    host = BatchBQ(*args, seed=123, ns_reserve=8)
+    dev = BatchBQ(*args, seed=123, device_resident=True)
+    grid = synthetic.query_grid(ns0, 1201)
+    grid_d = torch.from_numpy(grid).cuda()
+    for rnd in range(5):
+        dev.sync_host()
+        assert (dev.ns == host.ns).all() and (dev.nc == host.nc).all(), "round %d counts" % rnd
+        for p in range(P):
+            n, c = host.ns[p], host.nc[p]
+            assert np.array_equal(dev.x_s[p, :n], host.x_s[p, :n]) and np.array_equal(dev.l_s[p, :n], host.l_s[p, :n])
+            assert np.array_equal(dev.x_c[p, :c], host.x_c[p, :c]), "round %d problem %d candidates" % (rnd, p)
+        assert np.array_equal(dev.Z_mean(), host.Z_mean()) and np.array_equal(dev.Z_var(), host.Z_var())
+        idx_h, x_h = host.choose_next(grid)
+        idx_d, x_d = dev.choose_next(grid_d, on_device=True)
+        assert np.array_equal(idx_d.cpu().numpy(), idx_h) and np.array_equal(x_d.cpu().numpy(), x_h)
+        l_new = np.array([fl[p](x_h[p]) for p in range(P)])
+        host.add_observations(x_h, l_new)
+        dev.add_observations(x_d, torch.from_numpy(l_new).cuda())
+    assert dev.batch.capacity == 128 and host.ns.max() > 64
+    host.close()
+    dev.close()
+
+
+def test_device_candidate_stream_is_numpys():
+    """bqb_batch_draw_candidates draws np.random.RandomState(seed).uniform(lo, hi, n) bit for bit, also across the
+    624-word regeneration of the generator (40 rounds x 16 draws x 2 words > 624)."""
+    from bayesian_quadrature_b200 import _lib
+    P, ns = 3, 5
+    x_s = np.array([[0.0, 1.0, 2.5, 4.0, 9.0], [-3.0, -1.0, 0.5, 2.0, 2.5], [10.0, 11.0, 12.0, 13.5, 15.0]])
+    b = _lib.Batch(P, ns)
+    hyp = np.tile([15.0, 2.0, 0.0, 0.2, 1.3, 0.0], (P, 1))
+    prior = np.tile([0.0, 10.0, 1e-9], (P, 1))             # tiny threshold: nothing is filtered
+    b.stage(np.full(P, ns), x_s, np.ones_like(x_s), hyp, prior)
+    seeds = np.array([0, 8728, 4294967295], dtype=np.uint32)
+    b.seed_candidates(seeds)
+    rs = [np.random.RandomState(int(s)) for s in seeds]
+    for rnd in range(40):
+        b.draw_candidates(16)
+        st = b.get_staged()
+        for p in range(P):
+            want = np.sort(rs[p].uniform(x_s[p].min() - 2.0, x_s[p].max() + 2.0, 16))
+            assert st["nc"][p] == 16 and np.array_equal(st["x_c"][p], want), "round %d problem %d" % (rnd, p)
+    b.close()
+
+
 def test_log_lh_batch_matches_the_host_gps():
     # SURVEY 8(f).1: many hyper-parameter proposals per launch; equals gp_log_l.log_lh + gp_l.log_lh (bq.py:546)
     bq = make_bq()
