@@ -41,6 +41,8 @@ SYMBOLS = {
     "bqb_batch_capacity": (ctypes.c_int, [_vp]),
     "bqb_batch_info": (ctypes.c_int, [_vp, _dp, _dp, _dp, _ip, _dp]),
     "bqb_score_device": (ctypes.c_int, [_vp, _vp, _ll, ctypes.c_int, _vp, _vp, _vp, _ll, _vp, _vp]),
+    "bqb_predict_device": (ctypes.c_int, [_vp, _vp, _ll, ctypes.c_int, _vp, _vp, _ll, _vp]),
+    "bqb_predict_host": (ctypes.c_int, [_vp, _dp, _ll, ctypes.c_int, _dp, _dp]),
     "bqb_expected_var_host": (ctypes.c_int, [_vp, ctypes.c_int, _dp, ctypes.c_int, _dp, _ip]),
     "bqb_score_host": (ctypes.c_int, [_vp, _dp, _ll, ctypes.c_int, _dp, _dp, _ip]),
     "bqb_expected_var_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _ll, _vp, _vp]),
@@ -229,6 +231,29 @@ class Batch(object):
         _check(load().bqb_score_host(self._h, _pd(x_a), stride, na, _pd(esm), _pd(em) if want_em else None,
                                      st.ctypes.data_as(_ip) if want_status else None), "bqb_score_host")
         return esm, em, st
+
+    def predict_host(self, x):
+        """(l_mean, v_log_l) as [B, na] numpy arrays for x [na] (shared) or [B, na]: gp_l.mean(x), diag gp_log_l.cov(x)."""
+        x = _d(x)
+        B = self.n_inst
+        if x.ndim == 1:
+            stride, na = 0, x.shape[0]
+        else:
+            if x.shape[0] != B:
+                raise ValueError("x must be [na] or [n_inst, na]")
+            stride, na = x.shape[1], x.shape[1]
+        m, v = np.empty((B, na)), np.empty((B, na))
+        _check(load().bqb_predict_host(self._h, _pd(x), stride, na, _pd(m), _pd(v)), "bqb_predict_host")
+        return m, v
+
+    def predict_device(self, x, l_mean, v_log_l, stream=None):
+        """torch CUDA tensors: x float64 [na] or [B, na]; outputs float64 [B, na]."""
+        if x.dim() == 1:
+            stride, na = 0, x.shape[0]
+        else:
+            stride, na = x.stride(0), x.shape[1]
+        _check(load().bqb_predict_device(self._h, _ptr(x), stride, na, _ptr(l_mean), _ptr(v_log_l), l_mean.stride(0),
+                                         _vp(stream) if stream else None), "bqb_predict_device")
 
     def expected_var_host(self, x_a, inst=0, out=None):
         """BQ.expected_Z_var for one instance: numpy in, numpy out, plus the OR of the status bits.

@@ -220,14 +220,30 @@ class BQ(object):
         self._dev_model = None
 
     # ------------------------------------------------------------------ mean / variance of l (host GPs)
+    def _predict(self, x):
+        """(gp_l.mean(x), diag gp_log_l.cov(x)) for a vector of points in one device pass; None when the device factors
+        do not apply (noisy gp_l: they are those of the noise-free bordered matrix) and the host GPs must answer."""
+        if self.options["use_approx"] or self.gp_l.get_param("s") != 0:
+            return None
+        x = np.ascontiguousarray(x, dtype=DTYPE)
+        if x.ndim != 1 or not np.isfinite(x).all():
+            return None
+        m, v = self._device_model().batch.predict_host(x)
+        return m[0], v[0]
+
     def l_mean(self, x):
         """Mean of the final approximation to l: the mean of the GP over exp(log l) (bq.py:177-200)."""
-        return self.gp_l.mean(x)
+        pred = self._predict(x)
+        return self.gp_l.mean(x) if pred is None else pred[0]
 
     def l_var(self, x):
         """Marginal variance of the final approximation (bq.py:202-231)."""
-        v_log_l = np.diag(self.gp_log_l.cov(x)).copy()
-        m_l = self.gp_l.mean(x)
+        pred = self._predict(x)
+        if pred is None:
+            v_log_l = np.diag(self.gp_log_l.cov(x)).copy()
+            m_l = self.gp_l.mean(x)
+        else:
+            m_l, v_log_l = pred
         l_var = v_log_l * m_l ** 2
         l_var[l_var < 0] = 0
         return l_var

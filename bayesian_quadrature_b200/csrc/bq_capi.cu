@@ -339,6 +339,26 @@ int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int
     return 0;
 }
 
+int bqb_predict_device(bqb_batch *b, const double *d_x, long long x_stride, int na, double *d_l_mean, double *d_v_log_l,
+                       long long out_stride, void *stream) {
+    int rc = check_ready(b, "bqb_predict_device");
+    if (rc) return rc;
+    if (!d_x || !d_l_mean || !d_v_log_l || na < 0 || out_stride < na) return fail(BQB_EINVAL, "bqb_predict_device: bad arguments");
+    if (na == 0) return 0;
+    CU(cudaSetDevice(b->device));
+    ScoreArgs a;
+    a.models = b->d_models; a.lay = b->lay; a.x_a = d_x; a.xa_stride = x_stride; a.na = na;
+    a.esm = d_l_mean; a.em = d_v_log_l; a.status = nullptr; a.out_stride = out_stride; a.exp_tab = b->d_tab;
+    a.flags = nullptr; a.ndb_max = b->ndb_max; a.predict = 1;
+    for (int i0 = 0; i0 < b->n_inst; i0 += 32768) {
+        const int cnt = (b->n_inst - i0 < 32768) ? b->n_inst - i0 : 32768;
+        a.inst0 = i0;
+        CU(launch_score(a, cnt, b->sm_count, (cudaStream_t)stream));
+        b->launches++;
+    }
+    return 0;
+}
+
 static int grow(bqb_batch *b, size_t n_xa, size_t n_out) {
     if (n_xa > b->cap_xa) {
         if (b->d_xa) cudaFree(b->d_xa);
@@ -388,6 +408,26 @@ static bool mapped_host(const void *p, void **dev) {
     if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
     *dev = at.devicePointer;
     return true;
+}
+
+int bqb_predict_host(bqb_batch *b, const double *x, long long x_stride, int na, double *l_mean, double *v_log_l) {
+    int rc = check_ready(b, "bqb_predict_host");
+    if (rc) return rc;
+    if (!x || !l_mean || !v_log_l || na < 0) return fail(BQB_EINVAL, "bqb_predict_host: bad arguments");
+    if (na == 0) return 0;
+    CU(cudaSetDevice(b->device));
+    const size_t B = b->n_inst;
+    const size_t n_x = x_stride ? B * (size_t)x_stride : (size_t)na;
+    rc = grow(b, n_x, B * (size_t)na);
+    if (rc) return rc;
+    cudaStream_t s = 0;
+    CU(cudaMemcpyAsync(b->d_xa, x, sizeof(double) * n_x, cudaMemcpyHostToDevice, s));
+    rc = bqb_predict_device(b, b->d_xa, x_stride, na, b->d_esm, b->d_em, na, s);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(l_mean, b->d_esm, sizeof(double) * B * na, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(v_log_l, b->d_em, sizeof(double) * B * na, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return 0;
 }
 
 int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, double *out, int *flags_out) {

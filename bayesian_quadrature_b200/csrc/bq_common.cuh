@@ -97,6 +97,7 @@ struct ScoreArgs {
     double *part_val = nullptr;         // [gridDim.x] per-CTA minimum of ev ...
     long long *part_idx = nullptr;      // ... and the first index attaining it (np.argmin semantics); may be null
     int chunk_frags = 0;                // streamed kernels: fragments per operand chunk (set by launch_score)
+    int predict = 0;                    // 1: prediction mode (esm <- gp_l.mean(x), em <- diag gp_log_l.cov(x))
 };
 
 #ifdef __CUDACC__

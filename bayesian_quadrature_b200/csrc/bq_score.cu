@@ -333,8 +333,12 @@ __device__ __forceinline__ void park_q(double (&q0)[NT], double (&q1)[NT], doubl
     }
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, bool EPI>
+// MODE 0: esm / em / status.  MODE 1: additionally the fused expected-variance + argmin epilogue.  MODE 2: prediction --
+// the same passes, but the tail returns the posterior mean of gp_l (BQ.l_mean, bq.py:177-200) in `esm` and the
+// posterior variance of gp_log_l (the factor of BQ.l_var, bq.py:202-231) in `em`: no shortcut, no jitter pattern.
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a) {
+    constexpr bool EPI = MODE == 1, PRED = MODE == 2;
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     constexpr bool LOCKSTEP = STREAM || ALIGN;              // warps must keep reaching the CTA barriers
     constexpr int THREADS = WARPS * 32;
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
             if (!isfinite(xv)) {
                 esm = em = nan("");
                 st = ST_XA_BAD;
-            } else if (scr[3 * SCR_STRIDE + lane] != 0.0) {
+            } else if (!PRED && scr[3 * SCR_STRIDE + lane] != 0.0) {
                 em = Zm; esm = Zm * Zm; st = ST_SHORTCUT;         // bq.py:456-459
             } else {
                 const double qs = scr[lane], qt = scr[SCR_STRIDE + lane], tmv = scr[2 * SCR_STRIDE + lane];
@@ -519,7 +523,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                 unsigned mask = 0;
                 for (int j = 0; j < nc; ++j) {
                     const double dc = s_xc[j] - xv;
-                    if (fabs(dc) < thresh) mask |= 1u << j;     // bq.py:470 (strict <)
+                    if (!PRED && fabs(dc) < thresh) mask |= 1u << j;     // bq.py:470 (strict <)
                     dr[j * SCR_STRIDE] = fma(c_l, exp_kernel<TABN>(dc * dc, Cl, dmax_l, s_tab), dr[j * SCR_STRIDE]);   // w = k_c + W k_s
                 }
                 double qc = 0, vg = 0, va = 0, bg = 0, kaa;     // bg = u_gamma_c . u_alpha_c of this pattern
@@ -571,7 +575,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                     kaa = s_small[H_KAA_N];
                 }
                 const double s_ = kaa - (qs + qc);                        // Schur pivot of the new point
-                if (!pd || !(s_ > 0.0)) {
+                if (PRED) {
+                    esm = dr[(nc + 1) * SCR_STRIDE] + va;                 // gp_l.mean(x) = K_l(x, x_sc) alpha_l
+                    em = s_small[H_KTT] - qt;                             // diag gp_log_l.cov(x)
+                } else if (!pd || !(s_ > 0.0)) {
                     em = Zm; esm = Zm * Zm; st = ST_NOTPD;                // bq.py:481-490
                 } else {
                     const double ba = s_small[H_BA_S] + bg;               // int_K(x_sc) . alpha_P
@@ -646,7 +653,7 @@ static size_t smem_need(const ScoreArgs &a, int chunk_frags) {
            SMEM_STATIC_MISC;
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, bool EPI>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, int MODE>
 static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     a.chunk_frags = 0;
@@ -657,7 +664,7 @@ static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream
         a.chunk_frags = cf;
     }
     const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small, a.ndb_max, a.chunk_frags);
-    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, EPI>;
+    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     const int n_units = (a.na + 8 * NT * WARPS - 1) / (8 * NT * WARPS);
@@ -673,8 +680,9 @@ static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream
 template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED>
 static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     // the fused expected-variance / argmin epilogue is a separate instantiation so that plain scoring keeps its registers
-    if (a.ev) return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, true>(a, n_inst, sm_count, stream, grid_x);
-    return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, false>(a, n_inst, sm_count, stream, grid_x);
+    if (a.predict) return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, 2>(a, n_inst, sm_count, stream, grid_x);
+    if (a.ev) return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, 1>(a, n_inst, sm_count, stream, grid_x);
+    return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, 0>(a, n_inst, sm_count, stream, grid_x);
 }
 
 // nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 160 and 256 (operands streamed).  The tilings

@@ -133,6 +133,14 @@ int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int
 int bqb_score_host(bqb_batch *b, const double *x_a, long long xa_stride, int na, double *esm, double *em,
                    int *status);
 
+/* Batched prediction at na points for every instance: l_mean = gp_l.mean(x), the mean of the final
+ * approximation (BQ.l_mean, bq.py:177-200), and v_log_l = diag gp_log_l.cov(x), from which BQ.l_var (bq.py:202-231) is
+ * max(v_log_l * l_mean^2, 0).  Same layout conventions as bqb_score_*; requires s_l = 0 (the scoring factors are those
+ * of the noise-free bordered matrix). */
+int bqb_predict_device(bqb_batch *b, const double *d_x, long long x_stride, int na, double *d_l_mean,
+                       double *d_v_log_l, long long out_stride, void *stream);
+int bqb_predict_host(bqb_batch *b, const double *x, long long x_stride, int na, double *l_mean, double *v_log_l);
+
 /* out[p] = Z_mean^2 + Z_var - esm[p] for instance `inst` (BQ.expected_Z_var, bq.py:374-377).
  * DEVICE pointers. */
 int bqb_expected_var_device(bqb_batch *b, int inst, const double *d_esm, long long na, double *d_out,

@@ -193,6 +193,34 @@ def test_batch_of_problems_rounds_match_the_oracle(oracle):
     bb.close()
 
 
+def test_l_mean_l_var_on_device_match_the_host_gps(oracle):
+    """BQ.l_mean / BQ.l_var (bq.py:177-231) from one device pass of the scoring operands equal the
+    gp-object route of the reference (gp_l.mean, diag gp_log_l.cov) and the oracle's gp_log_l covariance; the
+    reference's own check (test_bq_object.py:87-91): l_mean(x_s) reproduces l_s."""
+    for ns in (9, 64, 150):
+        if ns == 9:
+            bq = make_bq()
+        else:
+            from bayesian_quadrature_b200 import BQ, GaussianKernel, synthetic
+            bq = synthetic.make_bq(BQ, GaussianKernel, ns)
+        x = np.linspace(bq.x_s.min() - 8, bq.x_s.max() + 8, 1537)
+        x = np.concatenate([x, bq.x_s, bq.x_c])             # also exactly on observations and candidates (no shortcut here)
+        m_dev, v_dev = bq._predict(x)
+        m_host = bq.gp_l.mean(x)
+        v_host = np.diag(bq.gp_log_l.cov(x))
+        assert_close(m_dev, m_host, "l_mean ns=%d" % ns, rtol=1e-9, atol=1e-12 * np.abs(m_host).max())
+        assert_close(v_dev, v_host, "v_log_l ns=%d" % ns, rtol=1e-9, atol=1e-10 * np.abs(v_host).max())
+        om = oracle.OracleModel(bq.x_s, bq.l_s, bq.x_c, bq.gp_log_l.params, bq.gp_l.params, float(bq.options["x_mean"][0]),
+                                float(bq.options["x_cov"][0, 0]), bq.options["candidate_thresh"])
+        _, c = om.gp_log_l_mean_cov(x)
+        assert_close(v_dev, c, "v_log_l vs oracle ns=%d" % ns, rtol=1e-9, atol=1e-10 * np.abs(c).max())
+        assert np.allclose(bq.l_mean(bq.x_s), bq.l_s, atol=1e-4)
+        lv = bq.l_var(x)
+        # v_log_l is a cancellation (k_tt - k^T K^-1 k -> 0 at the observations): compare by the absolute tolerance above
+        assert (lv >= 0).all()
+        assert np.allclose(lv, np.maximum(v_host * m_host ** 2, 0), rtol=1e-7, atol=1e-9 * np.abs(v_host).max() * (m_host ** 2).max())
+
+
 def test_device_resident_rounds_equal_the_host_rounds():
     """with the observations, the per-problem numpy-compatible MT19937 candidate streams, the candidate
     filter and add_observation on the GPU, every round gives bit-identical candidates, observations, chosen points
