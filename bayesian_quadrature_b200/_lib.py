@@ -51,6 +51,8 @@ SYMBOLS = {
     "bqb_argmin_pair_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp]),
     "bqb_choose_step_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _ll, _vp, _vp]),
     "bqb_argmin_rows_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp, _vp]),
+    "bqb_batch_set_cutoff": (ctypes.c_int, [_vp, ctypes.c_double]),
+    "bqb_batch_work_counter": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
     "bqb_launch_count": (ctypes.c_ulonglong, [_vp]),
     "bqb_model_doubles": (ctypes.c_int, [_vp]),
     "bqb_model_read": (ctypes.c_int, [_vp, ctypes.c_int, _dp]),
@@ -304,6 +306,16 @@ class Batch(object):
         """Per-instance (min, first index) of the CUDA tensor v [n_inst, n] into mins (float64) / idxs (int64)."""
         _check(load().bqb_argmin_rows_device(self._h, _ptr(v), v.stride(0), v.shape[1], _ptr(mins), _ptr(idxs),
                                              _vp(stream) if stream else None), "bqb_argmin_rows_device")
+
+    def set_cutoff(self, cut_arg):
+        """Relevance cut-off of the band skipping (default 72; float('inf') = dense algorithm)."""
+        _check(load().bqb_batch_set_cutoff(self._h, float(cut_arg)), "bqb_batch_set_cutoff")
+
+    def work_counter(self, enable=True):
+        """DMMA instructions executed since the last call (0 if the counter was off); (re)arms or disarms the counter."""
+        n = ctypes.c_ulonglong(0)
+        _check(load().bqb_batch_work_counter(self._h, int(bool(enable)), ctypes.byref(n)), "bqb_batch_work_counter")
+        return int(n.value)
 
     @property
     def launch_count(self):

@@ -2,6 +2,7 @@
 // Plain pointers and sizes only; no torch types.  Every entry point returns 0 on success,
 // a negative BQB_E* code for argument errors and a positive cudaError_t otherwise; the
 // message is kept per thread (bqb_last_error).
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,6 +59,9 @@ struct bqb_batch {
     unsigned *d_mt = nullptr;          // [624][n_inst] Mersenne-Twister words
     int *d_mti = nullptr, *d_overflow = nullptr;
     std::vector<int> h_ns, h_nc;
+    // scoring: relevance cut-off (bq_score.cu, CUT_ARG; +inf = dense) and the optional executed-work counter
+    double cut_arg = 72.0;
+    unsigned long long *d_work_ctr = nullptr;
     double *d_xs = nullptr, *d_ls = nullptr, *d_xc = nullptr, *d_hyp = nullptr, *d_prior = nullptr;
     // host-buffer scoring staging (grown on demand)
     double *d_xa = nullptr, *d_esm = nullptr, *d_em = nullptr;
@@ -125,6 +129,7 @@ int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     CU(cudaMalloc(&b->d_prior, sizeof(double) * (size_t)n_inst * 3));
     CU(cudaMalloc(&b->d_red_val, sizeof(double) * 4096));
     CU(cudaMalloc(&b->d_red_idx, sizeof(long long) * 4096));
+    if (getenv("BQB_DENSE") && atoi(getenv("BQB_DENSE"))) b->cut_arg = INFINITY;
     b->h_hdr.resize((size_t)n_inst * H_COUNT);
     b->h_ns.resize(n_inst);
     b->h_nc.resize(n_inst);
@@ -136,7 +141,7 @@ void bqb_batch_destroy(bqb_batch *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     void *ptrs[] = {b->d_models, b->d_tab, b->d_work, b->d_ns, b->d_nc, b->d_xs, b->d_ls, b->d_xc, b->d_hyp, b->d_prior,
-                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags, b->d_mt, b->d_mti, b->d_overflow};
+                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags, b->d_mt, b->d_mti, b->d_overflow, b->d_work_ctr};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaStream_t st : b->pipe) if (st) cudaStreamDestroy(st);
     if (b->h_flags) cudaFreeHost(b->h_flags);
@@ -325,6 +330,7 @@ int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int
     if (na == 0) return 0;
     CU(cudaSetDevice(b->device));
     ScoreArgs a;
+    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
     a.models = b->d_models; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = xa_stride; a.na = na;
     a.esm = d_esm; a.em = d_em; a.status = d_status; a.out_stride = out_stride; a.exp_tab = b->d_tab;
     a.flags = d_flags; a.ndb_max = b->ndb_max;
@@ -347,6 +353,7 @@ int bqb_predict_device(bqb_batch *b, const double *d_x, long long x_stride, int 
     if (na == 0) return 0;
     CU(cudaSetDevice(b->device));
     ScoreArgs a;
+    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
     a.models = b->d_models; a.lay = b->lay; a.x_a = d_x; a.xa_stride = x_stride; a.na = na;
     a.esm = d_l_mean; a.em = d_v_log_l; a.status = nullptr; a.out_stride = out_stride; a.exp_tab = b->d_tab;
     a.flags = nullptr; a.ndb_max = b->ndb_max; a.predict = 1;
@@ -459,6 +466,7 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
     CU(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->n_inst, b->pipe[0]));
     if (nchunk > 1) CU(cudaStreamSynchronize(b->pipe[0]));
     ScoreArgs a;
+    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
     a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.xa_stride = 0;
     a.em = nullptr; a.status = nullptr; a.exp_tab = b->d_tab; a.flags = b->d_flags; a.inst0 = 0; a.ndb_max = b->ndb_max;
     int c = 0;
@@ -543,6 +551,7 @@ int bqb_choose_step_device(bqb_batch *b, int inst, const double *d_x_a, int na, 
     CU(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
     ScoreArgs a;
+    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
     a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = 0; a.na = na;
     a.esm = d_esm; a.em = nullptr; a.status = nullptr; a.out_stride = na; a.exp_tab = b->d_tab; a.flags = nullptr;
     a.inst0 = 0; a.ndb_max = b->ndb_max;
@@ -564,6 +573,25 @@ int bqb_argmin_rows_device(bqb_batch *b, const double *d_v, long long stride, lo
 }
 
 unsigned long long bqb_launch_count(bqb_batch *b) { return b ? b->launches : 0; }
+
+int bqb_batch_set_cutoff(bqb_batch *b, double cut_arg) {
+    if (!b || !(cut_arg > 0)) return fail(BQB_EINVAL, "bqb_batch_set_cutoff: cut_arg must be positive (INFINITY = dense)");
+    b->cut_arg = cut_arg;
+    return 0;
+}
+
+int bqb_batch_work_counter(bqb_batch *b, int enable, unsigned long long *dmma_out) {
+    if (!b) return fail(BQB_EINVAL, "bqb_batch_work_counter: null batch");
+    CU(cudaSetDevice(b->device));
+    if (dmma_out) {
+        *dmma_out = 0;
+        if (b->d_work_ctr) CU(cudaMemcpy(dmma_out, b->d_work_ctr, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    }
+    if (enable && !b->d_work_ctr) CU(cudaMalloc(&b->d_work_ctr, sizeof(unsigned long long)));
+    if (b->d_work_ctr) CU(cudaMemset(b->d_work_ctr, 0, sizeof(unsigned long long)));
+    if (!enable && b->d_work_ctr) { cudaFree(b->d_work_ctr); b->d_work_ctr = nullptr; }
+    return 0;
+}
 
 int bqb_model_doubles(bqb_batch *b) { return b ? b->lay.total : 0; }
 

@@ -106,42 +106,107 @@ __device__ __forceinline__ void stage(double *dst, const double *__restrict__ sr
     for (int i = threadIdx.x; i < count / 2; i += THREADS) d2[i] = __ldg(s2 + i);
 }
 
-// Cross-kernel B fragments of one sub-tile: bf[ks][nt] = exp(-(x - x_s[k])^2 / (2 w^2)), k = 4 ks + (lane & 3).
-// Groups of 4 k-steps are branch free so that the 4 NT independent exp chains interleave.  TL additionally
-// accumulates gp_log_l.mean (bq.py:493) and pre-filters np.isclose(x_a, x_s, atol=1e-4) (bq.py:456): one integer
-// compare of the high word of d^2 against an upper bound of every tolerance^2 (non-negative doubles order like
-// their bits); the exact test runs afterwards only for the rare points that pass (isclose_exact).
-template <int KS, int NT, int TABN, bool TL>
-__device__ __forceinline__ void gen_fragments(double (&bf)[KS][NT], const double (&x)[NT], double C, int d2max_hi, int nks, int kq,
-                                              const double *s_xs, const double *s_atl, int tol2_hi,
-                                              const double *s_tab, double (&tm)[NT], int (&close)[NT]) {
+// Mask of the k-steps (4 observations each) of a sub-tile that are numerically relevant: bit ks.
+template <int KS> struct KMask { using type = unsigned; };
+template <> struct KMask<40> { using type = unsigned long long; };
+template <> struct KMask<64> { using type = unsigned long long; };
+
+// A cross-kernel element whose exponent lies more than CUT_ARG below the largest one of its own point is below
+// e^-72 = 5e-32 of that point's leading element: with cond(K) < 1e9 it cannot change any of the point's results at
+// double precision ("band skipping").  K-steps in which every element of the sub-tile is that small are
+// neither exponentiated nor multiplied.
+constexpr double CUT_ARG = 72.0;
+
+// Cross-kernel B fragments of one sub-tile: bf[ks][nt] = exp(-(x - x_s[k])^2 / (2 w^2)), k = 4 ks + (lane & 3), in two
+// passes.  Pass 1 computes every squared distance (2 FP64 operations per element) and, on the integer pipe, each
+// point's smallest one, from which the relevance threshold follows; a warp-wide OR (REDUX) of the lanes' masks gives
+// the sub-tile's k-step mask.  Pass 2 turns the squared distances of the relevant k-steps into exponentials (7 FP64 +
+// 6 integer instructions per element): groups of GK k-steps are branch free so that GK NT independent exp chains
+// interleave, and a group runs if any of its k-steps is relevant.  With SKIP = false every k-step is relevant.
+// TL additionally accumulates gp_log_l.mean (bq.py:493) and pre-filters np.isclose(x_a, x_s, atol=1e-4) (bq.py:456):
+// the high word of the point's smallest d^2 against an upper bound of every tolerance^2 (non-negative doubles order
+// like their bits); the exact test runs afterwards only for the rare points that pass (isclose_exact).
+template <int KS, int NT, int TABN, bool TL, bool SKIP>
+__device__ __forceinline__ typename KMask<KS>::type gen_fragments(double (&bf)[KS][NT], const double (&x)[NT], double C,
+                                                                   int d2max_hi, double cut_d2, int nks, int kq,
+                                                                   const double *s_xs, const double *s_atl, int tol2_hi,
+                                                                   const double *s_tab, double (&tm)[NT], int (&close)[NT]) {
+    using mask_t = typename KMask<KS>::type;
     // 8 independent exp chains per branch-free group: with one CTA of 8 warps per SM (two warps per scheduler) the
     // NT = 1 exp phase was latency bound at 4 (ncu: 47 % of its stalls on fixed-latency dependencies)
     constexpr int GK = (NT == 1) ? 8 : 4;
+    constexpr int NG = (KS + GK - 1) / GK;
+    // ---- pass 1: squared distances, per-point minimum (high words)
+    int minhi[NT];
 #pragma unroll
-    for (int g = 0; g < (KS + GK - 1) / GK; ++g) {
+    for (int nt = 0; nt < NT; ++nt) minhi[nt] = 0x7fffffff;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
         if (GK * g < nks) {
 #pragma unroll
             for (int j = 0; j < GK; ++j) {
                 const int ks = GK * g + j;
                 if (ks < KS) {
-                    const int k = 4 * ks + kq;
-                    const double xs = s_xs[k];
+                    const double xs = s_xs[4 * ks + kq];
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
                         const double d = x[nt] - xs;
                         const double d2 = d * d;
-                        const double e = exp_kernel<TABN>(d2, C, d2max_hi, s_tab);
-                        bf[ks][nt] = e;
-                        if (TL) {
-                            close[nt] |= (__double2hiint(d2) <= tol2_hi);
-                            tm[nt] = fma(s_atl[k], e, tm[nt]);
-                        }
+                        bf[ks][nt] = d2;
+                        minhi[nt] = min(minhi[nt], __double2hiint(d2));
                     }
                 }
             }
         }
     }
+    mask_t mask;
+    if constexpr (SKIP || TL) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            minhi[nt] = min(minhi[nt], __shfl_xor_sync(0xffffffffu, minhi[nt], 1));
+            minhi[nt] = min(minhi[nt], __shfl_xor_sync(0xffffffffu, minhi[nt], 2));
+            if (TL) close[nt] = (minhi[nt] <= tol2_hi);
+        }
+    }
+    if constexpr (SKIP) {
+        int thr[NT];                                 // high word of (smallest d^2 of the point) + CUT_ARG / |nh|, rounded up
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) thr[nt] = __double2hiint(__hiloint2double(minhi[nt], 0) + cut_d2) + 1;
+        unsigned lm0 = 0, lm1 = 0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            bool act = false;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) act |= (__double2hiint(bf[ks][nt]) <= thr[nt]);
+            if (ks < 32) lm0 |= act ? (1u << ks) : 0u;
+            else lm1 |= act ? (1u << (ks - 32)) : 0u;
+        }
+        lm0 = __reduce_or_sync(0xffffffffu, lm0);
+        if (KS > 32) lm1 = __reduce_or_sync(0xffffffffu, lm1);
+        mask = (mask_t)lm0 | ((mask_t)lm1 << (KS > 32 ? 32 : 0));
+        mask &= (nks >= (int)(8 * sizeof(mask_t))) ? ~(mask_t)0 : (((mask_t)1 << nks) - 1);      // k-steps past nks hold garbage
+    } else {
+        mask = (nks >= (int)(8 * sizeof(mask_t))) ? ~(mask_t)0 : (((mask_t)1 << nks) - 1);
+    }
+    // ---- pass 2: exponentials of the relevant groups
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        if ((mask >> (GK * g)) & (((mask_t)1 << GK) - 1)) {
+#pragma unroll
+            for (int j = 0; j < GK; ++j) {
+                const int ks = GK * g + j;
+                if (ks < KS) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        const double e = exp_kernel<TABN>(bf[ks][nt], C, d2max_hi, s_tab);
+                        bf[ks][nt] = e;
+                        if (TL) tm[nt] = fma(s_atl[4 * ks + kq], e, tm[nt]);
+                    }
+                }
+            }
+        }
+    }
+    return mask;
 }
 
 // Exact np.isclose(x_a, x_s, atol=1e-4): |x_a - x_s[k]| <= 1e-4 + 1e-5 |x_s[k]| for this lane's k residues (padded
@@ -161,7 +226,8 @@ template <int N> __device__ __forceinline__ void async_wait() { asm volatile("cp
 // around it can stay rolled: the instruction footprint is KS DMMAs, not KS^2/2.
 template <int KS, int NT>
 __device__ __forceinline__ void row_block(const double *af, int lim, const double (&bf)[KS][NT], double (&q0)[NT],
-                                          double (&q1)[NT]) {
+                                          double (&q1)[NT], typename KMask<KS>::type mask) {
+    using mask_t = typename KMask<KS>::type;
     constexpr bool DUAL = (NT == 1);    // NT == 1: split even / odd k-steps into two chains to cover the DMMA latency
     double c0[NT], c1[NT], e0[NT], e1[NT];
 #pragma unroll
@@ -169,12 +235,14 @@ __device__ __forceinline__ void row_block(const double *af, int lim, const doubl
 #pragma unroll
     for (int ks = 0; ks < KS; ks += 2) {
         if (ks >= lim) break;
-        const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
+        if (mask & ((mask_t)3 << ks)) {              // warp-uniform: a relevant k-step in this pair
+            const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
-            if (DUAL) dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);
-            else dmma(c0[nt], c1[nt], a1, bf[ks + 1][nt]);
+            for (int nt = 0; nt < NT; ++nt) {
+                dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
+                if (DUAL) dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);
+                else dmma(c0[nt], c1[nt], a1, bf[ks + 1][nt]);
+            }
         }
     }
 #pragma unroll
@@ -192,7 +260,8 @@ __device__ __forceinline__ void row_block(const double *af, int lim, const doubl
 // limA = k-steps of the first row block (2 rb + 2); the second one has two more.
 template <int KS, int NT>
 __device__ __forceinline__ void row_block_pair(const double *afA, const double *afB, int limA, const double (&bf)[KS][NT],
-                                               double (&q0)[NT], double (&q1)[NT]) {
+                                               double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask) {
+    using mask_t = typename KMask<KS>::type;
     static_assert(KS % 4 == 0, "k-steps come in groups of 4");
     double a0[NT], a1[NT], b0[NT], b1[NT], c0[NT], c1[NT], d0[NT], d1[NT];   // (a, b): block A even / odd k; (c, d): block B
 #pragma unroll
@@ -200,6 +269,7 @@ __device__ __forceinline__ void row_block_pair(const double *afA, const double *
 #pragma unroll
     for (int ks = 0; ks < KS; ks += 4) {
         if (ks >= limA + 2) break;           // both row blocks are complete
+        if (!(mask & ((mask_t)15 << ks))) continue;                // warp-uniform: nothing relevant in these four k-steps
         if (ks + 4 <= limA) {
             double fa[4], fb[4];
 #pragma unroll
@@ -251,26 +321,46 @@ __device__ __forceinline__ void row_block_pair(const double *afA, const double *
 // Row blocks [rb0, rb1) of a triangular operand whose fragment (rb, ks) sits at base[(tri_frags(rb) + ks) * 32]
 template <int KS, int NT>
 __device__ __forceinline__ void row_blocks_rolled(const double *base, int rb0, int rb1, const double (&bf)[KS][NT],
-                                                  double (&q0)[NT], double (&q1)[NT]) {
+                                                  double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask) {
+    using mask_t = typename KMask<KS>::type;
     int rb = rb0;
 #pragma unroll 1
-    for (; rb + 1 < rb1; rb += 2)
-        row_block_pair<KS, NT>(base + tri_frags(rb) * 32, base + tri_frags(rb + 1) * 32, 2 * rb + 2, bf, q0, q1);
-    if (rb < rb1) row_block<KS, NT>(base + tri_frags(rb) * 32, 2 * rb + 2, bf, q0, q1);
+    for (; rb + 1 < rb1; rb += 2) {
+        // rows above the first relevant k-step see none of it (lower-triangular operand): 2 rb + 4 k-steps at most
+        if (2 * rb + 4 < (int)(8 * sizeof(mask_t)) && !(mask & (((mask_t)1 << (2 * rb + 4)) - 1))) continue;
+        row_block_pair<KS, NT>(base + tri_frags(rb) * 32, base + tri_frags(rb + 1) * 32, 2 * rb + 2, bf, q0, q1, mask);
+    }
+    if (rb < rb1) row_block<KS, NT>(base + tri_frags(rb) * 32, 2 * rb + 2, bf, q0, q1, mask);
+}
+
+// (row block, k-step) products a triangular pass executes for a relevance mask: sum over row blocks rb < nb of
+// popc(mask & low(2 rb + 2)), at the pair granularity of the DMMA loops.  Only used for the work counter.
+template <int KS>
+__device__ __forceinline__ unsigned count_ksteps(typename KMask<KS>::type mask, int nb) {
+    unsigned long long m = mask;
+    m = (m | (m >> 1)) & 0x5555555555555555ull;              // a pair runs if either k-step is relevant ...
+    m |= m << 1;                                             // ... and then both are multiplied
+    unsigned n = 0;
+    for (int rb = 0; rb < nb; ++rb) n += __popcll(2 * rb + 2 >= 64 ? m : (m & ((1ull << (2 * rb + 2)) - 1)));
+    return n;
 }
 
 // Lower-triangular pass with shared-memory resident operands: q += (rows of (A . B))^2.
 // ROLLED = false unrolls the row-block loop as well (exact trip counts, no early-exit branches).
 template <int KS, int NT, bool ALIGN, bool ROLLED>
 __device__ __forceinline__ void tri_pass(const double *af_res, const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT],
-                                         int nb, int lane) {
+                                         int nb, int lane, typename KMask<KS>::type mask) {
+    using mask_t = typename KMask<KS>::type;
     if (ALIGN) __syncthreads();                                 // all warps of the CTA enter the DMMA phase together
     if constexpr (ROLLED) {
-        row_blocks_rolled<KS, NT>(af_res + lane, 0, nb, bf, q0, q1);
+        row_blocks_rolled<KS, NT>(af_res + lane, 0, nb, bf, q0, q1, mask);
     } else {
 #pragma unroll
-        for (int rb = 0; rb < KS / 2; ++rb)        // lim is a compile-time constant after unrolling: the early exit folds away
-            if (rb < nb) row_block<KS, NT>(af_res + tri_frags(rb) * 32 + lane, 2 * rb + 2, bf, q0, q1);
+        for (int rb = 0; rb < KS / 2; ++rb) {      // lim is a compile-time constant after unrolling: the early exit folds away
+            constexpr int BITS = 8 * sizeof(mask_t);
+            const mask_t low = (2 * rb + 2 >= BITS) ? ~(mask_t)0 : (((mask_t)1 << (2 * rb + 2)) - 1);
+            if (rb < nb && (mask & low)) row_block<KS, NT>(af_res + tri_frags(rb) * 32 + lane, 2 * rb + 2, bf, q0, q1, mask);
+        }
     }
 }
 
@@ -300,7 +390,8 @@ __device__ __forceinline__ void tri_stream_begin(const double *__restrict__ af_g
 }
 template <int KS, int NT>
 __device__ __forceinline__ void tri_stream_run(const double *__restrict__ af_gmem, Stream &st, const double (&bf)[KS][NT],
-                                               double (&q0)[NT], double (&q1)[NT], int nb, int lane) {
+                                               double (&q0)[NT], double (&q1)[NT], int nb, int lane,
+                                               typename KMask<KS>::type mask) {
     int rb0 = 0, rb1 = st.chk[1], cur = 0, ci = 0;
     while (rb0 < nb) {
         const int rb2 = st.chk[ci + 2];
@@ -313,7 +404,7 @@ __device__ __forceinline__ void tri_stream_run(const double *__restrict__ af_gme
             bulk_g2s(st.buf + (cur ^ 1) * st.stride, af_gmem + tri_frags(rb1) * 32, bytes, st.bar + (cur ^ 1));
         }
         const double *base = st.buf + cur * st.stride - tri_frags(rb0) * 32 + lane;
-        row_blocks_rolled<KS, NT>(base, rb0, rb1, bf, q0, q1);
+        row_blocks_rolled<KS, NT>(base, rb0, rb1, bf, q0, q1, mask);
         rb0 = rb1; rb1 = rb2; cur ^= 1; ++ci;
     }
     __syncthreads();                                            // both buffers are free again (next pass)
@@ -384,6 +475,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     const double nhl = s_small[H_NHL];
     const double Cl = nhl * ExpC<TABN>::INVN, Ctl = s_small[H_NHTL] * ExpC<TABN>::INVN;   // exponent scale in table units
     const int dmax_l = exp_d2max_hi(nhl), dmax_tl = exp_d2max_hi(s_small[H_NHTL]);
+    using mask_t = typename KMask<KS>::type;
+    // relevance threshold in units of d^2 (a.cut_arg = CUT_ARG, or +inf: every k-step is relevant, the dense algorithm)
+    const double cut_l = a.cut_arg / fabs(nhl), cut_tl = a.cut_arg / fabs(s_small[H_NHTL]);
+    unsigned long long n_kstep = 0;                         // (row block, k-step) products executed by this warp (a.work)
     const int tol2_hi = __double2hiint(s_small[H_TOL2MAX]) + 1;
     double *scr = s_scr + warp * SM::scr(a.ndb_max);        // rows: 0 qs, 1 qt, 2 tm, 3 isclose, 4.. dense rows, then x_a
 
@@ -448,9 +543,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
             // ---- phase L: K_l cross-kernel fragments, triangular rows then the dense candidate / g rows
             if (ALIGN) __syncthreads();                  // ... and the exp phase together (DMMA / DFMA mixing costs pipe throughput)
             if constexpr (STREAM) tri_stream_begin(M + lay.off_af_l_tri, strm);
-            gen_fragments<KS, NT, TABN, false>(bf, x, Cl, dmax_l, nks, kq, s_xs, s_atl, tol2_hi, s_tab, tm, close);
-            if constexpr (STREAM) tri_stream_run<KS, NT>(M + lay.off_af_l_tri, strm, bf, q0, q1, nb, lane);
-            else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_l, bf, q0, q1, nb, lane);
+            mask_t mask = gen_fragments<KS, NT, TABN, false, true>(bf, x, Cl, dmax_l, cut_l, nks, kq, s_xs, s_atl, tol2_hi, s_tab, tm, close);
+            if constexpr (STREAM) tri_stream_run<KS, NT>(M + lay.off_af_l_tri, strm, bf, q0, q1, nb, lane, mask);
+            else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_l, bf, q0, q1, nb, lane, mask);
+            if (a.work) n_kstep += count_ksteps<KS>(mask, nb) + ndb * __popcll((unsigned long long)mask);
 #pragma unroll
             for (int db = 0; db < 3; ++db) {
                 if (db < ndb) {
@@ -460,7 +556,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                     for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
 #pragma unroll
                     for (int ks = 0; ks < KS; ks += 2) {
-                        if (ks < nks) {                  // nks is even
+                        if (ks < nks && (mask & ((mask_t)3 << ks))) {      // nks is even; warp-uniform relevance test
                             const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
 #pragma unroll
                             for (int nt = 0; nt < NT; ++nt) {
@@ -482,12 +578,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
             for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
             if (ALIGN) __syncthreads();
             if constexpr (STREAM) tri_stream_begin(M + lay.off_af_tl_tri, strm);
-            gen_fragments<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, nks, kq, s_xs, s_atl, tol2_hi, s_tab, tm, close);
+            mask = gen_fragments<KS, NT, TABN, true, true>(bf, x, Ctl, dmax_tl, cut_tl, nks, kq, s_xs, s_atl, tol2_hi, s_tab, tm, close);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
                 if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
-            if constexpr (STREAM) tri_stream_run<KS, NT>(M + lay.off_af_tl_tri, strm, bf, q0, q1, nb, lane);
-            else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane);
+            if constexpr (STREAM) tri_stream_run<KS, NT>(M + lay.off_af_tl_tri, strm, bf, q0, q1, nb, lane, mask);
+            else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane, mask);
+            if (a.work) n_kstep += count_ksteps<KS>(mask, nb);
             park_q<NT>(q0, q1, scr, 1, col0, kq, pq);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
@@ -622,6 +719,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
         }
         __syncwarp();
     }
+    if (a.work && lane == 0 && n_kstep) atomicAdd(a.work, n_kstep * NT);     // DMMA instructions of this warp
     if (EPI) {                                              // (min, first index) of this CTA's points
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

@@ -528,7 +528,8 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) bq_setup_kernel(SetupArgs a)
     }
     for (int i = tid; i < lay.nsp_cap; i += SETUP_THREADS) {
         const bool in = i < ns;
-        M[lay.off_xs + i] = in ? x_s[i] : 0.0;                           // padded: finite value x zero operand columns
+        M[lay.off_xs + i] = in ? x_s[i] : 1e150;                         // padded: far away (d^2 = 1e300 stays finite, never the
+                                                                         // nearest observation of a point) x zero operand columns
         M[lay.off_tol + i] = in ? 1e-4 + 1e-5 * fabs(x_s[i]) : -1.0;     // np.isclose(x_a, x_s, atol=1e-4), rtol 1e-5
         M[lay.off_atl + i] = in ? c_tl * a_tl[i] : 0.0;
     }

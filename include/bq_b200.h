@@ -178,6 +178,17 @@ int bqb_choose_step_device(bqb_batch *b, int inst, const double *d_x_a, int na, 
 int bqb_argmin_rows_device(bqb_batch *b, const double *d_v, long long stride, long long n, double *d_min,
                            long long *d_idx, void *stream);
 
+/* Band skipping: a cross-kernel element exp(-(x_a - x_s[k])^2 / 2w^2) whose exponent lies more than
+ * cut_arg below the largest one of its own query point is treated as zero, and groups of four observations in which
+ * every element of a 16-point sub-tile is that small are neither exponentiated nor multiplied.  Default 72
+ * (e^-72 = 5e-32 of the point's leading element: below double-precision relevance for cond(K) < 1e9);
+ * INFINITY (or the environment variable BQB_DENSE=1 at batch creation) runs the dense algorithm. */
+int bqb_batch_set_cutoff(bqb_batch *b, double cut_arg);
+/* Executed-work counter of the scoring kernel: returns in *dmma_out (may be NULL) the number of DMMA.8x8x4
+ * instructions (512 flop each) executed by the launches since the last call, then clears it; enable = 1 keeps
+ * counting (a few integer instructions per sub-tile), enable = 0 switches it off (the default). */
+int bqb_batch_work_counter(bqb_batch *b, int enable, unsigned long long *dmma_out);
+
 /* Introspection for tests and the bench harness. */
 unsigned long long bqb_launch_count(bqb_batch *b);   /* kernels launched through this batch so far */
 int bqb_model_doubles(bqb_batch *b);                  /* size of one device model block */
