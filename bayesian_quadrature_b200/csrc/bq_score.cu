@@ -33,13 +33,6 @@ namespace bqb {
 // launch_score picks the largest size (<= CHUNK_FRAGS_MAX) that fits next to the resident pieces.
 constexpr int CHUNK_FRAGS_MAX = 256;
 
-// STREAM: row blocks [rb0, end) whose fragments fit one chunk buffer (always at least one row block)
-__device__ __forceinline__ int chunk_end_rb(int rb0, int nb, int chunk_frags) {
-    int used = 0, r = rb0;
-    while (r < nb && (r == rb0 || used + 2 * r + 2 <= chunk_frags)) { used += 2 * r + 2; ++r; }
-    return r;
-}
-
 // ---- mbarrier + bulk-copy (TMA) primitives of the operand stream
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
@@ -117,35 +110,29 @@ template <> struct KMask<64> { using type = unsigned long long; };
 // neither exponentiated nor multiplied.
 constexpr double CUT_ARG = 72.0;
 
-// Cross-kernel B fragments of one sub-tile: bf[ks][nt] = exp(-(x - x_s[k])^2 / (2 w^2)), k = 4 ks + (lane & 3), in two
-// passes.  Pass 1 computes every squared distance (2 FP64 operations per element) and, on the integer pipe, each
-// point's smallest one, from which the relevance threshold follows; a warp-wide OR (REDUX) of the lanes' masks gives
-// the sub-tile's k-step mask.  Pass 2 turns the squared distances of the relevant k-steps into exponentials (7 FP64 +
-// 6 integer instructions per element): groups of GK k-steps are branch free so that GK NT independent exp chains
-// interleave, and a group runs if any of its k-steps is relevant.  With SKIP = false every k-step is relevant.
-// TL additionally accumulates gp_log_l.mean (bq.py:493) and pre-filters np.isclose(x_a, x_s, atol=1e-4) (bq.py:456):
-// the high word of the point's smallest d^2 against an upper bound of every tolerance^2 (non-negative doubles order
-// like their bits); the exact test runs afterwards only for the rare points that pass (isclose_exact).
-template <int KS, int NT, int TABN, bool TL, bool SKIP>
-__device__ __forceinline__ typename KMask<KS>::type gen_fragments(double (&bf)[KS][NT], const double (&x)[NT], double C,
-                                                                   int d2max_hi, double cut_d2, int nks, int kq,
-                                                                   const double *s_xs, const double *s_atl, int tol2_hi,
-                                                                   const double *s_tab, double (&tm)[NT], int (&close)[NT]) {
+// Cross-kernel B fragments of one sub-tile, bf[ks][nt] = exp(-(x - x_s[k])^2 / (2 w^2)), k = 4 ks + (lane & 3), are
+// produced in two steps.
+//
+// gen_masks (once per sub-tile, serves both kernels -- the distances are the same, only the widths differ): every squared
+// distance (2 FP64 operations per element, left in bf), on the integer pipe each point's smallest one, from which the two
+// relevance thresholds follow, and a warp-wide OR (REDUX) of the lanes' bit masks: the sub-tile's relevant k-steps under
+// K_l and under K_tl.  It also pre-filters np.isclose(x_a, x_s, atol=1e-4) (bq.py:456): the high word of the point's
+// smallest d^2 against an upper bound of every tolerance^2 (non-negative doubles order like their bits); the exact test
+// runs afterwards only for the rare points that pass (isclose_exact).
+template <int KS, int NT>
+__device__ __forceinline__ void gen_masks(double (&bf)[KS][NT], const double (&x)[NT], double cut_l, double cut_tl, int nks, int kq,
+                                          const double *s_xs, int tol2_hi, int (&close)[NT], typename KMask<KS>::type &mask_l,
+                                          typename KMask<KS>::type &mask_tl) {
     using mask_t = typename KMask<KS>::type;
-    // 8 independent exp chains per branch-free group: with one CTA of 8 warps per SM (two warps per scheduler) the
-    // NT = 1 exp phase was latency bound at 4 (ncu: 47 % of its stalls on fixed-latency dependencies)
-    constexpr int GK = (NT == 1) ? 8 : 4;
-    constexpr int NG = (KS + GK - 1) / GK;
-    // ---- pass 1: squared distances, per-point minimum (high words)
     int minhi[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) minhi[nt] = 0x7fffffff;
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        if (GK * g < nks) {
+    for (int g = 0; g < (KS + 3) / 4; ++g) {
+        if (4 * g < nks) {
 #pragma unroll
-            for (int j = 0; j < GK; ++j) {
-                const int ks = GK * g + j;
+            for (int j = 0; j < 4; ++j) {
+                const int ks = 4 * g + j;
                 if (ks < KS) {
                     const double xs = s_xs[4 * ks + kq];
 #pragma unroll
@@ -159,46 +146,63 @@ __device__ __forceinline__ typename KMask<KS>::type gen_fragments(double (&bf)[K
             }
         }
     }
-    mask_t mask;
-    if constexpr (SKIP || TL) {
+    int thr_l[NT], thr_tl[NT];                       // high word of (smallest d^2 of the point) + CUT_ARG / |nh|, rounded up
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        minhi[nt] = min(minhi[nt], __shfl_xor_sync(0xffffffffu, minhi[nt], 1));
+        minhi[nt] = min(minhi[nt], __shfl_xor_sync(0xffffffffu, minhi[nt], 2));
+        close[nt] = (minhi[nt] <= tol2_hi);
+        const double dmin = __hiloint2double(minhi[nt], 0);
+        thr_l[nt] = __double2hiint(dmin + cut_l) + 1;
+        thr_tl[nt] = __double2hiint(dmin + cut_tl) + 1;
+    }
+    unsigned l0 = 0, l1 = 0, t0 = 0, t1 = 0;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        bool al = false, at = false;
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
-            minhi[nt] = min(minhi[nt], __shfl_xor_sync(0xffffffffu, minhi[nt], 1));
-            minhi[nt] = min(minhi[nt], __shfl_xor_sync(0xffffffffu, minhi[nt], 2));
-            if (TL) close[nt] = (minhi[nt] <= tol2_hi);
+            const int h = __double2hiint(bf[ks][nt]);
+            al |= (h <= thr_l[nt]);
+            at |= (h <= thr_tl[nt]);
         }
+        if (ks < 32) { l0 |= al ? (1u << ks) : 0u; t0 |= at ? (1u << ks) : 0u; }
+        else { l1 |= al ? (1u << (ks - 32)) : 0u; t1 |= at ? (1u << (ks - 32)) : 0u; }
     }
-    if constexpr (SKIP) {
-        int thr[NT];                                 // high word of (smallest d^2 of the point) + CUT_ARG / |nh|, rounded up
+    l0 = __reduce_or_sync(0xffffffffu, l0);
+    t0 = __reduce_or_sync(0xffffffffu, t0);
+    if (KS > 32) { l1 = __reduce_or_sync(0xffffffffu, l1); t1 = __reduce_or_sync(0xffffffffu, t1); }
+    const mask_t valid = (nks >= (int)(8 * sizeof(mask_t))) ? ~(mask_t)0 : (((mask_t)1 << nks) - 1);   // k-steps past nks hold garbage
+    mask_l = ((mask_t)l0 | ((mask_t)l1 << (KS > 32 ? 32 : 0))) & valid;
+    mask_tl = ((mask_t)t0 | ((mask_t)t1 << (KS > 32 ? 32 : 0))) & valid;
+}
+
+// gen_exps turns the squared distances of the relevant k-steps into exponentials (7 FP64 + 6 integer instructions per
+// element): groups of GK k-steps are branch free so that GK NT independent exp chains interleave, and a group runs if
+// any of its k-steps is relevant.  The K_l pass finds the squared distances in bf; the K_tl pass recomputes them (bf
+// holds K_l values by then) and accumulates gp_log_l.mean (bq.py:493).
+template <int KS, int NT, int TABN, bool TL>
+__device__ __forceinline__ void gen_exps(double (&bf)[KS][NT], const double (&x)[NT], double C, int d2max_hi,
+                                         typename KMask<KS>::type mask, int kq, const double *s_xs, const double *s_atl,
+                                         const double *s_tab, double (&tm)[NT]) {
+    using mask_t = typename KMask<KS>::type;
+    // 8 independent exp chains per branch-free group: with one CTA of 8 warps per SM (two warps per scheduler) the
+    // NT = 1 exp phase was latency bound at 4 (ncu: 47 % of its stalls on fixed-latency dependencies)
+    constexpr int GK = (NT == 1) ? 8 : 4;
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) thr[nt] = __double2hiint(__hiloint2double(minhi[nt], 0) + cut_d2) + 1;
-        unsigned lm0 = 0, lm1 = 0;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            bool act = false;
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) act |= (__double2hiint(bf[ks][nt]) <= thr[nt]);
-            if (ks < 32) lm0 |= act ? (1u << ks) : 0u;
-            else lm1 |= act ? (1u << (ks - 32)) : 0u;
-        }
-        lm0 = __reduce_or_sync(0xffffffffu, lm0);
-        if (KS > 32) lm1 = __reduce_or_sync(0xffffffffu, lm1);
-        mask = (mask_t)lm0 | ((mask_t)lm1 << (KS > 32 ? 32 : 0));
-        mask &= (nks >= (int)(8 * sizeof(mask_t))) ? ~(mask_t)0 : (((mask_t)1 << nks) - 1);      // k-steps past nks hold garbage
-    } else {
-        mask = (nks >= (int)(8 * sizeof(mask_t))) ? ~(mask_t)0 : (((mask_t)1 << nks) - 1);
-    }
-    // ---- pass 2: exponentials of the relevant groups
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
+    for (int g = 0; g < (KS + GK - 1) / GK; ++g) {
         if ((mask >> (GK * g)) & (((mask_t)1 << GK) - 1)) {
 #pragma unroll
             for (int j = 0; j < GK; ++j) {
                 const int ks = GK * g + j;
                 if (ks < KS) {
+                    double xs = 0.0;
+                    if (TL) xs = s_xs[4 * ks + kq];
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
-                        const double e = exp_kernel<TABN>(bf[ks][nt], C, d2max_hi, s_tab);
+                        double d2 = bf[ks][nt];
+                        if (TL) { const double d = x[nt] - xs; d2 = d * d; }
+                        const double e = exp_kernel<TABN>(d2, C, d2max_hi, s_tab);
                         bf[ks][nt] = e;
                         if (TL) tm[nt] = fma(s_atl[4 * ks + kq], e, tm[nt]);
                     }
@@ -206,7 +210,6 @@ __device__ __forceinline__ typename KMask<KS>::type gen_fragments(double (&bf)[K
             }
         }
     }
-    return mask;
 }
 
 // Exact np.isclose(x_a, x_s, atol=1e-4): |x_a - x_s[k]| <= 1e-4 + 1e-5 |x_s[k]| for this lane's k residues (padded
@@ -364,50 +367,82 @@ __device__ __forceinline__ void tri_pass(const double *af_res, const double (&bf
     }
 }
 
-// Streamed variant (operands do not fit in shared memory): chunks of whole row blocks move global (L2) -> shared
-// with ONE bulk-copy (TMA) instruction issued by one thread and completing on an mbarrier, into two alternating
-// buffers; the copy of chunk i+1 is in flight while the CTA's warps run the DMMAs of chunk i.  (The first version
-// staged chunks with per-thread cp.async: ~16 LDGSTS + address arithmetic per thread and chunk, each LDGSTS batch
-// preceded by three dummy LDS in the SASS, and two CTA barriers per chunk.)
-// The chunk boundaries depend only on nb: s_chk[i] = first row block of chunk i (padded with nb), tabulated once per
-// CTA -- recomputing them in every pass cost as many instructions as the exponentials.
-constexpr int CHUNK_TAB = 40;
+// Streamed variant (operands do not fit in shared memory).  Only the *band slab* of a triangular operand is needed for
+// a sub-tile: the row blocks rb >= klo / 2 and, of each, the k-steps [klo, khi) that are relevant for any warp of the
+// CTA (klo aligned to the 4-k-step groups of the DMMA loops).  A slab chunk is up to R such row blocks, each one bulk
+// copy (TMA) of W = khi - klo fragments issued by one lane of warp 0 and completing, in bytes, on the buffer's mbarrier;
+// two chunk buffers alternate, so that the next chunk (of this operand or of the next one) lands while the CTA's warps
+// run the DMMAs of the current one.  A row block that reaches its diagonal before khi copies a few fragments of the
+// next row block (same array, unused).  With every k-step relevant this degenerates to streaming whole rows.
+// (History: per-thread cp.async staging cost ~16 LDGSTS + address arithmetic per thread and chunk, each LDGSTS batch
+// preceded by three dummy LDS in the SASS, and two CTA barriers per chunk; whole-operand TMA chunks were latency
+// bound once band skipping had removed most of the arithmetic.)
+struct SlabPlan {
+    int klo, W, rb_first, R, nchunk;
+};
+template <int KS>
+__device__ __forceinline__ SlabPlan make_slab_plan(typename KMask<KS>::type um, int nks, int nb, int cap_frags) {
+    SlabPlan p;
+    if (um == 0) { p.klo = p.W = p.rb_first = p.R = p.nchunk = 0; return p; }
+    const unsigned long long m = um;
+    const int lo = __ffsll((long long)m) - 1, hi = 64 - __clzll((long long)m);      // relevant k-steps lie in [lo, hi)
+    p.klo = lo & ~3;
+    const int khi = min((hi + 3) & ~3, nks);
+    p.W = khi - p.klo;
+    p.rb_first = p.klo >> 1;                          // even: row blocks are consumed in pairs
+    p.R = max(2, (cap_frags / p.W) & ~1);
+    p.nchunk = (nb - p.rb_first + p.R - 1) / p.R;
+    return p;
+}
 struct Stream {
     unsigned long long *bar;      // [2] "chunk landed" barriers, one per buffer
-    const int *chk;               // chunk table
     double *buf;                  // two buffers of `stride` doubles
     int stride;
     unsigned phase;               // bit b: parity to wait for on buffer b
 };
-// first chunk of a pass into buffer 0; called before the exp phase so that it lands underneath it.  Every thread has
-// left the previous pass (CTA barrier at the end of tri_stream_run), so buffer 0 is free.
-__device__ __forceinline__ void tri_stream_begin(const double *__restrict__ af_gmem, const Stream &st) {
-    if (threadIdx.x == 0) {
-        const unsigned bytes = tri_frags(st.chk[1]) * 256;
-        mbar_expect_tx(st.bar, bytes);
-        bulk_g2s(st.buf, af_gmem, bytes, st.bar);
-    }
+// warp 0, all lanes: issue slab chunk c of `op` into buffer `b`
+__device__ __forceinline__ void slab_issue(const double *__restrict__ op, const SlabPlan &p, int c, int nb, const Stream &st, int b,
+                                           int lane) {
+    const int rb0 = p.rb_first + c * p.R, n = min(nb - rb0, p.R);
+    if (lane == 0) mbar_expect_tx(st.bar + b, (unsigned)(n * p.W * 256));
+    __syncwarp();
+    if (lane < n)
+        bulk_g2s(st.buf + b * st.stride + lane * p.W * 32, op + (size_t)(tri_frags(rb0 + lane) + p.klo) * 32, (unsigned)(p.W * 256),
+                 st.bar + b);
 }
+// row blocks [rb0, rb1) of a slab chunk that starts at row block rb0
 template <int KS, int NT>
-__device__ __forceinline__ void tri_stream_run(const double *__restrict__ af_gmem, Stream &st, const double (&bf)[KS][NT],
-                                               double (&q0)[NT], double (&q1)[NT], int nb, int lane,
-                                               typename KMask<KS>::type mask) {
-    int rb0 = 0, rb1 = st.chk[1], cur = 0, ci = 0;
-    while (rb0 < nb) {
-        const int rb2 = st.chk[ci + 2];
-        mbar_wait(st.bar + cur, (st.phase >> cur) & 1u);        // chunk `cur` has landed
-        st.phase ^= 1u << cur;
-        __syncthreads();                                        // everybody is done with chunk cur ^ 1 ...
-        if (rb1 < nb && threadIdx.x == 0) {                     // ... so its buffer takes the next chunk while this one is consumed
-            const unsigned bytes = (tri_frags(rb2) - tri_frags(rb1)) * 256;
-            mbar_expect_tx(st.bar + (cur ^ 1), bytes);
-            bulk_g2s(st.buf + (cur ^ 1) * st.stride, af_gmem + tri_frags(rb1) * 32, bytes, st.bar + (cur ^ 1));
-        }
-        const double *base = st.buf + cur * st.stride - tri_frags(rb0) * 32 + lane;
-        row_blocks_rolled<KS, NT>(base, rb0, rb1, bf, q0, q1, mask);
-        rb0 = rb1; rb1 = rb2; cur ^= 1; ++ci;
+__device__ __forceinline__ void slab_rows(const double *buf, const SlabPlan &p, int rb0, int rb1, const double (&bf)[KS][NT],
+                                          double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask, int lane) {
+    using mask_t = typename KMask<KS>::type;
+    int rb = rb0;
+#pragma unroll 1
+    for (; rb + 1 < rb1; rb += 2) {
+        if (2 * rb + 4 < (int)(8 * sizeof(mask_t)) && !(mask & (((mask_t)1 << (2 * rb + 4)) - 1))) continue;
+        const double *afA = buf + ((rb - rb0) * p.W - p.klo) * 32 + lane;       // afA[ks * 32] = fragment (rb, ks)
+        row_block_pair<KS, NT>(afA, afA + p.W * 32, 2 * rb + 2, bf, q0, q1, mask);
     }
-    __syncthreads();                                            // both buffers are free again (next pass)
+    if (rb < rb1) row_block<KS, NT>(buf + ((rb - rb0) * p.W - p.klo) * 32 + lane, 2 * rb + 2, bf, q0, q1, mask);
+}
+// One operand's part of the sub-tile's chunk sequence: chunks [seq0, seq0 + p.nchunk) of `ntot`; chunk s lives in buffer
+// s & 1 and chunk s + 2 is issued (from `op` or, past this operand's end, from `op_next`) once every warp is done with s.
+template <int KS, int NT>
+__device__ __forceinline__ void slab_pass(const double *__restrict__ op, const SlabPlan &p, const double *__restrict__ op_next,
+                                          const SlabPlan &p_next, int seq0, int ntot, Stream &st, const double (&bf)[KS][NT],
+                                          double (&q0)[NT], double (&q1)[NT], int nb, int lane, int warp,
+                                          typename KMask<KS>::type mask) {
+    for (int c = 0; c < p.nchunk; ++c) {
+        const int sq = seq0 + c, b = sq & 1;
+        mbar_wait(st.bar + b, (st.phase >> b) & 1u);            // the chunk has landed
+        st.phase ^= 1u << b;
+        const int rb0 = p.rb_first + c * p.R;
+        slab_rows<KS, NT>(st.buf + b * st.stride, p, rb0, min(nb, rb0 + p.R), bf, q0, q1, mask, lane);
+        __syncthreads();                                        // every warp is done with buffer b
+        if (warp == 0 && sq + 2 < ntot) {
+            if (c + 2 < p.nchunk) slab_issue(op, p, c + 2, nb, st, b, lane);
+            else slab_issue(op_next, p_next, c + 2 - p.nchunk, nb, st, b, lane);
+        }
+    }
 }
 
 // Sum the 8 row slots of the squared accumulators (lanes with equal lane & 3) and park them in scratch row `row`
@@ -453,13 +488,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     __syncthreads();
     const int nc = (int)s_small[H_NC], nsp = (int)s_small[H_NSP], ndb = (int)s_small[H_NDB];
     const int nb = nsp >> 3, nks = nsp >> 2;
-    __shared__ int s_chk[STREAM ? CHUNK_TAB : 1];
     __shared__ __align__(8) unsigned long long s_bar[2];
-    Stream strm{s_bar, s_chk, s_ops, a.chunk_frags * 32, 0u};
+    // the warps' relevance masks (K_l, K_tl) of a sub-tile; two sets alternate so that a fast warp's next sub-tile cannot
+    // overwrite what a slow warp still reads (there is no CTA barrier between two sub-tiles that stream nothing)
+    __shared__ unsigned long long s_wm[STREAM ? 4 * WARPS : 1];
+    int wm_set = 0;
+    Stream strm{s_bar, s_ops, a.chunk_frags * 32, 0u};
     if constexpr (STREAM) {
         if (tid == 0) {
-            int r = 0;
-            for (int i = 0; i < CHUNK_TAB; ++i) { s_chk[i] = r; if (r < nb) r = chunk_end_rb(r, nb, a.chunk_frags); }
             mbar_init(s_bar, 1);
             mbar_init(s_bar + 1, 1);
             mbar_init_fence();
@@ -542,9 +578,33 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 
             // ---- phase L: K_l cross-kernel fragments, triangular rows then the dense candidate / g rows
             if (ALIGN) __syncthreads();                  // ... and the exp phase together (DMMA / DFMA mixing costs pipe throughput)
-            if constexpr (STREAM) tri_stream_begin(M + lay.off_af_l_tri, strm);
-            mask_t mask = gen_fragments<KS, NT, TABN, false, true>(bf, x, Cl, dmax_l, cut_l, nks, kq, s_xs, s_atl, tol2_hi, s_tab, tm, close);
-            if constexpr (STREAM) tri_stream_run<KS, NT>(M + lay.off_af_l_tri, strm, bf, q0, q1, nb, lane, mask);
+            mask_t mask, mask_tl;
+            gen_masks<KS, NT>(bf, x, cut_l, cut_tl, nks, kq, s_xs, tol2_hi, close, mask, mask_tl);
+            SlabPlan plan_l, plan_tl;
+            int nchunks = 0;
+            if constexpr (STREAM) {                      // the CTA's union of relevant k-steps decides what is streamed
+                unsigned long long *wm = s_wm + wm_set * 2 * WARPS;
+                wm_set ^= 1;
+                if (lane == 0) { wm[2 * warp] = mask; wm[2 * warp + 1] = mask_tl; }
+                __syncthreads();                         // (every warp has also left the previous sub-tile's buffers)
+                unsigned long long um_l = 0, um_tl = 0;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) { um_l |= wm[2 * w]; um_tl |= wm[2 * w + 1]; }
+                plan_l = make_slab_plan<KS>((mask_t)um_l, nks, nb, a.chunk_frags);
+                plan_tl = make_slab_plan<KS>((mask_t)um_tl, nks, nb, a.chunk_frags);
+                nchunks = plan_l.nchunk + plan_tl.nchunk;
+                if (warp == 0) {
+#pragma unroll
+                    for (int sq = 0; sq < 2; ++sq) {
+                        if (sq < plan_l.nchunk) slab_issue(M + lay.off_af_l_tri, plan_l, sq, nb, strm, sq, lane);
+                        else if (sq < nchunks) slab_issue(M + lay.off_af_tl_tri, plan_tl, sq - plan_l.nchunk, nb, strm, sq, lane);
+                    }
+                }
+            }
+            gen_exps<KS, NT, TABN, false>(bf, x, Cl, dmax_l, mask, kq, s_xs, s_atl, s_tab, tm);
+            if constexpr (STREAM)
+                slab_pass<KS, NT>(M + lay.off_af_l_tri, plan_l, M + lay.off_af_tl_tri, plan_tl, 0, nchunks, strm, bf, q0, q1, nb, lane,
+                                  warp, mask);
             else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_l, bf, q0, q1, nb, lane, mask);
             if (a.work) n_kstep += count_ksteps<KS>(mask, nb) + ndb * __popcll((unsigned long long)mask);
 #pragma unroll
@@ -577,12 +637,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
             if (ALIGN) __syncthreads();
-            if constexpr (STREAM) tri_stream_begin(M + lay.off_af_tl_tri, strm);
-            mask = gen_fragments<KS, NT, TABN, true, true>(bf, x, Ctl, dmax_tl, cut_tl, nks, kq, s_xs, s_atl, tol2_hi, s_tab, tm, close);
+            mask = mask_tl;
+            gen_exps<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, mask, kq, s_xs, s_atl, s_tab, tm);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
                 if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
-            if constexpr (STREAM) tri_stream_run<KS, NT>(M + lay.off_af_tl_tri, strm, bf, q0, q1, nb, lane, mask);
+            if constexpr (STREAM)
+                slab_pass<KS, NT>(M + lay.off_af_tl_tri, plan_tl, M + lay.off_af_tl_tri, plan_tl, plan_l.nchunk, nchunks, strm, bf, q0, q1,
+                                  nb, lane, warp, mask);
             else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane, mask);
             if (a.work) n_kstep += count_ksteps<KS>(mask, nb);
             park_q<NT>(q0, q1, scr, 1, col0, kq, pq);
@@ -755,10 +817,10 @@ template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN
 static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     a.chunk_frags = 0;
-    if (STREAM) {       // the largest chunk that fits; a chunk must hold the longest row block (KS fragments)
+    if (STREAM) {       // the largest chunk buffers that fit
         int cf = CHUNK_FRAGS_MAX;
-        while (cf >= KS && smem_need<KS, NT, WARPS, STREAM, TABN>(a, cf) > SMEM_LIMIT) cf -= 16;
-        if (cf < KS) return cudaErrorInvalidConfiguration;
+        while (cf >= 2 * KS && smem_need<KS, NT, WARPS, STREAM, TABN>(a, cf) > SMEM_LIMIT) cf -= 16;
+        if (cf < 2 * KS) return cudaErrorInvalidConfiguration;      // a slab chunk holds at least two whole row blocks
         a.chunk_frags = cf;
     }
     const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small, a.ndb_max, a.chunk_frags);
@@ -789,10 +851,11 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     switch (a.lay.nsp_cap) {
         case 16: return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream, grid_x);
-        case 64: return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
+        case 64:
+            return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
         case 128:
             if (smem_need<32, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
-                return launch_cfg<32, 2, 8, 1, false, 512, false, false>(a, n_inst, sm_count, stream, grid_x);
+                return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
             return launch_cfg<32, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
         case 160: return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
         case 256: return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
