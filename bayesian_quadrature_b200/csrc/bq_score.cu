@@ -261,56 +261,76 @@ __device__ __forceinline__ void row_block(const double *af, int lim, const doubl
 // A-fragment loads of a group are issued ahead of its DMMAs.  ncu on the ns = 256 kernel had 42 % of the DMMA-phase
 // stalls on the LDS -> DMMA scoreboard and one ISETP + BRA per two DMMAs with the one-block-at-a-time loop.
 // limA = k-steps of the first row block (2 rb + 2); the second one has two more.
+//
+// pair_group is the group of four k-steps starting at the compile-time k-step K0 (the B fragments are registers).
+template <int KS, int NT, int K0>
+__device__ __forceinline__ void pair_group(const double *afA, const double *afB, int limA, const double (&bf)[KS][NT],
+                                           double (&a0)[NT], double (&a1)[NT], double (&b0)[NT], double (&b1)[NT],
+                                           double (&c0)[NT], double (&c1)[NT], double (&d0)[NT], double (&d1)[NT]) {
+    constexpr int ks = K0;
+    if (ks + 4 <= limA) {
+        double fa[4], fb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { fa[j] = afA[(ks + j) * 32]; fb[j] = afB[(ks + j) * 32]; }
+#pragma unroll
+        for (int j = 0; j < 4; j += 2)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                dmma(a0[nt], a1[nt], fa[j], bf[ks + j][nt]);
+                dmma(c0[nt], c1[nt], fb[j], bf[ks + j][nt]);
+                dmma(b0[nt], b1[nt], fa[j + 1], bf[ks + j + 1][nt]);
+                dmma(d0[nt], d1[nt], fb[j + 1], bf[ks + j + 1][nt]);
+            }
+    } else if (ks + 2 <= limA) {             // limA == ks + 2: two more k-steps for both, then B's last two
+        const double fa0 = afA[ks * 32], fa1 = afA[(ks + 1) * 32];
+        double fb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fb[j] = afB[(ks + j) * 32];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            dmma(a0[nt], a1[nt], fa0, bf[ks][nt]);
+            dmma(c0[nt], c1[nt], fb[0], bf[ks][nt]);
+            dmma(b0[nt], b1[nt], fa1, bf[ks + 1][nt]);
+            dmma(d0[nt], d1[nt], fb[1], bf[ks + 1][nt]);
+            dmma(c0[nt], c1[nt], fb[2], bf[ks + 2][nt]);
+            dmma(d0[nt], d1[nt], fb[3], bf[ks + 3][nt]);
+        }
+    } else {                                 // limA == ks: only B's last two k-steps remain
+        const double fb0 = afB[ks * 32], fb1 = afB[(ks + 1) * 32];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            dmma(c0[nt], c1[nt], fb0, bf[ks][nt]);
+            dmma(d0[nt], d1[nt], fb1, bf[ks + 1][nt]);
+        }
+    }
+}
+
+// [g0, kend): first relevant group of four k-steps and the end (a multiple of 4) of the last one, from the mask.  The
+// groups are entered through a jump table at g0 and left at kend or at the diagonal: with a band of 2-4 groups out of up
+// to 16, testing every group of every row-block pair cost more than the DMMAs (ncu, ns = 256).
 template <int KS, int NT>
 __device__ __forceinline__ void row_block_pair(const double *afA, const double *afB, int limA, const double (&bf)[KS][NT],
-                                               double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask) {
+                                               double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask, int g0, int kend) {
     using mask_t = typename KMask<KS>::type;
-    static_assert(KS % 4 == 0, "k-steps come in groups of 4");
+    static_assert(KS % 4 == 0 && KS <= 64, "k-steps come in groups of 4, at most 16 groups");
     double a0[NT], a1[NT], b0[NT], b1[NT], c0[NT], c1[NT], d0[NT], d1[NT];   // (a, b): block A even / odd k; (c, d): block B
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) { a0[nt] = a1[nt] = b0[nt] = b1[nt] = c0[nt] = c1[nt] = d0[nt] = d1[nt] = 0.0; }
-#pragma unroll
-    for (int ks = 0; ks < KS; ks += 4) {
-        if (ks >= limA + 2) break;           // both row blocks are complete
-        if (!(mask & ((mask_t)15 << ks))) continue;                // warp-uniform: nothing relevant in these four k-steps
-        if (ks + 4 <= limA) {
-            double fa[4], fb[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { fa[j] = afA[(ks + j) * 32]; fb[j] = afB[(ks + j) * 32]; }
-#pragma unroll
-            for (int j = 0; j < 4; j += 2)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    dmma(a0[nt], a1[nt], fa[j], bf[ks + j][nt]);
-                    dmma(c0[nt], c1[nt], fb[j], bf[ks + j][nt]);
-                    dmma(b0[nt], b1[nt], fa[j + 1], bf[ks + j + 1][nt]);
-                    dmma(d0[nt], d1[nt], fb[j + 1], bf[ks + j + 1][nt]);
-                }
-        } else {
-            if (ks + 2 <= limA) {            // limA == ks + 2: two more k-steps for both, then B's last two
-                const double fa0 = afA[ks * 32], fa1 = afA[(ks + 1) * 32];
-                double fb[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) fb[j] = afB[(ks + j) * 32];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    dmma(a0[nt], a1[nt], fa0, bf[ks][nt]);
-                    dmma(c0[nt], c1[nt], fb[0], bf[ks][nt]);
-                    dmma(b0[nt], b1[nt], fa1, bf[ks + 1][nt]);
-                    dmma(d0[nt], d1[nt], fb[1], bf[ks + 1][nt]);
-                    dmma(c0[nt], c1[nt], fb[2], bf[ks + 2][nt]);
-                    dmma(d0[nt], d1[nt], fb[3], bf[ks + 3][nt]);
-                }
-            } else {                         // limA == ks: only B's last two k-steps remain
-                const double fb0 = afB[ks * 32], fb1 = afB[(ks + 1) * 32];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    dmma(c0[nt], c1[nt], fb0, bf[ks][nt]);
-                    dmma(d0[nt], d1[nt], fb1, bf[ks + 1][nt]);
-                }
-            }
-        }
+    const int kstop = min(kend, limA + 2);   // both row blocks are complete at limA + 2
+#define BQB_GRP(G)                                                                                                       \
+    case G:                                                                                                              \
+        if constexpr (4 * (G) < KS) {                                                                                    \
+            if (4 * (G) >= kstop) break;                                                                                 \
+            if (mask & ((mask_t)15 << (4 * (G))))      /* holes: observations need not be sorted */                      \
+                pair_group<KS, NT, 4 * (G)>(afA, afB, limA, bf, a0, a1, b0, b1, c0, c1, d0, d1);                         \
+        }                                                                                                                \
+        [[fallthrough]];
+    switch (g0) {
+        BQB_GRP(0) BQB_GRP(1) BQB_GRP(2) BQB_GRP(3) BQB_GRP(4) BQB_GRP(5) BQB_GRP(6) BQB_GRP(7)
+        BQB_GRP(8) BQB_GRP(9) BQB_GRP(10) BQB_GRP(11) BQB_GRP(12) BQB_GRP(13) BQB_GRP(14) BQB_GRP(15)
+        default: break;
     }
+#undef BQB_GRP
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
         const double rA0 = a0[nt] + b0[nt], rA1 = a1[nt] + b1[nt], rB0 = c0[nt] + d0[nt], rB1 = c1[nt] + d1[nt];
@@ -321,17 +341,28 @@ __device__ __forceinline__ void row_block_pair(const double *afA, const double *
     }
 }
 
+// first relevant group of four k-steps / end of the last one
+template <typename mask_t>
+__device__ __forceinline__ void mask_groups(mask_t mask, int &g0, int &kend) {
+    const unsigned long long m = mask;
+    g0 = (__ffsll((long long)m) - 1) >> 2;
+    kend = (64 - __clzll((long long)m) + 3) & ~3;
+}
+
 // Row blocks [rb0, rb1) of a triangular operand whose fragment (rb, ks) sits at base[(tri_frags(rb) + ks) * 32]
 template <int KS, int NT>
 __device__ __forceinline__ void row_blocks_rolled(const double *base, int rb0, int rb1, const double (&bf)[KS][NT],
                                                   double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask) {
     using mask_t = typename KMask<KS>::type;
+    if (!mask) return;
+    int g0, kend;
+    mask_groups(mask, g0, kend);
     int rb = rb0;
 #pragma unroll 1
     for (; rb + 1 < rb1; rb += 2) {
         // rows above the first relevant k-step see none of it (lower-triangular operand): 2 rb + 4 k-steps at most
         if (2 * rb + 4 < (int)(8 * sizeof(mask_t)) && !(mask & (((mask_t)1 << (2 * rb + 4)) - 1))) continue;
-        row_block_pair<KS, NT>(base + tri_frags(rb) * 32, base + tri_frags(rb + 1) * 32, 2 * rb + 2, bf, q0, q1, mask);
+        row_block_pair<KS, NT>(base + tri_frags(rb) * 32, base + tri_frags(rb + 1) * 32, 2 * rb + 2, bf, q0, q1, mask, g0, kend);
     }
     if (rb < rb1) row_block<KS, NT>(base + tri_frags(rb) * 32, 2 * rb + 2, bf, q0, q1, mask);
 }
@@ -415,32 +446,40 @@ template <int KS, int NT>
 __device__ __forceinline__ void slab_rows(const double *buf, const SlabPlan &p, int rb0, int rb1, const double (&bf)[KS][NT],
                                           double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask, int lane) {
     using mask_t = typename KMask<KS>::type;
+    if (!mask) return;
+    int g0, kend;
+    mask_groups(mask, g0, kend);
     int rb = rb0;
 #pragma unroll 1
     for (; rb + 1 < rb1; rb += 2) {
         if (2 * rb + 4 < (int)(8 * sizeof(mask_t)) && !(mask & (((mask_t)1 << (2 * rb + 4)) - 1))) continue;
         const double *afA = buf + ((rb - rb0) * p.W - p.klo) * 32 + lane;       // afA[ks * 32] = fragment (rb, ks)
-        row_block_pair<KS, NT>(afA, afA + p.W * 32, 2 * rb + 2, bf, q0, q1, mask);
+        row_block_pair<KS, NT>(afA, afA + p.W * 32, 2 * rb + 2, bf, q0, q1, mask, g0, kend);
     }
     if (rb < rb1) row_block<KS, NT>(buf + ((rb - rb0) * p.W - p.klo) * 32 + lane, 2 * rb + 2, bf, q0, q1, mask);
 }
-// One operand's part of the sub-tile's chunk sequence: chunks [seq0, seq0 + p.nchunk) of `ntot`; chunk s lives in buffer
-// s & 1 and chunk s + 2 is issued (from `op` or, past this operand's end, from `op_next`) once every warp is done with s.
+// The DMMAs of one operand for one sub-tile.  `res`: the whole slab already sits in the (contiguous) buffers, fetched once
+// per super-tile on barrier 0 -- the first sub-tile waits for it.  Otherwise the slab is streamed for this sub-tile in
+// chunks: chunks 0 and 1 were issued by the caller, chunk c lives in buffer c & 1 and chunk c + 2 is issued once every
+// warp is done with chunk c.
 template <int KS, int NT>
-__device__ __forceinline__ void slab_pass(const double *__restrict__ op, const SlabPlan &p, const double *__restrict__ op_next,
-                                          const SlabPlan &p_next, int seq0, int ntot, Stream &st, const double (&bf)[KS][NT],
-                                          double (&q0)[NT], double (&q1)[NT], int nb, int lane, int warp,
+__device__ __forceinline__ void slab_pass(const double *__restrict__ op, const SlabPlan &p, bool res, bool first_sub, Stream &st,
+                                          const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT], int nb, int lane, int warp,
                                           typename KMask<KS>::type mask) {
-    for (int c = 0; c < p.nchunk; ++c) {
-        const int sq = seq0 + c, b = sq & 1;
-        mbar_wait(st.bar + b, (st.phase >> b) & 1u);            // the chunk has landed
-        st.phase ^= 1u << b;
-        const int rb0 = p.rb_first + c * p.R;
-        slab_rows<KS, NT>(st.buf + b * st.stride, p, rb0, min(nb, rb0 + p.R), bf, q0, q1, mask, lane);
-        __syncthreads();                                        // every warp is done with buffer b
-        if (warp == 0 && sq + 2 < ntot) {
-            if (c + 2 < p.nchunk) slab_issue(op, p, c + 2, nb, st, b, lane);
-            else slab_issue(op_next, p_next, c + 2 - p.nchunk, nb, st, b, lane);
+    const int nch = res ? (p.nchunk ? 1 : 0) : p.nchunk;
+    const int R = res ? nb - p.rb_first : p.R;
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+        const int b = res ? 0 : (c & 1);
+        if (!res || first_sub) {
+            mbar_wait(st.bar + b, (st.phase >> b) & 1u);        // the chunk (slab) has landed
+            st.phase ^= 1u << b;
+        }
+        const int rb0 = p.rb_first + c * R;
+        slab_rows<KS, NT>(st.buf + b * st.stride, p, rb0, min(nb, rb0 + R), bf, q0, q1, mask, lane);
+        if (!res) {
+            __syncthreads();                                    // every warp is done with buffer b
+            if (warp == 0 && c + 2 < nch) slab_issue(op, p, c + 2, nb, st, b, lane);
         }
     }
 }
@@ -493,6 +532,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     // overwrite what a slow warp still reads (there is no CTA barrier between two sub-tiles that stream nothing)
     __shared__ unsigned long long s_wm[STREAM ? 4 * WARPS : 1];
     int wm_set = 0;
+    __shared__ unsigned long long s_mt[STREAM ? 4 * WARPS : 1];      // K_tl masks of a warp's sub-tiles, kept for the K_tl pass
     Stream strm{s_bar, s_ops, a.chunk_frags * 32, 0u};
     if constexpr (STREAM) {
         if (tid == 0) {
@@ -561,102 +601,159 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
         async_commit();
         if (!LOCKSTEP && base >= a.na) continue;     // warp-uniform; lock-step warps must keep hitting the barriers
 
+        // ---- STREAM: what to stream for this super-tile.  Relevance masks of all its sub-tiles (a cheap extra distance
+        // pass) are OR-ed over the CTA; if the resulting band slab of an operand fits the two chunk buffers it is fetched
+        // ONCE and serves every sub-tile (pass-major order: K_l for all sub-tiles, then K_tl), otherwise each sub-tile
+        // streams it in chunks.
+        SlabPlan plan_l, plan_tl;
+        bool res_l = false, res_tl = false;
+        if constexpr (STREAM) {
+            mask_t u_l = 0, u_tl = 0;
 #pragma unroll 1
-        for (int sub = 0; sub < nsub; ++sub) {
-            const int col0 = sub * 8 * NT;
-            double x[NT];
+            for (int sub = 0; sub < nsub; ++sub) {
+                double x[NT], bf[KS][NT];
+                int close[NT];
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                const double v = xrow[col0 + nt * 8 + pq];      // points past na were filled with 0
-                x[nt] = isfinite(v) ? v : 0.0;       // invalid x_a is reported by the tail (ST_XA_BAD)
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double v = xrow[sub * 8 * NT + nt * 8 + pq];
+                    x[nt] = isfinite(v) ? v : 0.0;
+                }
+                mask_t m1, m2;
+                gen_masks<KS, NT>(bf, x, cut_l, cut_tl, nks, kq, s_xs, tol2_hi, close, m1, m2);
+                u_l |= m1; u_tl |= m2;
             }
-            double bf[KS][NT];
-            double q0[NT], q1[NT], tm[NT];
-            int close[NT];
+            unsigned long long *wm = s_wm + wm_set * 2 * WARPS;
+            wm_set ^= 1;
+            if (lane == 0) { wm[2 * warp] = u_l; wm[2 * warp + 1] = u_tl; }
+            __syncthreads();                             // (every warp has also left the previous super-tile's buffers)
+            unsigned long long um_l = 0, um_tl = 0;
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = tm[nt] = 0.0; close[nt] = 0; }
+            for (int w = 0; w < WARPS; ++w) { um_l |= wm[2 * w]; um_tl |= wm[2 * w + 1]; }
+            plan_l = make_slab_plan<KS>((mask_t)um_l, nks, nb, a.chunk_frags);
+            plan_tl = make_slab_plan<KS>((mask_t)um_tl, nks, nb, a.chunk_frags);
+            res_l = (nb - plan_l.rb_first) * plan_l.W <= 2 * a.chunk_frags;
+            res_tl = (nb - plan_tl.rb_first) * plan_tl.W <= 2 * a.chunk_frags;
+        }
 
-            // ---- phase L: K_l cross-kernel fragments, triangular rows then the dense candidate / g rows
-            if (ALIGN) __syncthreads();                  // ... and the exp phase together (DMMA / DFMA mixing costs pipe throughput)
-            mask_t mask, mask_tl;
-            gen_masks<KS, NT>(bf, x, cut_l, cut_tl, nks, kq, s_xs, tol2_hi, close, mask, mask_tl);
-            SlabPlan plan_l, plan_tl;
-            int nchunks = 0;
-            if constexpr (STREAM) {                      // the CTA's union of relevant k-steps decides what is streamed
-                unsigned long long *wm = s_wm + wm_set * 2 * WARPS;
-                wm_set ^= 1;
-                if (lane == 0) { wm[2 * warp] = mask; wm[2 * warp + 1] = mask_tl; }
-                __syncthreads();                         // (every warp has also left the previous sub-tile's buffers)
-                unsigned long long um_l = 0, um_tl = 0;
+        constexpr int NPH = STREAM ? 2 : 1;              // STREAM: pass 0 = K_l, pass 1 = K_tl; otherwise both per sub-tile
 #pragma unroll
-                for (int w = 0; w < WARPS; ++w) { um_l |= wm[2 * w]; um_tl |= wm[2 * w + 1]; }
-                plan_l = make_slab_plan<KS>((mask_t)um_l, nks, nb, a.chunk_frags);
-                plan_tl = make_slab_plan<KS>((mask_t)um_tl, nks, nb, a.chunk_frags);
-                nchunks = plan_l.nchunk + plan_tl.nchunk;
-                if (warp == 0) {
-#pragma unroll
-                    for (int sq = 0; sq < 2; ++sq) {
-                        if (sq < plan_l.nchunk) slab_issue(M + lay.off_af_l_tri, plan_l, sq, nb, strm, sq, lane);
-                        else if (sq < nchunks) slab_issue(M + lay.off_af_tl_tri, plan_tl, sq - plan_l.nchunk, nb, strm, sq, lane);
-                    }
+        for (int ph = 0; ph < NPH; ++ph) {
+            const bool do_l = !STREAM || ph == 0, do_tl = !STREAM || ph == 1;
+            const SlabPlan &plan = ph ? plan_tl : plan_l;
+            const bool res = ph ? res_tl : res_l;
+            const double *op = M + (ph ? lay.off_af_tl_tri : lay.off_af_l_tri);
+            if constexpr (STREAM) {
+                if (ph == 1) __syncthreads();            // every warp is done with the K_l slab
+                if (res && plan.nchunk && warp == 0) {   // whole slab: one copy per row block, all on barrier 0
+                    const int n = nb - plan.rb_first;
+                    if (lane == 0) mbar_expect_tx(strm.bar, (unsigned)(n * plan.W * 256));
+                    __syncwarp();
+                    if (lane < n)
+                        bulk_g2s(strm.buf + lane * plan.W * 32, op + (size_t)(tri_frags(plan.rb_first + lane) + plan.klo) * 32,
+                                 (unsigned)(plan.W * 256), strm.bar);
                 }
             }
-            gen_exps<KS, NT, TABN, false>(bf, x, Cl, dmax_l, mask, kq, s_xs, s_atl, s_tab, tm);
-            if constexpr (STREAM)
-                slab_pass<KS, NT>(M + lay.off_af_l_tri, plan_l, M + lay.off_af_tl_tri, plan_tl, 0, nchunks, strm, bf, q0, q1, nb, lane,
-                                  warp, mask);
-            else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_l, bf, q0, q1, nb, lane, mask);
-            if (a.work) n_kstep += count_ksteps<KS>(mask, nb) + ndb * __popcll((unsigned long long)mask);
+#pragma unroll 1
+            for (int sub = 0; sub < nsub; ++sub) {
+                const int col0 = sub * 8 * NT;
+                double x[NT];
 #pragma unroll
-            for (int db = 0; db < 3; ++db) {
-                if (db < ndb) {
-                    const double *af = s_af_d + (db * nks) * 32 + lane;
-                    double c0[NT], c1[NT], e0[NT], e1[NT];
+                for (int nt = 0; nt < NT; ++nt) {
+                    const double v = xrow[col0 + nt * 8 + pq];      // points past na were filled with 0
+                    x[nt] = isfinite(v) ? v : 0.0;       // invalid x_a is reported by the tail (ST_XA_BAD)
+                }
+                double bf[KS][NT];
+                double q0[NT], q1[NT], tm[NT];
+                int close[NT];
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
+                for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = tm[nt] = 0.0; close[nt] = 0; }
+                mask_t mask = 0, mask_tl = 0;
+
+                if (do_l) {
+                    // ---- K_l: cross-kernel fragments, triangular rows then the dense candidate / g rows
+                    if (ALIGN) __syncthreads();          // all warps enter the exp phase together (DMMA / DFMA mixing costs pipe throughput)
+                    gen_masks<KS, NT>(bf, x, cut_l, cut_tl, nks, kq, s_xs, tol2_hi, close, mask, mask_tl);
+                    if constexpr (STREAM) {
+                        if (lane == 0) s_mt[warp * 4 + sub] = mask_tl;      // the K_tl pass of this sub-tile needs it
+                        if (!res && plan.nchunk && warp == 0) {             // chunked: first two chunks, under the exp phase
+                            slab_issue(op, plan, 0, nb, strm, 0, lane);
+                            if (plan.nchunk > 1) slab_issue(op, plan, 1, nb, strm, 1, lane);
+                        }
 #pragma unroll
-                    for (int ks = 0; ks < KS; ks += 2) {
-                        if (ks < nks && (mask & ((mask_t)3 << ks))) {      // nks is even; warp-uniform relevance test
-                            const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
-#pragma unroll
-                            for (int nt = 0; nt < NT; ++nt) {
-                                dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
-                                dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);     // 2 chains: the dense rows are few
-                            }
+                        for (int nt = 0; nt < NT; ++nt) {                   // isclose (bq.py:456) is settled in this pass
+                            if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
+                            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 1);
+                            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 2);
+                            if (kq == 0) scr[3 * SCR_STRIDE + col0 + nt * 8 + pq] = close[nt] ? 1.0 : 0.0;
                         }
                     }
+                    gen_exps<KS, NT, TABN, false>(bf, x, Cl, dmax_l, mask, kq, s_xs, s_atl, s_tab, tm);
+                    if constexpr (STREAM) slab_pass<KS, NT>(op, plan, res, sub == 0, strm, bf, q0, q1, nb, lane, warp, mask);
+                    else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_l, bf, q0, q1, nb, lane, mask);
+                    if (a.work) n_kstep += count_ksteps<KS>(mask, nb) + ndb * __popcll((unsigned long long)mask);
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-                        *reinterpret_cast<double2 *>(scr + (SCR_DENSE + db * 8 + pq) * SCR_STRIDE + col0 + nt * 8 + 2 * kq) =
-                            make_double2(c0[nt] + e0[nt], c1[nt] + e1[nt]);
+                    for (int db = 0; db < 3; ++db) {
+                        if (db < ndb) {
+                            const double *af = s_af_d + (db * nks) * 32 + lane;
+                            double c0[NT], c1[NT], e0[NT], e1[NT];
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
+#pragma unroll
+                            for (int ks = 0; ks < KS; ks += 2) {
+                                if (ks < nks && (mask & ((mask_t)3 << ks))) {      // nks is even; warp-uniform relevance test
+                                    const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
+#pragma unroll
+                                    for (int nt = 0; nt < NT; ++nt) {
+                                        dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
+                                        dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);     // 2 chains: the dense rows are few
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt)
+                                *reinterpret_cast<double2 *>(scr + (SCR_DENSE + db * 8 + pq) * SCR_STRIDE + col0 + nt * 8 + 2 * kq) =
+                                    make_double2(c0[nt] + e0[nt], c1[nt] + e1[nt]);
+                        }
+                    }
+                    park_q<NT>(q0, q1, scr, 0, col0, kq, pq);
                 }
-            }
-            park_q<NT>(q0, q1, scr, 0, col0, kq, pq);
 
-            // ---- phase TL: K_tl fragments, gp_log_l.mean and the isclose test
+                if (do_tl) {
+                    // ---- K_tl: fragments, gp_log_l.mean and (non-streamed kernels) the isclose test
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
-            if (ALIGN) __syncthreads();
-            mask = mask_tl;
-            gen_exps<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, mask, kq, s_xs, s_atl, s_tab, tm);
+                    for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
+                    if (ALIGN) __syncthreads();
+                    if constexpr (STREAM) {
+                        mask = (mask_t)s_mt[warp * 4 + sub];
+                        if (!res && plan.nchunk && warp == 0) {
+                            slab_issue(op, plan, 0, nb, strm, 0, lane);
+                            if (plan.nchunk > 1) slab_issue(op, plan, 1, nb, strm, 1, lane);
+                        }
+                    } else {
+                        mask = mask_tl;
+                    }
+                    gen_exps<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, mask, kq, s_xs, s_atl, s_tab, tm);
+                    if constexpr (STREAM) {
+                        slab_pass<KS, NT>(op, plan, res, sub == 0, strm, bf, q0, q1, nb, lane, warp, mask);
+                    } else {
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-                if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
-            if constexpr (STREAM)
-                slab_pass<KS, NT>(M + lay.off_af_tl_tri, plan_tl, M + lay.off_af_tl_tri, plan_tl, plan_l.nchunk, nchunks, strm, bf, q0, q1,
-                                  nb, lane, warp, mask);
-            else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane, mask);
-            if (a.work) n_kstep += count_ksteps<KS>(mask, nb);
-            park_q<NT>(q0, q1, scr, 1, col0, kq, pq);
+                        for (int nt = 0; nt < NT; ++nt)
+                            if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
+                        tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane, mask);
+                    }
+                    if (a.work) n_kstep += count_ksteps<KS>(mask, nb);
+                    park_q<NT>(q0, q1, scr, 1, col0, kq, pq);
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 1);
-                tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 2);
-                close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 1);
-                close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 2);
-                if (kq == 0) {
-                    scr[2 * SCR_STRIDE + col0 + nt * 8 + pq] = tm[nt];
-                    scr[3 * SCR_STRIDE + col0 + nt * 8 + pq] = close[nt] ? 1.0 : 0.0;
+                    for (int nt = 0; nt < NT; ++nt) {
+                        tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 1);
+                        tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 2);
+                        if (kq == 0) scr[2 * SCR_STRIDE + col0 + nt * 8 + pq] = tm[nt];
+                        if constexpr (!STREAM) {
+                            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 1);
+                            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 2);
+                            if (kq == 0) scr[3 * SCR_STRIDE + col0 + nt * 8 + pq] = close[nt] ? 1.0 : 0.0;
+                        }
+                    }
                 }
             }
         }
