@@ -113,82 +113,82 @@ constexpr double CUT_ARG = 72.0;
 // Cross-kernel B fragments of one sub-tile, bf[ks][nt] = exp(-(x - x_s[k])^2 / (2 w^2)), k = 4 ks + (lane & 3), are
 // produced in two steps.
 //
-// gen_masks (once per sub-tile, serves both kernels -- the distances are the same, only the widths differ): every squared
-// distance (2 FP64 operations per element, left in bf), on the integer pipe each point's smallest one, from which the two
-// relevance thresholds follow, and a warp-wide OR (REDUX) of the lanes' bit masks: the sub-tile's relevant k-steps under
-// K_l and under K_tl.  It also pre-filters np.isclose(x_a, x_s, atol=1e-4) (bq.py:456): the high word of the point's
-// smallest d^2 against an upper bound of every tolerance^2 (non-negative doubles order like their bits); the exact test
-// runs afterwards only for the rare points that pass (isclose_exact).
-template <int KS, int NT>
-__device__ __forceinline__ void gen_masks(double (&bf)[KS][NT], const double (&x)[NT], double cut_l, double cut_tl, int nks, int kq,
-                                          const double *s_xs, int tol2_hi, int (&close)[NT], typename KMask<KS>::type &mask_l,
-                                          typename KMask<KS>::type &mask_tl) {
+// gen_masks (once per super-tile of 32 points per warp, serves both kernels and all sub-tiles): which k-steps are
+// relevant.  The per-point criterion (exponent within CUT_ARG of the point's own largest) is bounded from the hull of
+// the warp's points instead of being evaluated per element: with c and hw the centre and half-width of the hull and dc
+// the distance from c to its nearest observation, every point has an observation within reach = dc + hw, so an
+// observation can only be relevant for some point if (|x_s[k] - c| - hw)^2 <= reach^2 + cut.  That is one comparison
+// per observation (lane <-> observation, nsp / 32 steps, distances kept in registers) and a ballot per 32
+// observations; the hull and dc are warp-reduced with REDUX on float-rounded values (rounded outwards: the criterion
+// only has to be conservative).  The first version computed every squared distance of every sub-tile and built the
+// masks bit by bit, which cost more instructions than the exponentials it saved.  For sorted query vectors (grids) the
+// hull criterion selects the same k-steps as the per-point one; for scattered points it selects more (never fewer).
+__device__ __forceinline__ int float_key(float f) {          // order-preserving map float -> int
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : (i ^ 0x7fffffff);
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
+
+template <int KS>
+__device__ __forceinline__ void gen_masks(double xv, bool valid, double cut_l, double cut_tl, int nsp, int lane,
+                                          const double *s_xs, typename KMask<KS>::type &mask_l, typename KMask<KS>::type &mask_tl) {
     using mask_t = typename KMask<KS>::type;
-    int minhi[NT];
+    constexpr int NW = (KS + 7) / 8;                 // 32-observation words
+    // hull of the warp's points (one per lane; lanes past the end or with invalid x do not count)
+    const double xc = fmin(fmax(xv, -1e30), 1e30);
+    const int klo = valid ? float_key(__double2float_rd(xc)) : 0x7fffffff;
+    const int khi = valid ? float_key(__double2float_ru(xc)) : (int)0x80000000;
+    const double xlo = (double)key_float(__reduce_min_sync(0xffffffffu, klo));
+    const double xhi = (double)key_float(__reduce_max_sync(0xffffffffu, khi));
+    if (!(xlo <= xhi)) { mask_l = 0; mask_tl = 0; return; }      // no valid point in this warp's tile
+    const double c = 0.5 * (xlo + xhi), hw = 0.5 * (xhi - xlo);
+    double dk[NW];
+    double dmin = INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) minhi[nt] = 0x7fffffff;
-#pragma unroll
-    for (int g = 0; g < (KS + 3) / 4; ++g) {
-        if (4 * g < nks) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int ks = 4 * g + j;
-                if (ks < KS) {
-                    const double xs = s_xs[4 * ks + kq];
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        const double d = x[nt] - xs;
-                        const double d2 = d * d;
-                        bf[ks][nt] = d2;
-                        minhi[nt] = min(minhi[nt], __double2hiint(d2));
-                    }
-                }
-            }
-        }
+    for (int i = 0; i < NW; ++i) {
+        const int k = 32 * i + lane;
+        dk[i] = (k < nsp) ? fabs(s_xs[k] - c) : INFINITY;        // padded observations sit at 1e150
+        dmin = fmin(dmin, dk[i]);
     }
-    int thr_l[NT], thr_tl[NT];                       // high word of (smallest d^2 of the point) + CUT_ARG / |nh|, rounded up
+    // nearest observation to c, rounded up (positive floats order like their bits)
+    const float dcf = __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(__double2float_ru(fmin(dmin, 3e38)))));
+    const double reach = (double)dcf + hw;
+    const double r2_l = fma(reach, reach, cut_l), r2_tl = fma(reach, reach, cut_tl);        // inf for cut = inf (dense)
+    mask_t ml = 0, mt = 0;
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        minhi[nt] = min(minhi[nt], __shfl_xor_sync(0xffffffffu, minhi[nt], 1));
-        minhi[nt] = min(minhi[nt], __shfl_xor_sync(0xffffffffu, minhi[nt], 2));
-        close[nt] = (minhi[nt] <= tol2_hi);
-        const double dmin = __hiloint2double(minhi[nt], 0);
-        thr_l[nt] = __double2hiint(dmin + cut_l) + 1;
-        thr_tl[nt] = __double2hiint(dmin + cut_tl) + 1;
+    for (int i = 0; i < NW; ++i) {
+        const double t = fmax(dk[i] - hw, 0.0), t2 = t * t;
+        const bool in = 32 * i + lane < nsp;
+        unsigned bl = __ballot_sync(0xffffffffu, in && t2 <= r2_l), bt = __ballot_sync(0xffffffffu, in && t2 <= r2_tl);
+        // observation bits -> k-step bits: k-step j of this word is relevant if any of bits 4j .. 4j+3 is set
+        bl |= bl >> 1; bl |= bl >> 2; bl &= 0x11111111u;
+        bl = (bl | (bl >> 3)) & 0x03030303u; bl = (bl | (bl >> 6)) & 0x000f000fu; bl = (bl | (bl >> 12)) & 0xffu;
+        bt |= bt >> 1; bt |= bt >> 2; bt &= 0x11111111u;
+        bt = (bt | (bt >> 3)) & 0x03030303u; bt = (bt | (bt >> 6)) & 0x000f000fu; bt = (bt | (bt >> 12)) & 0xffu;
+        ml |= (mask_t)bl << (8 * i);
+        mt |= (mask_t)bt << (8 * i);
     }
-    unsigned l0 = 0, l1 = 0, t0 = 0, t1 = 0;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-        bool al = false, at = false;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int h = __double2hiint(bf[ks][nt]);
-            al |= (h <= thr_l[nt]);
-            at |= (h <= thr_tl[nt]);
-        }
-        if (ks < 32) { l0 |= al ? (1u << ks) : 0u; t0 |= at ? (1u << ks) : 0u; }
-        else { l1 |= al ? (1u << (ks - 32)) : 0u; t1 |= at ? (1u << (ks - 32)) : 0u; }
-    }
-    l0 = __reduce_or_sync(0xffffffffu, l0);
-    t0 = __reduce_or_sync(0xffffffffu, t0);
-    if (KS > 32) { l1 = __reduce_or_sync(0xffffffffu, l1); t1 = __reduce_or_sync(0xffffffffu, t1); }
-    const mask_t valid = (nks >= (int)(8 * sizeof(mask_t))) ? ~(mask_t)0 : (((mask_t)1 << nks) - 1);   // k-steps past nks hold garbage
-    mask_l = ((mask_t)l0 | ((mask_t)l1 << (KS > 32 ? 32 : 0))) & valid;
-    mask_tl = ((mask_t)t0 | ((mask_t)t1 << (KS > 32 ? 32 : 0))) & valid;
+    mask_l = ml;
+    mask_tl = mt;
 }
 
-// gen_exps turns the squared distances of the relevant k-steps into exponentials (7 FP64 + 6 integer instructions per
+// gen_exps computes the squared distances and exponentials of the relevant k-steps (9 FP64 + 6 integer instructions per
 // element): groups of GK k-steps are branch free so that GK NT independent exp chains interleave, and a group runs if
-// any of its k-steps is relevant.  The K_l pass finds the squared distances in bf; the K_tl pass recomputes them (bf
-// holds K_l values by then) and accumulates gp_log_l.mean (bq.py:493).
+// any of its k-steps is relevant.  The K_tl pass also accumulates gp_log_l.mean (bq.py:493) and pre-filters
+// np.isclose(x_a, x_s, atol=1e-4) (bq.py:456): the high word of the point's smallest d^2 (its nearest observation is
+// always in a relevant k-step) against an upper bound of every tolerance^2 -- non-negative doubles order like their
+// bits; the exact test runs afterwards only for the rare points that pass (isclose_exact).
 template <int KS, int NT, int TABN, bool TL>
 __device__ __forceinline__ void gen_exps(double (&bf)[KS][NT], const double (&x)[NT], double C, int d2max_hi,
                                          typename KMask<KS>::type mask, int kq, const double *s_xs, const double *s_atl,
-                                         const double *s_tab, double (&tm)[NT]) {
+                                         const double *s_tab, double (&tm)[NT], int tol2_hi, int (&close)[NT]) {
     using mask_t = typename KMask<KS>::type;
     // 8 independent exp chains per branch-free group: with one CTA of 8 warps per SM (two warps per scheduler) the
     // NT = 1 exp phase was latency bound at 4 (ncu: 47 % of its stalls on fixed-latency dependencies)
     constexpr int GK = (NT == 1) ? 8 : 4;
+    int minhi[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) minhi[nt] = 0x7fffffff;
 #pragma unroll
     for (int g = 0; g < (KS + GK - 1) / GK; ++g) {
         if ((mask >> (GK * g)) & (((mask_t)1 << GK) - 1)) {
@@ -196,19 +196,25 @@ __device__ __forceinline__ void gen_exps(double (&bf)[KS][NT], const double (&x)
             for (int j = 0; j < GK; ++j) {
                 const int ks = GK * g + j;
                 if (ks < KS) {
-                    double xs = 0.0;
-                    if (TL) xs = s_xs[4 * ks + kq];
+                    const double xs = s_xs[4 * ks + kq];
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
-                        double d2 = bf[ks][nt];
-                        if (TL) { const double d = x[nt] - xs; d2 = d * d; }
+                        const double d = x[nt] - xs;
+                        const double d2 = d * d;
                         const double e = exp_kernel<TABN>(d2, C, d2max_hi, s_tab);
                         bf[ks][nt] = e;
-                        if (TL) tm[nt] = fma(s_atl[4 * ks + kq], e, tm[nt]);
+                        if (TL) {
+                            minhi[nt] = min(minhi[nt], __double2hiint(d2));
+                            tm[nt] = fma(s_atl[4 * ks + kq], e, tm[nt]);
+                        }
                     }
                 }
             }
         }
+    }
+    if (TL) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) close[nt] = (minhi[nt] <= tol2_hi);      // per lane; the caller ORs the four k residues
     }
 }
 
@@ -532,7 +538,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     // overwrite what a slow warp still reads (there is no CTA barrier between two sub-tiles that stream nothing)
     __shared__ unsigned long long s_wm[STREAM ? 4 * WARPS : 1];
     int wm_set = 0;
-    __shared__ unsigned long long s_mt[STREAM ? 4 * WARPS : 1];      // K_tl masks of a warp's sub-tiles, kept for the K_tl pass
     Stream strm{s_bar, s_ops, a.chunk_frags * 32, 0u};
     if constexpr (STREAM) {
         if (tid == 0) {
@@ -605,26 +610,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
         // pass) are OR-ed over the CTA; if the resulting band slab of an operand fits the two chunk buffers it is fetched
         // ONCE and serves every sub-tile (pass-major order: K_l for all sub-tiles, then K_tl), otherwise each sub-tile
         // streams it in chunks.
+        // relevance masks of this warp's points (both kernels; shared by the super-tile's sub-tiles)
+        mask_t wmask_l, wmask_tl;
+        {
+            const double xv = xrow[lane];
+            gen_masks<KS>(xv, lane < npw && base + lane < a.na && isfinite(xv), cut_l, cut_tl, nsp, lane, s_xs, wmask_l, wmask_tl);
+        }
+        // ---- STREAM: what to stream for this super-tile.  The warps' masks are OR-ed over the CTA; if the resulting band
+        // slab of an operand fits the two chunk buffers it is fetched ONCE and serves every sub-tile (pass-major order: K_l
+        // for all sub-tiles, then K_tl), otherwise each sub-tile streams it in chunks.
         SlabPlan plan_l, plan_tl;
         bool res_l = false, res_tl = false;
         if constexpr (STREAM) {
-            mask_t u_l = 0, u_tl = 0;
-#pragma unroll 1
-            for (int sub = 0; sub < nsub; ++sub) {
-                double x[NT], bf[KS][NT];
-                int close[NT];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const double v = xrow[sub * 8 * NT + nt * 8 + pq];
-                    x[nt] = isfinite(v) ? v : 0.0;
-                }
-                mask_t m1, m2;
-                gen_masks<KS, NT>(bf, x, cut_l, cut_tl, nks, kq, s_xs, tol2_hi, close, m1, m2);
-                u_l |= m1; u_tl |= m2;
-            }
             unsigned long long *wm = s_wm + wm_set * 2 * WARPS;
             wm_set ^= 1;
-            if (lane == 0) { wm[2 * warp] = u_l; wm[2 * warp + 1] = u_tl; }
+            if (lane == 0) { wm[2 * warp] = wmask_l; wm[2 * warp + 1] = wmask_tl; }
             __syncthreads();                             // (every warp has also left the previous super-tile's buffers)
             unsigned long long um_l = 0, um_tl = 0;
 #pragma unroll
@@ -667,27 +667,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                 int close[NT];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = tm[nt] = 0.0; close[nt] = 0; }
-                mask_t mask = 0, mask_tl = 0;
+                mask_t mask = wmask_l;
+                const mask_t mask_tl = wmask_tl;
+                if constexpr (STREAM) {
+                    if (!res && plan.nchunk && warp == 0) {                 // chunked: first two chunks, under the exp phase
+                        slab_issue(op, plan, 0, nb, strm, 0, lane);
+                        if (plan.nchunk > 1) slab_issue(op, plan, 1, nb, strm, 1, lane);
+                    }
+                }
 
                 if (do_l) {
                     // ---- K_l: cross-kernel fragments, triangular rows then the dense candidate / g rows
                     if (ALIGN) __syncthreads();          // all warps enter the exp phase together (DMMA / DFMA mixing costs pipe throughput)
-                    gen_masks<KS, NT>(bf, x, cut_l, cut_tl, nks, kq, s_xs, tol2_hi, close, mask, mask_tl);
-                    if constexpr (STREAM) {
-                        if (lane == 0) s_mt[warp * 4 + sub] = mask_tl;      // the K_tl pass of this sub-tile needs it
-                        if (!res && plan.nchunk && warp == 0) {             // chunked: first two chunks, under the exp phase
-                            slab_issue(op, plan, 0, nb, strm, 0, lane);
-                            if (plan.nchunk > 1) slab_issue(op, plan, 1, nb, strm, 1, lane);
-                        }
-#pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) {                   // isclose (bq.py:456) is settled in this pass
-                            if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
-                            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 1);
-                            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 2);
-                            if (kq == 0) scr[3 * SCR_STRIDE + col0 + nt * 8 + pq] = close[nt] ? 1.0 : 0.0;
-                        }
-                    }
-                    gen_exps<KS, NT, TABN, false>(bf, x, Cl, dmax_l, mask, kq, s_xs, s_atl, s_tab, tm);
+                    gen_exps<KS, NT, TABN, false>(bf, x, Cl, dmax_l, mask, kq, s_xs, s_atl, s_tab, tm, tol2_hi, close);
                     if constexpr (STREAM) slab_pass<KS, NT>(op, plan, res, sub == 0, strm, bf, q0, q1, nb, lane, warp, mask);
                     else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_l, bf, q0, q1, nb, lane, mask);
                     if (a.work) n_kstep += count_ksteps<KS>(mask, nb) + ndb * __popcll((unsigned long long)mask);
@@ -719,39 +711,28 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                 }
 
                 if (do_tl) {
-                    // ---- K_tl: fragments, gp_log_l.mean and (non-streamed kernels) the isclose test
+                    // ---- K_tl: fragments, gp_log_l.mean and the isclose test
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
                     if (ALIGN) __syncthreads();
-                    if constexpr (STREAM) {
-                        mask = (mask_t)s_mt[warp * 4 + sub];
-                        if (!res && plan.nchunk && warp == 0) {
-                            slab_issue(op, plan, 0, nb, strm, 0, lane);
-                            if (plan.nchunk > 1) slab_issue(op, plan, 1, nb, strm, 1, lane);
-                        }
-                    } else {
-                        mask = mask_tl;
-                    }
-                    gen_exps<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, mask, kq, s_xs, s_atl, s_tab, tm);
-                    if constexpr (STREAM) {
-                        slab_pass<KS, NT>(op, plan, res, sub == 0, strm, bf, q0, q1, nb, lane, warp, mask);
-                    } else {
+                    mask = mask_tl;
+                    gen_exps<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, mask, kq, s_xs, s_atl, s_tab, tm, tol2_hi, close);
 #pragma unroll
-                        for (int nt = 0; nt < NT; ++nt)
-                            if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
-                        tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane, mask);
-                    }
+                    for (int nt = 0; nt < NT; ++nt)
+                        if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
+                    if constexpr (STREAM) slab_pass<KS, NT>(op, plan, res, sub == 0, strm, bf, q0, q1, nb, lane, warp, mask);
+                    else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane, mask);
                     if (a.work) n_kstep += count_ksteps<KS>(mask, nb);
                     park_q<NT>(q0, q1, scr, 1, col0, kq, pq);
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
                         tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 1);
                         tm[nt] += __shfl_xor_sync(0xffffffffu, tm[nt], 2);
-                        if (kq == 0) scr[2 * SCR_STRIDE + col0 + nt * 8 + pq] = tm[nt];
-                        if constexpr (!STREAM) {
-                            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 1);
-                            close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 2);
-                            if (kq == 0) scr[3 * SCR_STRIDE + col0 + nt * 8 + pq] = close[nt] ? 1.0 : 0.0;
+                        close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 1);
+                        close[nt] |= __shfl_xor_sync(0xffffffffu, close[nt], 2);
+                        if (kq == 0) {
+                            scr[2 * SCR_STRIDE + col0 + nt * 8 + pq] = tm[nt];
+                            scr[3 * SCR_STRIDE + col0 + nt * 8 + pq] = close[nt] ? 1.0 : 0.0;
                         }
                     }
                 }
