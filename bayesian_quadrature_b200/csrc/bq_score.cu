@@ -690,15 +690,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                             double c0[NT], c1[NT], e0[NT], e1[NT];
 #pragma unroll
                             for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
+                            constexpr int GK = (NT == 1) ? 8 : 4;          // the groups of gen_exps: all of a relevant group's
+#pragma unroll                                                             // B fragments exist; mask bits past nks are clear
+                            for (int g = 0; g < KS / GK; ++g) {
+                                if ((mask >> (GK * g)) & (((mask_t)1 << GK) - 1)) {     // warp-uniform: a real branch around GK DMMAs
+                                    double fa[GK];
 #pragma unroll
-                            for (int ks = 0; ks < KS; ks += 2) {
-                                if (ks < nks && (mask & ((mask_t)3 << ks))) {      // nks is even; warp-uniform relevance test
-                                    const double a0 = af[ks * 32], a1 = af[(ks + 1) * 32];
+                                    for (int j = 0; j < GK; ++j) fa[j] = (GK * g + j < nks) ? af[(GK * g + j) * 32] : 0.0;
 #pragma unroll
-                                    for (int nt = 0; nt < NT; ++nt) {
-                                        dmma(c0[nt], c1[nt], a0, bf[ks][nt]);
-                                        dmma(e0[nt], e1[nt], a1, bf[ks + 1][nt]);     // 2 chains: the dense rows are few
-                                    }
+                                    for (int j = 0; j < GK; j += 2)
+#pragma unroll
+                                        for (int nt = 0; nt < NT; ++nt) {
+                                            dmma(c0[nt], c1[nt], fa[j], bf[GK * g + j][nt]);
+                                            dmma(e0[nt], e1[nt], fa[j + 1], bf[GK * g + j + 1][nt]);     // 2 chains: the dense rows are few
+                                        }
                                 }
                             }
 #pragma unroll

@@ -93,6 +93,44 @@ def test_capi_vs_oracle_random(lib, oracle, ns, seed):
     b.close()
 
 
+@pytest.mark.parametrize("ns,shuffle", [(64, False), (64, True), (128, True), (150, False), (256, True), (256, False)])
+def test_band_skipping_equals_the_dense_algorithm(lib, ns, shuffle):
+    """The scoring kernels skip cross-kernel k-steps whose elements are below e^-72 of their point's leading element
+    (DESIGN.md 4.1).  Against the same kernels with the cut-off at infinity (the dense algorithm): same scores to far
+    below the parity tolerance on a sorted grid, on scattered points (where the hull criterion keeps more), on far-away
+    points, and with observations in arbitrary order (appended observations are not sorted); and fewer DMMAs."""
+    from bayesian_quadrature_b200 import synthetic
+    rs = np.random.RandomState(ns)
+    x_s, l_s = synthetic.observations(ns)
+    perm = rs.permutation(ns) if shuffle else np.arange(ns)      # arbitrary observation order
+    x_s, l_s = x_s[perm], l_s[perm]
+    x_c = np.sort(rs.uniform(x_s.min(), x_s.max(), 3)) + 0.6
+    x_c = x_c[(np.abs(x_c[:, None] - x_s[None, :]).min(axis=1) > 0.5)]
+    opt = synthetic.options(ns)
+    b = lib.Batch(1, ns)
+    info = b.setup([ns], [x_c.size], x_s[None], l_s[None], x_c[None] if x_c.size else np.zeros((1, 0)),
+                   np.array([synthetic.PARAMS_TL + synthetic.PARAMS_L]), np.array([[opt["x_mean"], opt["x_var"], 0.5]]))
+    assert info["status"][0] == 0
+    grid = synthetic.query_grid(ns, 20011)
+    scattered = rs.uniform(grid[0], grid[-1], 20011)
+    far = np.array([grid[0] - 1e3, grid[-1] + 1e6, 1e300, -1e300])
+    for name, x_a in (("grid", grid), ("scattered", scattered), ("far", far)):
+        b.set_cutoff(72.0)
+        b.work_counter(True)
+        esm, em, st = b.score_host(x_a)
+        work_band = b.work_counter(True)
+        b.set_cutoff(float("inf"))
+        esm_d, em_d, st_d = b.score_host(x_a)
+        work_dense = b.work_counter(False)
+        assert (st == st_d).all()
+        assert_close(esm[0], esm_d[0], "%s esm ns=%d" % (name, ns), rtol=1e-12, atol=1e-300)
+        assert_close(em[0], em_d[0], "%s em ns=%d" % (name, ns), rtol=1e-12, atol=1e-300)
+        assert 0 < work_band <= work_dense
+        if name == "grid" and not shuffle:           # sorted observations: the relevant k-steps of a tile are few and contiguous
+            assert work_band < 0.5 * work_dense, (work_band, work_dense)
+    b.close()
+
+
 def test_hyper_set_batch_vs_reference(lib):
     """C4 semantics: one instance per hyper-parameter set, shared x_a, marginal loss and argmin."""
     import torch
