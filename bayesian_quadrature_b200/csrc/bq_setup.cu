@@ -246,6 +246,24 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) bq_setup_kernel(SetupArgs a)
     __syncthreads();
     if (s_fail) { if (tid == 0) M[H_STATUS] = s_fail; return; }
 
+    // ---- P0b: observations in ascending order of x (stable rank sort; n <= 256).  Every result of this kernel and of the
+    // scoring kernel is invariant under a permutation of the observations (up to rounding), and with sorted observations
+    // the k-steps that matter for a query point are few and contiguous (band skipping, bq_score.cu) whatever order the
+    // caller -- or add_observation, which appends -- left them in.  Already sorted input is left exactly as it is.
+    {
+        double *xs_sorted = vec + 29 * (size_t)ncap, *ls_sorted = vec + 30 * (size_t)ncap;
+        for (int i = tid; i < ns; i += SETUP_THREADS) {
+            const double xi = x_s[i];
+            int rank = 0;
+            for (int j = 0; j < ns; ++j) rank += (x_s[j] < xi) || (x_s[j] == xi && j < i);
+            xs_sorted[rank] = xi;
+            ls_sorted[rank] = l_s[i];
+        }
+        __syncthreads();
+        x_s = xs_sorted;
+        l_s = ls_sorted;
+    }
+
     const double c_tl = (h_tl * h_tl) / (SQRT_2PI * w_tl);
     const double c_l = (h_l * h_l) / (SQRT_2PI * w_l);
 
