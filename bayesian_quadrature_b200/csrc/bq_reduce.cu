@@ -126,6 +126,74 @@ __global__ void argmin_partials_kernel(double *bv, long long *bi, int nblocks, l
     if (threadIdx.x == 0) { pair[0] = best; pair[1] = (double)(idx + offset); }
 }
 
+// Fused "reduce + exchange" of choose_next over a sharded query vector (bq.py:663 across ranks): the one warp that
+// reduces this rank's per-CTA partials stores its (min, first global index) pair straight into every rank's exchange
+// buffer over NVLink (peer-mapped symmetric memory, slot [parity][writer rank]), flags it with the step number, waits for
+// the other ranks' flags in its OWN buffer, and reduces the W pairs -- one small kernel instead of a reduction kernel, an
+// NCCL all-gather and a device-to-host copy.  Two slot sets alternate with the step parity: a rank can be at most one
+// step ahead of the slowest one (it needs that rank's flag of the current step), so a slot is never overwritten before
+// it was read.  The spin is bounded; on time-out out[2] = 1.  `out` may be page-locked host memory.
+struct PeerSlots {
+    double *slot[16];
+};
+__global__ void argmin_exchange_kernel(const double *bv, const long long *bi, int nblocks, long long offset, PeerSlots peers,
+                                       int world, int rank, unsigned long long seq, double *out) {
+    const int lane = threadIdx.x;
+    double best = INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    for (int b = lane; b < nblocks; b += 32) better(best, idx, bv[b], bi[b]);
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+        better(best, idx, v2, i2);
+    }
+    const int par = (int)(seq & 1ull);
+    const double tag = (double)seq;
+    if (lane < world) {                                   // lane r publishes to rank r
+        volatile double *dst = peers.slot[lane] + ((size_t)par * world + rank) * 4;
+        dst[0] = best;
+        dst[1] = (double)(idx + offset);
+        __threadfence_system();
+        dst[2] = tag;
+    }
+    double v = INFINITY;
+    long long gi = 0x7fffffffffffffffLL;
+    int timed_out = 0;
+    if (lane < world) {                                   // lane r collects rank r's pair
+        volatile double *src = peers.slot[rank] + ((size_t)par * world + lane) * 4;
+        long long spins = 0;
+        while (src[2] != tag) {
+            if (++spins > (1LL << 24)) { timed_out = 1; break; }
+        }
+        __threadfence_system();
+        v = src[0];
+        gi = (long long)src[1];
+        if (v != v) v = INFINITY;                         // NaN never wins (np.nanargmin-free semantics of dist.combine_argmin)
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const long long i2 = __shfl_xor_sync(0xffffffffu, gi, o);
+        better(v, gi, v2, i2);
+        timed_out |= __shfl_xor_sync(0xffffffffu, timed_out, o);
+    }
+    if (lane == 0) {
+        out[0] = v;
+        out[1] = (double)gi;
+        out[2] = (double)timed_out;
+        __threadfence_system();
+        out[3] = tag;
+    }
+}
+
+cudaError_t launch_argmin_exchange(const double *bv, const long long *bi, int nblocks, long long offset, void *const *peer_slots,
+                                   int world, int rank, unsigned long long seq, double *out, cudaStream_t s) {
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) return cudaErrorInvalidValue;
+    PeerSlots p;
+    for (int r = 0; r < 16; ++r) p.slot[r] = r < world ? (double *)peer_slots[r] : nullptr;
+    argmin_exchange_kernel<<<1, 32, 0, s>>>(bv, bi, nblocks, offset, p, world, rank, seq, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_argmin_partials(double *bv, long long *bi, int nblocks, long long offset, double *pair, cudaStream_t s) {
     argmin_partials_kernel<<<1, 32, 0, s>>>(bv, bi, nblocks, offset, pair);
     return cudaGetLastError();

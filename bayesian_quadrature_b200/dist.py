@@ -47,6 +47,55 @@ def all_argmin(local_min, local_idx, offset, device=None):
     return combine_argmin(out.cpu().numpy())
 
 
+class PairExchange(object):
+    """Cross-rank exchange of the (min, first global index) pair of a sharded choose_next step, done by the reduction
+    kernel itself (``bqb_choose_step_exchange``): every rank's exchange buffer is peer-mapped symmetric memory, the
+    kernel stores its pair into all of them over NVLink and reduces what the others stored into its own.  The result
+    lands in page-locked host memory, so a step needs no NCCL collective and no device-to-host copy call.
+
+    With one rank the buffer is ordinary device memory.  ``PairExchange.create`` returns None when symmetric memory is
+    not available (the caller then uses the NCCL all-gather of ``all_argmin`` / ``combine_argmin``)."""
+
+    def __init__(self, device, buf, ptrs, keep=None):
+        import ctypes
+        self.world, self.rank = world()
+        self.buf, self._keep = buf, keep
+        self.ptrs = (ctypes.c_void_p * self.world)(*[int(q) for q in ptrs])
+        self.out = torch.zeros(4, dtype=torch.float64).pin_memory()
+        self._out_np = self.out.numpy()
+        self.seq = 0
+
+    @classmethod
+    def create(cls, device):
+        W, _ = world()
+        if W == 1:
+            buf = torch.zeros(2 * W * 4, dtype=torch.float64, device=device)
+            return cls(device, buf, [buf.data_ptr()])
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty(2 * W * 4, dtype=torch.float64, device=device)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            ptrs = list(hdl.buffer_ptrs)
+            torch.cuda.synchronize(device)
+            dist.barrier()
+            return cls(device, buf, ptrs, keep=hdl)
+        except Exception as e:                        # no peer access / API not present: NCCL path
+            import warnings
+            warnings.warn("PairExchange: symmetric memory unavailable (%s); using the NCCL all-gather" % (e,))
+            return None
+
+    def step(self, batch, x_d, esm, ev, offset, inst=0):
+        """Enqueue scoring + fused reduce/exchange; returns after the stream has finished: (min, global index)."""
+        self.seq += 1
+        batch.choose_step_exchange(x_d, esm, ev, offset, self.ptrs, self.world, self.rank, self.seq, self.out.data_ptr(), inst=inst)
+        torch.cuda.current_stream().synchronize()
+        o = self._out_np
+        if o[3] != self.seq or o[2] != 0:
+            raise RuntimeError("PairExchange: a rank did not deliver its pair for step %d" % self.seq)
+        return float(o[0]), int(o[1])
+
+
 def all_gather_scores(local, n_total):
     """Concatenate the ranks' contiguous shards (shard_bounds order) into the full score vector."""
     W, _ = world()

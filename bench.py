@@ -227,9 +227,14 @@ def run_cuda(args):
     pair = torch.empty(2, dtype=torch.float64, device=dev)
     pairs = torch.empty(world, 2, dtype=torch.float64, device=dev) if world > 1 else None
 
+    # cross-rank exchange inside the reduction kernel (peer-mapped symmetric memory over NVLink); NCCL all-gather otherwise
+    exch = None if os.environ.get("BQB_EXCHANGE", "p2p") == "nccl" else bqdist.PairExchange.create(dev)
+
     def step():
-        # esm (bq.py:379-402), expected variance (bq.py:374-377) and the local (min, first global index) of the shard:
-        # the scoring kernel with its fused epilogue + one tiny reduction launch; the result stays on the device
+        # esm (bq.py:379-402), expected variance (bq.py:374-377) and the (min, first global index) over all shards:
+        # the scoring kernel with its fused epilogue + one tiny reduce-and-exchange launch; result in page-locked memory
+        if exch is not None:
+            return exch.step(batch, x_d, esm[0], evv, rank * NA)
         batch.choose_step_device(x_d, esm, evv, pair, offset=rank * NA)
         if world > 1:
             dist.all_gather_into_tensor(pairs.view(-1), pair)      # the path's only collective: W pairs of 16 B
@@ -333,7 +338,8 @@ def run_cuda(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C2: 1-D BQ, ns=%d nc=%d, expected_Z_var over a 10^6-point grid per GPU (%d points total)"
                                    % (NS, nc, na_total),
-                       "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "x_a sharded, %d rank(s)" % world},
+                       "l2": "flushed between timed steps (256 MiB memset)", "parallelism": "x_a sharded, %d rank(s)" % world,
+                       "exchange": "p2p stores from the reduction kernel (symmetric memory)" if exch is not None else "nccl all-gather"},
             "roofline": {"bound": "fp64", "kernel": "bq_score_kernel<KS=16,NT=2,WARPS=8,MINB=2,STREAM=0,TABN=2048,ALIGN=1>", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(), "traffic_unit": "bytes per launch (ncu dram read + write)",
                          "peak_source": peak_src,

@@ -173,6 +173,17 @@ int bqb_argmin_pair_device(bqb_batch *b, const double *d_v, long long n, long lo
 int bqb_choose_step_device(bqb_batch *b, int inst, const double *d_x_a, int na, double *d_esm, double *d_ev,
                            long long offset, double *d_pair, void *stream);
 
+/* bqb_choose_step_device whose reduction also does the cross-rank exchange of sharded runs (one process per GPU): the
+ * kernel that reduces this rank's partials stores its (min, first global index) pair into every rank's exchange
+ * buffer -- peer_slots[r] = device pointer, valid on THIS device, of rank r's buffer of 2 * world * 4 doubles, zero
+ * initialised (peer-mapped symmetric memory over NVLink; with world = 1 any device buffer) -- waits for the other
+ * ranks' pairs of the same step `seq` (1, 2, 3, ... identical on all ranks) and writes out4 = {global min, global first
+ * index, timed-out flag, seq}; out4 may be page-locked host memory.  Replaces the NCCL all-gather + local reduce +
+ * device-to-host copy of the deterministic choose_next (bq.py:663) across ranks.  Asynchronous on `stream`. */
+int bqb_choose_step_exchange(bqb_batch *b, int inst, const double *d_x_a, int na, double *d_esm, double *d_ev,
+                             long long offset, void *const *peer_slots, int world, int rank,
+                             unsigned long long seq, double *out4, void *stream);
+
 /* Per-instance (min, first index) of d_v [n_inst][stride] into DEVICE arrays d_min / d_idx [n_inst]: the
  * deterministic choose_next of a batch of independent problems (bq.py:663 per problem). */
 int bqb_argmin_rows_device(bqb_batch *b, const double *d_v, long long stride, long long n, double *d_min,

@@ -33,8 +33,22 @@ def main():
     assert idx_p == idx1 and mn_p == mn1 and xp == x_a[idx1], (idx_p, idx1, mn_p, mn1)
     xs, idx_s, mn_s = bqdist.choose_next_sharded(bq, x_a, htl, hl, ["h", "w"], shard="samples")
     assert idx_s == idx1 and abs(mn_s - mn1) <= 1e-12 * abs(mn1), (idx_s, idx1, mn_s, mn1)
+    # fused reduce + exchange (bqb_choose_step_exchange over peer-mapped symmetric memory) == the single-GPU argmin of
+    # expected_Z_var over the whole vector, for several consecutive steps (slot parity, step tags)
+    ex = bqdist.PairExchange.create(torch.device("cuda", local))
+    assert ex is not None, "symmetric memory unavailable on this box"
+    model = bq._device_model()
+    lo, hi = bqdist.shard_bounds(x_a.size, W, rank)
+    x_d = torch.from_numpy(x_a[lo:hi]).cuda()
+    esm_d = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+    ev_d = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+    want = (float(ref.min()), int(np.argmin(ref)))
+    for _ in range(5):
+        got = ex.step(model.batch, x_d, esm_d, ev_d, lo)
+        assert got == want, (got, want)
+    assert np.array_equal(ev_d.cpu().numpy(), ref[lo:hi])
     if rank == 0:
-        print("DIST_GPU_CHECK_OK world=%d argmin=%d" % (W, idx1))
+        print("DIST_GPU_CHECK_OK world=%d argmin=%d exchange=p2p" % (W, idx1))
     dist.destroy_process_group()
 
 
