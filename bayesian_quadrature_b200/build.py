@@ -2,6 +2,7 @@
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
@@ -10,6 +11,9 @@ SOURCES = ["bq_setup.cu", "bq_score.cu", "bq_reduce.cu", "bq_round.cu", "bq_capi
 HEADERS = ["bq_common.cuh", os.path.join("..", "..", "include", "bq_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-Xptxas", "-v"]
+#: bq_score.cu is compiled once per observation-capacity class (its instantiations only) plus once as the dispatcher,
+#: so that the classes build in parallel
+SCORE_CLASSES = [16, 64, 128, 160, 256]
 
 
 def _nvcc():
@@ -23,18 +27,38 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def _units():
+    """(source, object, extra flags) of every translation unit."""
+    units = []
+    for src in SOURCES:
+        base = src.replace(".cu", "")
+        if src == "bq_score.cu":
+            units.append((src, base + ".o", []))
+            units += [(src, "%s_%d.o" % (base, c), ["-DBQB_SCORE_CLASS=%d" % c]) for c in SCORE_CLASSES]
+        else:
+            units.append((src, base + ".o", []))
+    return units
+
+
+def _compile(unit):
+    src, obj, extra = unit
+    obj = os.path.join(CSRC, obj)
+    r = subprocess.run([_nvcc()] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    return unit, obj, r.returncode, r.stdout
+
+
 def build(force=False, verbose=False):
     if not force and not stale():
         return LIB
-    objs = []
-    log = []
-    for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        r = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj],
-                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        log.append(r.stdout)
-        if r.returncode:
-            raise RuntimeError("nvcc failed on %s:\n%s" % (src, r.stdout))
+    units = _units()
+    with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(_compile, units))
+    objs, log = [], []
+    for (src, _, extra), obj, rc, out in results:
+        log.append("==== %s %s\n%s" % (src, " ".join(extra), out))
+        if rc:
+            raise RuntimeError("nvcc failed on %s %s:\n%s" % (src, " ".join(extra), out))
         objs.append(obj)
     r = subprocess.run([_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

@@ -931,19 +931,43 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
 // nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 160 and 256 (operands streamed).  The tilings
 // are the measured best of the round-1 sweeps (profiles/ncu_score_r01.md); a resident instantiation falls back to the
 // streamed one when many candidates (scratch rows) push it over the shared-memory limit.
+//
+// This file is compiled once per capacity class (-DBQB_SCORE_CLASS=16|64|128|160|256: the instantiations of that class
+// only, so that the classes build in parallel) and once without the macro (the dispatcher).
+#define BQB_LAUNCH_DECL(C) cudaError_t launch_score_##C(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x)
+#ifndef BQB_SCORE_CLASS
+BQB_LAUNCH_DECL(16);
+BQB_LAUNCH_DECL(64);
+BQB_LAUNCH_DECL(128);
+BQB_LAUNCH_DECL(160);
+BQB_LAUNCH_DECL(256);
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     switch (a.lay.nsp_cap) {
-        case 16: return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream, grid_x);
-        case 64:
-            return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x);
-        case 128:
-            if (smem_need<32, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
-                return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
-            return launch_cfg<32, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
-        case 160: return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
-        case 256: return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
+        case 16: return launch_score_16(a, n_inst, sm_count, stream, grid_x);
+        case 64: return launch_score_64(a, n_inst, sm_count, stream, grid_x);
+        case 128: return launch_score_128(a, n_inst, sm_count, stream, grid_x);
+        case 160: return launch_score_160(a, n_inst, sm_count, stream, grid_x);
+        case 256: return launch_score_256(a, n_inst, sm_count, stream, grid_x);
         default: return cudaErrorInvalidValue;
     }
 }
+#elif BQB_SCORE_CLASS == 16
+BQB_LAUNCH_DECL(16) { return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream, grid_x); }
+#elif BQB_SCORE_CLASS == 64
+// (rolled pairs, free-running warps and 4 x 4-warp CTAs were all slower with band skipping: 0.31 / 0.37 / 0.34 / 0.47 ms vs 0.28)
+BQB_LAUNCH_DECL(64) { return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x); }
+#elif BQB_SCORE_CLASS == 128
+BQB_LAUNCH_DECL(128) {
+    if (smem_need<32, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
+        return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
+    return launch_cfg<32, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
+}
+#elif BQB_SCORE_CLASS == 160
+BQB_LAUNCH_DECL(160) { return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x); }
+#elif BQB_SCORE_CLASS == 256
+BQB_LAUNCH_DECL(256) { return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x); }
+#else
+#error "BQB_SCORE_CLASS must be 16, 64, 128, 160 or 256"
+#endif
 
 }  // namespace bqb
