@@ -50,7 +50,7 @@ SYMBOLS = {
     "bqb_argmin_device": (ctypes.c_int, [_vp, _vp, _ll, _dp, ctypes.POINTER(_ll), _vp]),
     "bqb_argmin_pair_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp]),
     "bqb_choose_step_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _ll, _vp, _vp]),
-    "bqb_choose_step_exchange": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _ll, ctypes.POINTER(_vp), ctypes.c_int,
+    "bqb_choose_step_exchange": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int, _vp, _vp, _ll, _ll, ctypes.POINTER(_vp), ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_ulonglong, _vp, _vp]),
     "bqb_argmin_rows_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp, _vp]),
     "bqb_batch_set_cutoff": (ctypes.c_int, [_vp, ctypes.c_double]),
@@ -304,10 +304,10 @@ class Batch(object):
         _check(load().bqb_choose_step_device(self._h, int(inst), _ptr(x_a), x_a.numel(), _ptr(esm), _ptr(ev), int(offset),
                                              _ptr(pair), _vp(stream) if stream else None), "bqb_choose_step_device")
 
-    def choose_step_exchange(self, x_a, esm, ev, offset, peer_ptrs, world, rank, seq, out_ptr, inst=0, stream=None):
+    def choose_step_exchange(self, x_a, esm, ev, offset, peer_ptrs, world, rank, seq, out_ptr, inst=0, stream=None, cyclic_block=0):
         """choose_step_device + cross-rank exchange in the reduction kernel (see dist.PairExchange); no host sync."""
         _check(load().bqb_choose_step_exchange(self._h, int(inst), _ptr(x_a), x_a.numel(), _ptr(esm), _ptr(ev), int(offset),
-                                               peer_ptrs, int(world), int(rank), int(seq), _vp(out_ptr),
+                                               int(cyclic_block), peer_ptrs, int(world), int(rank), int(seq), _vp(out_ptr),
                                                _vp(stream) if stream else None), "bqb_choose_step_exchange")
 
     def argmin_rows_device(self, v, mins, idxs, stream=None):

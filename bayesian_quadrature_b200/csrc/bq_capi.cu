@@ -33,8 +33,8 @@ cudaError_t launch_argmin(const double *v, long long n, double *scratch_val, lon
 cudaError_t launch_argmin_rows(const double *v, long long stride, long long n, int rows, double *mins, long long *idxs,
                                cudaStream_t s);
 cudaError_t launch_argmin_pair(const double *bv, const long long *bi, long long offset, double *pair, cudaStream_t s);
-cudaError_t launch_argmin_exchange(const double *bv, const long long *bi, int nblocks, long long offset, void *const *peer_slots,
-                                   int world, int rank, unsigned long long seq, double *out, cudaStream_t s);
+cudaError_t launch_argmin_exchange(const double *bv, const long long *bi, int nblocks, long long offset, long long cyc_block,
+                                   void *const *peer_slots, int world, int rank, unsigned long long seq, double *out, cudaStream_t s);
 cudaError_t launch_mt_seed(const unsigned *seeds, unsigned *mt, int *mti, int P, cudaStream_t s);
 cudaError_t launch_add_observations(double *x_s, double *l_s, int *ns, int stride, const double *prior, const double *x_new,
                                     const double *l_new, int P, int *overflow, cudaStream_t s);
@@ -566,11 +566,12 @@ int bqb_choose_step_device(bqb_batch *b, int inst, const double *d_x_a, int na, 
 }
 
 int bqb_choose_step_exchange(bqb_batch *b, int inst, const double *d_x_a, int na, double *d_esm, double *d_ev, long long offset,
-                             void *const *peer_slots, int world, int rank, unsigned long long seq, double *out4, void *stream) {
+                             long long cyclic_block, void *const *peer_slots, int world, int rank, unsigned long long seq,
+                             double *out4, void *stream) {
     int rc = check_ready(b, "bqb_choose_step_exchange");
     if (rc) return rc;
     if (inst < 0 || inst >= b->n_inst || !d_x_a || !d_ev || !peer_slots || !out4 || na < 1 || world < 1 || world > 16 || rank < 0 ||
-        rank >= world || seq == 0)
+        rank >= world || seq == 0 || cyclic_block < 0)
         return fail(BQB_EINVAL, "bqb_choose_step_exchange: bad arguments");
     CU(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
@@ -582,7 +583,7 @@ int bqb_choose_step_exchange(bqb_batch *b, int inst, const double *d_x_a, int na
     a.ev = d_ev; a.part_val = b->d_red_val; a.part_idx = b->d_red_idx;
     int grid_x = 0;
     CU(launch_score(a, 1, b->sm_count, s, &grid_x));
-    CU(launch_argmin_exchange(b->d_red_val, b->d_red_idx, grid_x, offset, peer_slots, world, rank, seq, out4, s));
+    CU(launch_argmin_exchange(b->d_red_val, b->d_red_idx, grid_x, offset, cyclic_block, peer_slots, world, rank, seq, out4, s));
     b->launches += 2;
     return 0;
 }

@@ -136,8 +136,8 @@ __global__ void argmin_partials_kernel(double *bv, long long *bi, int nblocks, l
 struct PeerSlots {
     double *slot[16];
 };
-__global__ void argmin_exchange_kernel(const double *bv, const long long *bi, int nblocks, long long offset, PeerSlots peers,
-                                       int world, int rank, unsigned long long seq, double *out) {
+__global__ void argmin_exchange_kernel(const double *bv, const long long *bi, int nblocks, long long offset, long long cyc_block,
+                                       PeerSlots peers, int world, int rank, unsigned long long seq, double *out) {
     const int lane = threadIdx.x;
     double best = INFINITY;
     long long idx = 0x7fffffffffffffffLL;
@@ -152,7 +152,9 @@ __global__ void argmin_exchange_kernel(const double *bv, const long long *bi, in
     if (lane < world) {                                   // lane r publishes to rank r
         volatile double *dst = peers.slot[lane] + ((size_t)par * world + rank) * 4;
         dst[0] = best;
-        dst[1] = (double)(idx + offset);
+        // global index of this rank's local index: contiguous shard (offset) or block-cyclic shards of cyc_block points
+        const long long g = cyc_block > 0 ? ((idx / cyc_block) * world + rank) * cyc_block + idx % cyc_block : idx + offset;
+        dst[1] = (double)g;
         __threadfence_system();
         dst[2] = tag;
     }
@@ -185,12 +187,12 @@ __global__ void argmin_exchange_kernel(const double *bv, const long long *bi, in
     }
 }
 
-cudaError_t launch_argmin_exchange(const double *bv, const long long *bi, int nblocks, long long offset, void *const *peer_slots,
-                                   int world, int rank, unsigned long long seq, double *out, cudaStream_t s) {
+cudaError_t launch_argmin_exchange(const double *bv, const long long *bi, int nblocks, long long offset, long long cyc_block,
+                                   void *const *peer_slots, int world, int rank, unsigned long long seq, double *out, cudaStream_t s) {
     if (world < 1 || world > 16 || rank < 0 || rank >= world) return cudaErrorInvalidValue;
     PeerSlots p;
     for (int r = 0; r < 16; ++r) p.slot[r] = r < world ? (double *)peer_slots[r] : nullptr;
-    argmin_exchange_kernel<<<1, 32, 0, s>>>(bv, bi, nblocks, offset, p, world, rank, seq, out);
+    argmin_exchange_kernel<<<1, 32, 0, s>>>(bv, bi, nblocks, offset, cyc_block, p, world, rank, seq, out);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,16 @@ def shard_bounds(n, world_size, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def cyclic_shard(x, world_size, rank, block):
+    """Block-cyclic shard of a vector whose length is a multiple of world_size * block: blocks rank, rank + W, rank + 2W, ...
+    Unlike contiguous shards, every rank gets the same mix of cheap (far from every observation) and expensive query
+    points, which matters since band skipping makes their cost differ."""
+    x = np.asarray(x)
+    if x.size % (world_size * block):
+        raise ValueError("vector length must be a multiple of world_size * block")
+    return np.ascontiguousarray(x.reshape(-1, world_size, block)[:, rank, :]).ravel()
+
+
 def combine_argmin(pairs):
     """pairs: [W, 2] array of (local min, global index of its first occurrence); NaN mins never win.
     Returns (min, index) with ties resolved to the smallest global index — np.argmin semantics."""
@@ -68,9 +78,12 @@ class PairExchange(object):
     @classmethod
     def create(cls, device):
         W, _ = world()
-        if W == 1:
-            buf = torch.zeros(2 * W * 4, dtype=torch.float64, device=device)
-            return cls(device, buf, [buf.data_ptr()])
+        import os
+        if W == 1 or os.environ.get("BQB_EXCHANGE") == "self":      # "self": diagnostic -- every rank exchanges with itself only
+            buf = torch.zeros(2 * 4, dtype=torch.float64, device=device)
+            ex = cls(device, buf, [buf.data_ptr()])
+            ex.world, ex.rank = 1, 0
+            return ex
         try:
             import torch.distributed._symmetric_memory as symm_mem
             buf = symm_mem.empty(2 * W * 4, dtype=torch.float64, device=device)
@@ -85,10 +98,20 @@ class PairExchange(object):
             warnings.warn("PairExchange: symmetric memory unavailable (%s); using the NCCL all-gather" % (e,))
             return None
 
-    def step(self, batch, x_d, esm, ev, offset, inst=0):
-        """Enqueue scoring + fused reduce/exchange; returns after the stream has finished: (min, global index)."""
+    def step_async(self, batch, x_d, esm, ev, offset, inst=0, cyclic_block=0):
+        """Enqueue scoring + fused reduce/exchange on the current stream and return at once (the ranks stay in step on the
+        device through the exchange itself); `result()` waits and reads the last step's pair."""
         self.seq += 1
-        batch.choose_step_exchange(x_d, esm, ev, offset, self.ptrs, self.world, self.rank, self.seq, self.out.data_ptr(), inst=inst)
+        batch.choose_step_exchange(x_d, esm, ev, offset, self.ptrs, self.world, self.rank, self.seq, self.out.data_ptr(), inst=inst,
+                                   cyclic_block=cyclic_block)
+
+    def step(self, batch, x_d, esm, ev, offset, inst=0, cyclic_block=0):
+        """One step, synchronously: (min, global index).  ``cyclic_block`` > 0: this rank holds blocks rank, rank + W, ... of
+        ``cyclic_block`` points (``cyclic_shard``) instead of one contiguous shard starting at ``offset``."""
+        self.step_async(batch, x_d, esm, ev, offset, inst=inst, cyclic_block=cyclic_block)
+        return self.result()
+
+    def result(self):
         torch.cuda.current_stream().synchronize()
         o = self._out_np
         if o[3] != self.seq or o[2] != 0:

@@ -178,10 +178,13 @@ int bqb_choose_step_device(bqb_batch *b, int inst, const double *d_x_a, int na, 
  * buffer -- peer_slots[r] = device pointer, valid on THIS device, of rank r's buffer of 2 * world * 4 doubles, zero
  * initialised (peer-mapped symmetric memory over NVLink; with world = 1 any device buffer) -- waits for the other
  * ranks' pairs of the same step `seq` (1, 2, 3, ... identical on all ranks) and writes out4 = {global min, global first
- * index, timed-out flag, seq}; out4 may be page-locked host memory.  Replaces the NCCL all-gather + local reduce +
- * device-to-host copy of the deterministic choose_next (bq.py:663) across ranks.  Asynchronous on `stream`. */
+ * index, timed-out flag, seq}; out4 may be page-locked host memory.  The global index of local point i is i + offset
+ * (contiguous shards, cyclic_block = 0) or ((i / cyclic_block) * world + rank) * cyclic_block + i % cyclic_block
+ * (block-cyclic shards: every rank sees the same mix of near- and far-field points, which band skipping makes cost
+ * differently).  Replaces the NCCL all-gather + local reduce + device-to-host copy of the deterministic choose_next
+ * (bq.py:663) across ranks.  Asynchronous on `stream`. */
 int bqb_choose_step_exchange(bqb_batch *b, int inst, const double *d_x_a, int na, double *d_esm, double *d_ev,
-                             long long offset, void *const *peer_slots, int world, int rank,
+                             long long offset, long long cyclic_block, void *const *peer_slots, int world, int rank,
                              unsigned long long seq, double *out4, void *stream);
 
 /* Per-instance (min, first index) of d_v [n_inst][stride] into DEVICE arrays d_min / d_idx [n_inst]: the

@@ -47,6 +47,14 @@ def main():
         got = ex.step(model.batch, x_d, esm_d, ev_d, lo)
         assert got == want, (got, want)
     assert np.array_equal(ev_d.cpu().numpy(), ref[lo:hi])
+    # the same with block-cyclic shards (global index computed by the exchange kernel)
+    blk, n_c = 1000, 100000
+    want_c = (float(ref[:n_c].min()), int(np.argmin(ref[:n_c])))
+    x_c = torch.from_numpy(bqdist.cyclic_shard(x_a[:n_c], W, rank, blk)).cuda()
+    esm_c, ev_c = torch.empty_like(x_c), torch.empty_like(x_c)
+    for _ in range(3):
+        got = ex.step(model.batch, x_c, esm_c, ev_c, 0, cyclic_block=blk)
+        assert got == want_c, (got, want_c)
     if rank == 0:
         print("DIST_GPU_CHECK_OK world=%d argmin=%d exchange=p2p" % (W, idx1))
     dist.destroy_process_group()
