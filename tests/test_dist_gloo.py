@@ -27,6 +27,22 @@ def test_combine_argmin_ties_and_nan():
     assert bqdist.combine_argmin([[np.nan, 0], [2.0, 3]]) == (2.0, 3)
 
 
+def test_cyclic_shard_and_its_index_map():
+    """Block-cyclic shards partition the vector, and the global index the exchange kernel computes for a local index
+    (include/bq_b200.h, bqb_choose_step_exchange) points back at the same element."""
+    x = np.arange(24000, dtype=np.float64)
+    for W, blk in ((1, 1000), (2, 1000), (3, 2000), (8, 500)):
+        parts = [bqdist.cyclic_shard(x, W, r, blk) for r in range(W)]
+        assert sorted(np.concatenate(parts).tolist()) == x.tolist()
+        for r, part in enumerate(parts):
+            i = np.arange(part.size)
+            g = ((i // blk) * W + r) * blk + i % blk
+            assert np.array_equal(x[g], part)
+            assert (np.diff(g) > 0).all()              # local order = global order: "first minimiser" survives sharding
+    with pytest.raises(ValueError):
+        bqdist.cyclic_shard(x, 7, 0, 1000)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
