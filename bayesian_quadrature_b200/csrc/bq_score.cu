@@ -14,16 +14,22 @@
 //   * the A operand (c L_ss^-1, the candidate rows W, g_gamma, g_alpha; and c L_tl^-1) is stored
 //     by the setup kernel in fragment order, so one conflict-free LDS.64 per lane feeds NT DMMAs.
 //     For ns <= 128 it is shared-memory resident for the life of the CTA; for ns <= 256 it does
-//     not fit (2 x 264 KB) and is streamed from L2 through a shared-memory chunk buffer, all warps
-//     of the CTA consuming a chunk in lock-step (STREAM);
+//     not fit (2 x 264 KB) and the part that is needed -- the band slab, below -- is fetched with
+//     TMA bulk copies completing on mbarriers (STREAM);
 //   * only v.v is needed from the triangular part: accumulators are squared and summed in
 //     registers, one block of 8 rows at a time, and no n x n (or n x T) intermediate is stored;
 //   * a warp works on a super-tile of 32 points (32 / (8 NT) sub-tiles); per-point partial results
 //     (v_s.v_s, v_t.v_t, tm, the candidate rows) are parked in a small shared-memory scratch and the
-//     candidate block (nc <= 16) plus the scalar algebra then run with one point per lane.
+//     candidate block (nc <= 16) plus the scalar algebra then run with one point per lane;
+//   * BAND SKIPPING: E decays so fast that, per point, only a short band of observations carries
+//     anything at double precision.  Per super-tile a warp derives a mask of relevant k-steps (groups of
+//     four observations; gen_masks) for each of the two kernels; k-steps outside it are neither
+//     exponentiated (gen_exps) nor multiplied (mask-predicated / jump-table DMMA loops), and the streamed
+//     variants fetch only the rows and columns of the operands that the CTA's masks touch.  The setup kernel
+//     sorts the observations, so the band is contiguous.  cut_arg = +inf makes every k-step relevant.
 //
-// Grid: persistent CTAs (a multiple of the SM count) striding over point tiles; gridDim.y = model
-// instances (hyper-parameter sets or independent problems).
+// Grid: persistent CTAs (a multiple of the SM count); super-tiles are dealt round-robin with a
+// unit-granular remainder; gridDim.y = model instances (hyper-parameter sets or independent problems).
 #include "bq_common.cuh"
 
 namespace bqb {
@@ -108,7 +114,8 @@ template <> struct KMask<64> { using type = unsigned long long; };
 // e^-72 = 5e-32 of that point's leading element: with cond(K) < 1e9 it cannot change any of the point's results at
 // double precision ("band skipping").  K-steps in which every element of the sub-tile is that small are
 // neither exponentiated nor multiplied.
-constexpr double CUT_ARG = 72.0;
+constexpr double CUT_ARG = 72.0;      // the default of ScoreArgs::cut_arg (bq_common.cuh) and bqb_batch_set_cutoff
+static_assert(CUT_ARG == 72.0, "keep in step with ScoreArgs::cut_arg and include/bq_b200.h");
 
 // Cross-kernel B fragments of one sub-tile, bf[ks][nt] = exp(-(x - x_s[k])^2 / (2 w^2)), k = 4 ks + (lane & 3), are
 // produced in two steps.
