@@ -72,6 +72,7 @@ struct bqb_batch {
     int *d_flags = nullptr;
     cudaStream_t pipe[2] = {nullptr, nullptr};
     int *h_flags = nullptr;            // pinned
+    int *h_cta_flags = nullptr;        // pinned, mapped: per-CTA status words of the zero-copy scoring launch
     double *d_red_val = nullptr;
     long long *d_red_idx = nullptr;
     std::vector<double> h_hdr;
@@ -147,6 +148,7 @@ void bqb_batch_destroy(bqb_batch *b) {
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaStream_t st : b->pipe) if (st) cudaStreamDestroy(st);
     if (b->h_flags) cudaFreeHost(b->h_flags);
+    if (b->h_cta_flags) cudaFreeHost(b->h_cta_flags);
     delete b;
 }
 
@@ -465,12 +467,16 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
     if (nchunk < 1) nchunk = 1;
     if (nchunk > 8) nchunk = 8;
     int per = ((na + nchunk - 1) / nchunk + 255) & ~255;
-    CU(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->n_inst, b->pipe[0]));
+    const bool zc = in_mapped && out_mapped;              // one launch; status words come back through mapped memory too
+    if (zc && !b->h_cta_flags) CU(cudaMallocHost(&b->h_cta_flags, sizeof(int) * 4096));
+    if (!zc) CU(cudaMemsetAsync(b->d_flags, 0, sizeof(int) * b->n_inst, b->pipe[0]));
     if (nchunk > 1) CU(cudaStreamSynchronize(b->pipe[0]));
+    int zc_grid = 0;
     ScoreArgs a;
     a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
     a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.xa_stride = 0;
-    a.em = nullptr; a.status = nullptr; a.exp_tab = b->d_tab; a.flags = b->d_flags; a.inst0 = 0; a.ndb_max = b->ndb_max;
+    a.em = nullptr; a.status = nullptr; a.exp_tab = b->d_tab; a.flags = zc ? nullptr : b->d_flags; a.inst0 = 0; a.ndb_max = b->ndb_max;
+    a.cta_flags = zc ? b->h_cta_flags : nullptr;
     int c = 0;
     for (int lo = 0; lo < na; lo += per, ++c) {
         const int n = (na - lo < per) ? na - lo : per;
@@ -486,7 +492,7 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
             // fused epilogue: Zm^2 + Zv - esm written straight into the caller's page-locked array
             a.esm = nullptr; a.ev = (double *)dout + lo;
             a.part_val = b->d_red_val + 2048 * (c & 1); a.part_idx = b->d_red_idx + 2048 * (c & 1);
-            CU(launch_score(a, 1, b->sm_count, s));
+            CU(launch_score(a, 1, b->sm_count, s, &zc_grid));
             b->launches += 1;
         } else {
             a.esm = b->d_esm + lo; a.ev = nullptr;
@@ -497,6 +503,13 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
         }
     }
     if (nchunk > 1) CU(cudaStreamSynchronize(b->pipe[1]));
+    if (zc) {
+        CU(cudaStreamSynchronize(b->pipe[0]));
+        int fl = 0;
+        for (int i = 0; i < zc_grid && i < 4096; ++i) fl |= b->h_cta_flags[i];
+        if (flags_out) *flags_out = fl;
+        return 0;
+    }
     CU(cudaMemcpyAsync(b->h_flags, b->d_flags, sizeof(int), cudaMemcpyDeviceToHost, b->pipe[0]));
     CU(cudaStreamSynchronize(b->pipe[0]));
     if (flags_out) *flags_out = *b->h_flags;

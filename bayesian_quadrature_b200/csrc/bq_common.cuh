@@ -90,6 +90,7 @@ struct ScoreArgs {
     long long out_stride = 0;
     const double *exp_tab = nullptr;    // [EXP_TAB]
     int *flags = nullptr;               // [B] OR of every point's status bits (may be null)
+    int *cta_flags = nullptr;           // [gridDim.y][gridDim.x] the same per CTA, written with plain stores (may be null)
     int inst0 = 0;
     int ndb_max = 1;                    // dense row blocks to reserve scratch for: ceil((max nc + 2) / 8)
     // optional fused epilogue of choose_next / expected_Z_var (single-instance launches only):

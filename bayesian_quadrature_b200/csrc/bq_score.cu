@@ -535,6 +535,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     const int inst = a.inst0 + blockIdx.y;
     const double *M = a.models + (size_t)inst * lay.total;
 
+    __shared__ int s_cta_st;                                // OR of the status bits of this CTA's points (a.cta_flags)
+    if (tid == 0) s_cta_st = 0;
     for (int i = tid; i < TABN; i += THREADS) s_tab[i] = a.exp_tab[(TABN == 2048 ? 0 : 2048) + i];
     for (int i = tid; i < lay.n_small; i += THREADS) s_small[i] = M[i];
     __syncthreads();
@@ -867,11 +869,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
             }
             if (o_em) o_em[p] = em;
             if (o_st) o_st[p] = st;
-            if (st && a.flags) atomicOr(a.flags + inst, st);
+            if (st) {                                       // rare: shortcut / fallback / invalid points
+                if (a.flags) atomicOr(a.flags + inst, st);
+                if (a.cta_flags) atomicOr(&s_cta_st, st);
+            }
         }
         __syncwarp();
     }
     if (a.work && lane == 0 && n_kstep) atomicAdd(a.work, n_kstep * NT);     // DMMA instructions of this warp
+    if (a.cta_flags) {                                      // one plain store per CTA (the array may be page-locked host memory)
+        __syncthreads();
+        if (tid == 0) a.cta_flags[blockIdx.y * gridDim.x + blockIdx.x] = s_cta_st;
+    }
     if (EPI) {                                              // (min, first index) of this CTA's points
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

@@ -6,14 +6,19 @@
 
 Workload (config.workload): BASELINE.json configs[1] — 1-D BQ, 64 observations, expected_Z_var over
 a 10^6-point grid (SURVEY.md §8(d) generator).  A *step* is one pass of the hot path over the
-grid: the scoring kernel (esm, em, status for every point), the expected-variance kernel
-(Zm^2 + Zv - esm) and the deterministic (min, first index) reduction choose_next needs; at N > 1
-every rank scores its own 10^6-point shard of an N x 10^6 grid (weak scaling) and the ranks
-exchange their (min, index) pairs with one NCCL all-gather.  The per-hyper-set setup kernel (Gram,
-Cholesky, Z_mean, Z_var — amortised over the grid) is timed separately (setup_ms).
+grid: the scoring kernel (esm for every point, expected variance Zm^2 + Zv - esm in its epilogue,
+per-CTA minima) and one small kernel that reduces them to the deterministic (min, first index)
+choose_next needs and — at N > 1 — exchanges the ranks' pairs over peer-mapped memory (NCCL
+all-gather if symmetric memory is unavailable); the result lands in page-locked host memory.  At
+N > 1 every rank scores 10^6 points of an N x 10^6 grid (weak scaling, block-cyclic shards).  The
+per-hyper-set setup kernel (Gram, Cholesky, Z_mean, Z_var — amortised over the grid)
+is timed separately (setup_ms).
 
-`value` is device-resident throughput (inputs already in HBM); `e2e` is the same pass through the
-public host API with host buffers, H2D and D2H copies inside the timed region.
+Timing: W warm-up steps, then K steps enqueued back to back between a barrier + synchronize on both
+sides, each bracketed by CUDA events on the launching stream; cold L2 through eight rotating 24 MB
+input/output sets (192 MB > 126 MB of L2); max over ranks.  `value` is device-resident throughput
+(inputs already in HBM); `e2e` is the same pass through the public host API (BQ.expected_Z_var) with
+page-locked host buffers, the host-to-device and device-to-host traffic inside the timed region.
 """
 import argparse
 import json

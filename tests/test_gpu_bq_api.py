@@ -74,6 +74,27 @@ def test_expected_squared_mean_valid_and_params():
             bq.expected_Z_var(np.array([0.1, bad]))
 
 
+def test_expected_Z_var_zero_copy_path_equals_the_staged_path():
+    """Page-locked query vectors are read by the kernel straight from host memory and the result is written straight
+    into the (page-locked) result array; status words come back per CTA through mapped memory.  Same values, same
+    exceptions as with pageable arrays."""
+    import torch
+    from bayesian_quadrature_b200 import BQ, GaussianKernel, synthetic
+    bq = synthetic.make_bq(BQ, GaussianKernel, 64)
+    x = synthetic.query_grid(64, 300007)
+    x[1234] = bq.x_s[5]                                # a shortcut point (bq.py:456-459)
+    x_pin = torch.from_numpy(x).pin_memory().numpy()
+    ev_staged = bq.expected_Z_var(x)                   # pageable input: staged H2D chunks
+    ev_zc = bq.expected_Z_var(x_pin)
+    assert np.array_equal(ev_zc, ev_staged)
+    assert ev_zc[1234] == bq.Z_mean() ** 2 + bq.Z_var() - bq.Z_mean() ** 2
+    for bad in (np.nan, np.inf):
+        x_bad = torch.from_numpy(x).pin_memory().numpy()
+        x_bad[299999] = bad
+        with pytest.raises(ValueError):
+            bq.expected_Z_var(x_bad)
+
+
 def test_expected_squared_mean_single_observation():
     # reference test_expected_squared_mean_1 (test_bq_object.py:286-300)
     X = np.array([0.0])
