@@ -162,11 +162,15 @@ def test_hyper_set_batch_vs_reference(lib):
     b.close()
 
 
-def test_independent_problems_batch(lib, oracle):
-    """C5 semantics: instances with different ns / nc / data in one batch, each with its own x_a."""
-    rs = np.random.RandomState(11)
-    B, cap = 6, 40
-    ns = rs.randint(20, cap + 1, B)
+@pytest.mark.parametrize("cap,lo", [(40, 20), (128, 70), (150, 10), (256, 100)])
+def test_independent_problems_batch(lib, oracle, cap, lo):
+    """C5 semantics: instances with different ns / nc / data in one batch, each with its own x_a -- in every kind of
+    scoring kernel (resident, resident rolled, streamed), with observations in arbitrary order (the setup kernel sorts
+    them) and instances far smaller than the batch's capacity class."""
+    rs = np.random.RandomState(11 + cap)
+    B = 6 if cap <= 128 else 4
+    ns = rs.randint(lo, cap + 1, B)
+    ns[0] = cap
     nc = rs.randint(0, 4, B)
     x_s, l_s, x_c = np.zeros((B, cap)), np.ones((B, cap)), np.zeros((B, 16))
     x_a = np.empty((B, 700))
@@ -175,6 +179,8 @@ def test_independent_problems_batch(lib, oracle):
         xs = 1.25 * (np.arange(ns[i]) - (ns[i] - 1) / 2.0) + rs.uniform(-0.1, 0.1, ns[i])
         ls = np.exp(-0.5 * ((xs - rs.uniform(-3, 3)) / 6.0) ** 2) * 0.2 + 1e-4
         xc = np.sort(rs.choice(xs[:-1], nc[i], replace=False) + 0.625)
+        perm = rs.permutation(ns[i])
+        xs, ls = xs[perm], ls[perm]
         x_s[i, :ns[i]], l_s[i, :ns[i]], x_c[i, :nc[i]] = xs, ls, xc
         x_a[i] = rs.uniform(xs.min() - 8, xs.max() + 8, 700)
         models.append(oracle.OracleModel(xs, ls, xc, (15, 2, 0), (0.2, 1.3, 0), 0.0, 10.0 * (ns[i] / 8.0) ** 2, 0.5))
