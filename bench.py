@@ -372,7 +372,7 @@ def run_cuda(args):
                                    % (NS, nc, na_total),
                        "l2": l2_note, "parallelism": "x_a sharded, %d rank(s), %s" % (world, "block-cyclic shards of %d points" % CYC if cyc else "contiguous shards"),
                        "exchange": "p2p stores from the reduction kernel (symmetric memory)" if exch is not None else "nccl all-gather"},
-            "roofline": {"bound": "fp64", "kernel": "bq_score_kernel<KS=16,NT=2,WARPS=8,MINB=2,STREAM=0,TABN=2048,ALIGN=1>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "tensor", "pipe": "FP64 DMMA (mma.m8n8k4.f64; shares the FP64 datapath with DFMA)", "kernel": "bq_score_kernel<KS=16,NT=2,WARPS=8,MINB=2,STREAM=0,TABN=2048,ALIGN=1>", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic(), "traffic_unit": "bytes per launch (ncu dram read + write)",
                          "peak_source": peak_src,
                          "flop_per_eval": wf, "exp_per_eval": w_exp(NS, nc), "kernel_ms": kern_ms_avg,
