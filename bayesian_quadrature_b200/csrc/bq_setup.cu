@@ -57,7 +57,7 @@ constexpr int CHB = 32;                      // Cholesky panel width
 constexpr int CH_STRIDE = CHB + 1;           // padded panel stride: conflict-free when lanes walk rows
 // dynamic shared memory (doubles) for matrices of order <= ncap: Cholesky block + panel, or 32 staged rows of L
 __host__ __device__ inline int setup_smem_doubles(int ncap) {
-    const int a = (CHB + ncap) * CH_STRIDE, b = CHB * (ncap + 1);
+    const int a = (CHB + ncap) * CH_STRIDE, b = CHB * (ncap + 1) + 2 * CHB * CH_STRIDE;     // chol_lower / tri_inverse
     return a > b ? a : b;
 }
 
@@ -134,12 +134,18 @@ __device__ int chol_lower(double *A, int ld, int n, double *sm) {
     return 0;
 }
 
-// X = L^-1 (lower, row-major, both ld): X[i][c] = (delta_ic - sum_{k=c}^{i-1} L[i][k] X[k][c]) / L[i][i].
-// One thread per column c: a column only depends on itself, so rows need no barrier; blocks of 32 rows of L
-// are staged in shared memory (one barrier pair per block) and read as warp broadcasts, X[k][c] is
-// contiguous across the warp.
+// X = L^-1 (lower, row-major, both ld; X is written as exact zeros above the diagonal), blocked by 32:
+//     X_II = L_II^-1,      X_IJ = -X_II (sum_{K=J}^{I-1} L_IK X_KJ)   for J < I.
+// Block rows are sequential (I needs the block rows above it); inside one, all threads work: the 32-row panel of L is
+// staged in shared memory, thread (warp w, lane c) accumulates rows w, w+8, w+16, w+24 of column c of a 32 x 32 block
+// product (L from shared memory as warp broadcasts, X_KJ from global / L2 memory, contiguous across the warp), the block
+// passes through shared memory once, and the same thread finishes its four rows of X_IJ.  (The previous version gave
+// every column to one thread, n^2 / 2 dependent global loads long: 27 % of the setup kernel's samples at ns = 128.)
 __device__ void tri_inverse(const double *L, double *X, int ld, int n, double *sm) {
-    const int tid = threadIdx.x, rs = ld + 1;        // staged row stride (ld = ncap)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = SETUP_THREADS / 32;
+    const int rs = ld + 1;                               // staged row stride (ld = ncap)
+    double *XD = sm + CHB * rs;                          // [32][33] X_II
+    double *SJ = XD + CHB * CH_STRIDE;                   // [32][33] one block of the sum
     for (int ib = 0; ib < n; ib += CHB) {
         const int h = (n - ib < CHB) ? n - ib : CHB, wdt = ib + h;       // rows ib .. ib+h-1, columns 0 .. wdt-1
         __syncthreads();
@@ -148,19 +154,53 @@ __device__ void tri_inverse(const double *L, double *X, int ld, int n, double *s
             sm[r * rs + k] = (k <= ib + r) ? L[(size_t)(ib + r) * ld + k] : 0.0;
         }
         __syncthreads();
-        for (int c = tid; c < n; c += SETUP_THREADS) {
-            const int c0 = c & ~31;                     // the warp's first column keeps the k loop warp-uniform
-            for (int r = 0; r < h; ++r) {
-                const int i = ib + r;
-                const double *row = sm + r * rs;
+        // X_II: forward substitution per column, one warp (lane = column)
+        if (warp == 0) {
+            const int c = lane;
+            for (int r = 0; r < CHB; ++r) {
                 double out = 0.0;
-                if (c <= i) {
-                    double sacc = (c == i) ? 1.0 : 0.0;
-                    for (int k = c0; k < i; ++k) sacc = fma(-row[k], X[(size_t)k * ld + c], sacc);   // X is 0 above the diagonal
-                    out = sacc / row[i];
+                if (r < h && c <= r && c < h) {
+                    double sacc = (c == r) ? 1.0 : 0.0;
+                    const double *row = sm + r * rs + ib;
+                    for (int k = c; k < r; ++k) sacc = fma(-row[k], XD[k * CH_STRIDE + c], sacc);
+                    out = sacc / row[r];
                 }
-                X[(size_t)i * ld + c] = out;
+                XD[r * CH_STRIDE + c] = out;             // own column only: no synchronisation needed between rows
             }
+        }
+        __syncthreads();
+        for (int e = tid; e < h * h; e += SETUP_THREADS) {
+            const int r = e / h, c = e - r * h;
+            X[(size_t)(ib + r) * ld + ib + c] = XD[r * CH_STRIDE + c];
+        }
+        // zeros right of the diagonal block (rows of this block row, columns past it)
+        for (int e = tid; e < h * (n - wdt); e += SETUP_THREADS) {
+            const int r = e / (n - wdt), c = e - r * (n - wdt);
+            X[(size_t)(ib + r) * ld + wdt + c] = 0.0;
+        }
+        // X_IJ for the block columns left of the diagonal
+        for (int jb = 0; jb < ib; jb += CHB) {
+            double acc[CHB / 8];
+#pragma unroll
+            for (int q = 0; q < CHB / 8; ++q) acc[q] = 0.0;
+            for (int k = jb; k < ib; ++k) {              // X[k][jb + lane] is zero for k < jb + lane (upper part of X_JJ)
+                const double xk = X[(size_t)k * ld + jb + lane];
+#pragma unroll
+                for (int q = 0; q < CHB / 8; ++q) acc[q] = fma(sm[(warp + nw * q) * rs + k], xk, acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < CHB / 8; ++q) SJ[(warp + nw * q) * CH_STRIDE + lane] = acc[q];
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < CHB / 8; ++q) {
+                const int r = warp + nw * q;
+                if (r < h) {
+                    double sacc = 0.0;
+                    for (int k = 0; k <= r; ++k) sacc = fma(XD[r * CH_STRIDE + k], SJ[k * CH_STRIDE + lane], sacc);
+                    X[(size_t)(ib + r) * ld + jb + lane] = -sacc;
+                }
+            }
+            __syncthreads();                             // SJ is reused by the next block column
         }
     }
     __syncthreads();
@@ -178,11 +218,34 @@ __device__ void lower_matvec(const double *X, int ld, int n, const double *v, do
     __syncthreads();
 }
 
-// out[c] = sum_{i>=c} X[i][c] v[i]   (thread per column)
-__device__ void lower_matvec_t(const double *X, int ld, int n, const double *v, double *out) {
+// out[c] = sum_{i>=c} X[i][c] v[i]: warp w takes rows w, w + 8, ... with its lanes across the columns (contiguous reads),
+// partial sums per warp in registers, combined through shared memory in warp order (deterministic).  (One thread per
+// column walking the rows was 10 % of the kernel's samples: n dependent global loads per thread.)
+__device__ void lower_matvec_t(const double *X, int ld, int n, const double *v, double *out, double *sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = SETUP_THREADS / 32;
+    constexpr int NQ = (SETUP_NMAX + 31) / 32;
+    double acc[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) acc[q] = 0.0;
+    for (int i = warp; i < n; i += nw) {
+        const double vi = v[i];
+        const double *row = X + (size_t)i * ld;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int c = lane + 32 * q;
+            if (c <= i) acc[q] = fma(row[c], vi, acc[q]);
+        }
+    }
+    __syncthreads();                                     // sm may still be in use by the caller's previous phase
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int c = lane + 32 * q;
+        if (c < n) sm[warp * ld + c] = acc[q];
+    }
+    __syncthreads();
     for (int c = threadIdx.x; c < n; c += SETUP_THREADS) {
         double s = 0;
-        for (int i = c; i < n; ++i) s += X[(size_t)i * ld + c] * v[i];
+        for (int w = 0; w < nw; ++w) s += sm[w * ld + c];
         out[c] = s;
     }
     __syncthreads();
@@ -281,7 +344,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) bq_setup_kernel(SetupArgs a)
     tri_inverse(Ltl, Xtl, ncap, ns, s_vec);
     // ---- P5: a_tl = K_tl^-1 tl_s
     lower_matvec(Xtl, ncap, ns, tl_s, tmp);
-    lower_matvec_t(Xtl, ncap, ns, tmp, a_tl);
+    lower_matvec_t(Xtl, ncap, ns, tmp, a_tl, s_vec);
     // ---- P6: l_c = exp(gp_log_l.mean(x_c))  (bq.py:985 / :942-950), one warp per candidate
     for (int j = warp; j < nc; j += nw) {
         double m = 0;
@@ -333,8 +396,8 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) bq_setup_kernel(SetupArgs a)
     // ---- P10: pattern-independent pieces
     lower_matvec(Xl, ncap, ns, b_sc, u_s);       // u_s  = L_ss^-1 b_s
     lower_matvec(Xl, ncap, ns, l_sc, ua_s);      // ua_s = L_ss^-1 l_s
-    lower_matvec_t(Xl, ncap, ns, u_s, gg);       // g_gamma = L_ss^-T u_s
-    lower_matvec_t(Xl, ncap, ns, ua_s, ga);      // g_alpha = L_ss^-T ua_s
+    lower_matvec_t(Xl, ncap, ns, u_s, gg, s_vec);       // g_gamma = L_ss^-T u_s
+    lower_matvec_t(Xl, ncap, ns, ua_s, ga, s_vec);      // g_alpha = L_ss^-T ua_s
     // W[j][k] = -sum_{i>=k} C[j][i] Linv[i][k],  C = L[ns + j][0:ns]
     for (int e = tid; e < nc * ns; e += SETUP_THREADS) {
         const int j = e / ns, k = e - j * ns;
@@ -398,7 +461,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, 3) bq_setup_kernel(SetupArgs a)
         tmp[i] = s;
     }
     __syncthreads();
-    lower_matvec_t(Xl, ncap, ns, tmp, alpha);
+    lower_matvec_t(Xl, ncap, ns, tmp, alpha, s_vec);
     double sumlog_l = 0;
     {
         double p = 0;
