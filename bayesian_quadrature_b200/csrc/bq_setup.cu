@@ -81,22 +81,31 @@ __device__ int chol_lower(double *A, int ld, int n, double *sm) {
             D[r * CH_STRIDE + c] = (c <= r) ? A[(size_t)(jb + r) * ld + jb + c] : 0.0;
         }
         __syncthreads();
-        // diagonal block, unblocked, one warp (w <= 32): lane r owns row r
-        if (warp == 0) {
+        // diagonal block in shared memory, all threads: per column a pivot, the scaled column (32 threads) and the rank-1
+        // update of the trailing block spread over the CTA; two barriers per column.  (One warp updating its rows
+        // serially while seven waited cost ~15 k cycles per block.)  The pivots go to a side array so that nobody
+        // overwrites D[j][j] while others still read it.
+        {
+            __shared__ double s_diag[CHB];
             for (int j = 0; j < w; ++j) {
                 const double d = D[j * CH_STRIDE + j];
-                if (!(d > 0.0)) { if (lane == 0 && s_info == 0) s_info = jb + j + 1; break; }
+                if (!(d > 0.0)) { if (tid == 0 && s_info == 0) s_info = jb + j + 1; break; }     // uniform: every thread reads the same d
                 const double dj = sqrt(d);
-                __syncwarp();
-                if (lane == j) D[j * CH_STRIDE + j] = dj;
-                if (lane > j && lane < w) D[lane * CH_STRIDE + j] /= dj;
-                __syncwarp();
-                if (lane > j && lane < w) {
-                    const double lij = D[lane * CH_STRIDE + j];
-                    for (int k = j + 1; k <= lane; ++k) D[lane * CH_STRIDE + k] -= lij * D[k * CH_STRIDE + j];
+                const int m = w - j - 1;                                   // rows / columns still below / right of j
+                if (tid == 0) s_diag[j] = dj;
+                if (tid < m) D[(j + 1 + tid) * CH_STRIDE + j] /= dj;
+                __syncthreads();
+                for (int e = tid; e < m * m; e += SETUP_THREADS) {
+                    const int rr = e / m, kk = e - rr * m;
+                    if (kk <= rr) {
+                        const int r = j + 1 + rr, k = j + 1 + kk;
+                        D[r * CH_STRIDE + k] = fma(-D[r * CH_STRIDE + j], D[k * CH_STRIDE + j], D[r * CH_STRIDE + k]);
+                    }
                 }
-                __syncwarp();
+                __syncthreads();
             }
+            __syncthreads();
+            if (s_info == 0 && tid < w) D[tid * CH_STRIDE + tid] = s_diag[tid];
         }
         __syncthreads();
         if (s_info) return s_info;
