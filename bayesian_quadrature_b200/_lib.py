@@ -54,6 +54,7 @@ SYMBOLS = {
                                                 ctypes.c_int, ctypes.c_ulonglong, _vp, _vp]),
     "bqb_argmin_rows_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp, _vp]),
     "bqb_batch_set_cutoff": (ctypes.c_int, [_vp, ctypes.c_double]),
+    "bqb_batch_set_presort": (ctypes.c_int, [_vp, ctypes.c_int]),
     "bqb_batch_work_counter": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
     "bqb_launch_count": (ctypes.c_ulonglong, [_vp]),
     "bqb_model_doubles": (ctypes.c_int, [_vp]),
@@ -318,6 +319,10 @@ class Batch(object):
     def set_cutoff(self, cut_arg):
         """Relevance cut-off of the band skipping (default 72; float('inf') = dense algorithm)."""
         _check(load().bqb_batch_set_cutoff(self._h, float(cut_arg)), "bqb_batch_set_cutoff")
+
+    def set_presort(self, mode):
+        """Pre-sort of unsorted query vectors in the host entry points: 0 never, 1 automatic (default), 2 always."""
+        _check(load().bqb_batch_set_presort(self._h, int(mode)), "bqb_batch_set_presort")
 
     def work_counter(self, enable=True):
         """DMMA instructions executed since the last call (0 if the counter was off); (re)arms or disarms the counter."""

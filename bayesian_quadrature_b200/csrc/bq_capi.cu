@@ -35,6 +35,8 @@ cudaError_t launch_argmin_rows(const double *v, long long stride, long long n, i
 cudaError_t launch_argmin_pair(const double *bv, const long long *bi, long long offset, double *pair, cudaStream_t s);
 cudaError_t launch_argmin_exchange(const double *bv, const long long *bi, int nblocks, long long offset, long long cyc_block,
                                    void *const *peer_slots, int world, int rank, unsigned long long seq, double *out, cudaStream_t s);
+cudaError_t sort_points(const double *d_x, int n, double *d_x_sorted, int *d_iota, int *d_perm, void *temp, size_t *temp_bytes,
+                        cudaStream_t s);
 cudaError_t launch_mt_seed(const unsigned *seeds, unsigned *mt, int *mti, int P, cudaStream_t s);
 cudaError_t launch_add_observations(double *x_s, double *l_s, int *ns, int stride, const double *prior, const double *x_new,
                                     const double *l_new, int P, int *overflow, cudaStream_t s);
@@ -64,6 +66,12 @@ struct bqb_batch {
     // scoring: relevance cut-off (bq_score.cu, CUT_ARG; +inf = dense) and the optional executed-work counter
     double cut_arg = 72.0;
     unsigned long long *d_work_ctr = nullptr;
+    // pre-sort of query vectors that do not look sorted (bq_sort.cu): 0 never, 1 automatic (default), 2 always
+    int presort = 1;
+    double *d_xsorted = nullptr;
+    int *d_perm = nullptr, *d_iota = nullptr;
+    void *d_sort_tmp = nullptr;
+    size_t cap_sort = 0, cap_sort_tmp = 0;
     double *d_xs = nullptr, *d_ls = nullptr, *d_xc = nullptr, *d_hyp = nullptr, *d_prior = nullptr;
     // host-buffer scoring staging (grown on demand)
     double *d_xa = nullptr, *d_esm = nullptr, *d_em = nullptr;
@@ -144,7 +152,7 @@ void bqb_batch_destroy(bqb_batch *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     void *ptrs[] = {b->d_models, b->d_tab, b->d_work, b->d_ns, b->d_nc, b->d_xs, b->d_ls, b->d_xc, b->d_hyp, b->d_prior,
-                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags, b->d_mt, b->d_mti, b->d_overflow, b->d_work_ctr};
+                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags, b->d_mt, b->d_mti, b->d_overflow, b->d_work_ctr, b->d_xsorted, b->d_perm, b->d_iota, b->d_sort_tmp};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaStream_t st : b->pipe) if (st) cudaStreamDestroy(st);
     if (b->h_flags) cudaFreeHost(b->h_flags);
@@ -326,8 +334,52 @@ static int check_ready(bqb_batch *b, const char *who) {
     return 0;
 }
 
+static int score_device_impl(bqb_batch *b, const double *d_x_a, long long xa_stride, int na, double *d_esm, double *d_em,
+                             int *d_status, long long out_stride, int *d_flags, const int *d_perm, void *stream);
+
 int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int na, double *d_esm, double *d_em,
                      int *d_status, long long out_stride, int *d_flags, void *stream) {
+    return score_device_impl(b, d_x_a, xa_stride, na, d_esm, d_em, d_status, out_stride, d_flags, nullptr, stream);
+}
+
+// A query vector "looks sorted" if ~2000 evenly spaced samples are ascending at stride 1 and at the sampling stride.
+// Only performance depends on the answer (sorted or not, every point is scored and lands in its own slot).
+static bool looks_sorted(const double *x, int n) {
+    const int stride = n / 2048 > 1 ? n / 2048 : 1;
+    for (int i = 0; i + stride < n; i += stride)
+        if (!(x[i] <= x[i + 1]) || !(x[i] <= x[i + stride])) return false;
+    return true;
+}
+
+// Sorts the n points at d_x on stream s: b->d_xsorted ascending, b->d_perm their original positions.
+static int sort_query(bqb_batch *b, const double *d_x, int n, cudaStream_t s) {
+    if ((size_t)n > b->cap_sort) {
+        if (b->d_xsorted) cudaFree(b->d_xsorted);
+        if (b->d_perm) cudaFree(b->d_perm);
+        if (b->d_iota) cudaFree(b->d_iota);
+        b->d_xsorted = nullptr; b->d_perm = b->d_iota = nullptr; b->cap_sort = 0;
+        CU(cudaMalloc(&b->d_xsorted, sizeof(double) * n));
+        CU(cudaMalloc(&b->d_perm, sizeof(int) * n));
+        CU(cudaMalloc(&b->d_iota, sizeof(int) * n));
+        b->cap_sort = n;
+    }
+    size_t need = 0;
+    CU(sort_points(d_x, n, b->d_xsorted, b->d_iota, b->d_perm, nullptr, &need, s));
+    if (need > b->cap_sort_tmp) {
+        if (b->d_sort_tmp) cudaFree(b->d_sort_tmp);
+        b->d_sort_tmp = nullptr; b->cap_sort_tmp = 0;
+        CU(cudaMalloc(&b->d_sort_tmp, need));
+        b->cap_sort_tmp = need;
+    }
+    need = b->cap_sort_tmp;
+    CU(sort_points(d_x, n, b->d_xsorted, b->d_iota, b->d_perm, b->d_sort_tmp, &need, s));
+    b->launches += 2;
+    return 0;
+}
+constexpr int PRESORT_MIN = 8192;     // below this the penalty of unsorted points is not worth a sort
+
+static int score_device_impl(bqb_batch *b, const double *d_x_a, long long xa_stride, int na, double *d_esm, double *d_em,
+                             int *d_status, long long out_stride, int *d_flags, const int *d_perm, void *stream) {
     int rc = check_ready(b, "bqb_score_device");
     if (rc) return rc;
     if (!d_x_a || !d_esm || na < 0 || out_stride < na) return fail(BQB_EINVAL, "bqb_score_device: bad arguments");
@@ -337,7 +389,7 @@ int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int
     a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
     a.models = b->d_models; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = xa_stride; a.na = na;
     a.esm = d_esm; a.em = d_em; a.status = d_status; a.out_stride = out_stride; a.exp_tab = b->d_tab;
-    a.flags = d_flags; a.ndb_max = b->ndb_max;
+    a.flags = d_flags; a.ndb_max = b->ndb_max; a.perm = d_perm;
     if (d_flags) CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * b->n_inst, (cudaStream_t)stream));
     // gridDim.y is limited to 65535
     for (int i0 = 0; i0 < b->n_inst; i0 += 32768) {
@@ -400,8 +452,15 @@ int bqb_score_host(bqb_batch *b, const double *x_a, long long xa_stride, int na,
     if (rc) return rc;
     cudaStream_t s = 0;
     CU(cudaMemcpyAsync(b->d_xa, x_a, sizeof(double) * n_xa, cudaMemcpyHostToDevice, s));
-    rc = bqb_score_device(b, b->d_xa, xa_stride, na, b->d_esm, em ? b->d_em : nullptr, status ? b->d_st : nullptr, na,
-                          nullptr, s);
+    const double *d_x = b->d_xa;
+    const int *d_perm = nullptr;
+    if (xa_stride == 0 && na >= PRESORT_MIN && (b->presort == 2 || (b->presort == 1 && !looks_sorted(x_a, na)))) {
+        rc = sort_query(b, b->d_xa, na, s);          // points in arbitrary order defeat band skipping: score them sorted
+        if (rc) return rc;
+        d_x = b->d_xsorted; d_perm = b->d_perm;
+    }
+    rc = score_device_impl(b, d_x, xa_stride, na, b->d_esm, em ? b->d_em : nullptr, status ? b->d_st : nullptr, na, nullptr,
+                           d_perm, s);
     if (rc) return rc;
     CU(cudaMemcpyAsync(esm, b->d_esm, sizeof(double) * B * na, cudaMemcpyDeviceToHost, s));
     if (em) CU(cudaMemcpyAsync(em, b->d_em, sizeof(double) * B * na, cudaMemcpyDeviceToHost, s));
@@ -448,9 +507,10 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
     if (na == 0) { if (flags_out) *flags_out = 0; return 0; }
     CU(cudaSetDevice(b->device));
     static const int zero_copy = getenv("BQB_ZERO_COPY") ? atoi(getenv("BQB_ZERO_COPY")) : 1;
+    const bool presort = na >= PRESORT_MIN && (b->presort == 2 || (b->presort == 1 && !looks_sorted(x_a, na)));
     void *dx = nullptr, *dout = nullptr;
-    const bool in_mapped = zero_copy && mapped_host(x_a, &dx);
-    const bool out_mapped = zero_copy && mapped_host(out, &dout);
+    const bool in_mapped = !presort && zero_copy && mapped_host(x_a, &dx);      // a vector to be sorted is staged on the device
+    const bool out_mapped = !presort && zero_copy && mapped_host(out, &dout);
     if (!in_mapped || !out_mapped) {
         rc = grow(b, (size_t)na, (size_t)b->n_inst * na);
         if (rc) return rc;
@@ -463,7 +523,7 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
     // Buffers that are not page-locked go through device staging in chunks that alternate between two streams, so
     // that the H2D copy of one chunk, the kernels of another and the D2H copy of a third overlap.
     static const int min_chunk = getenv("BQB_PIPE_CHUNK") ? atoi(getenv("BQB_PIPE_CHUNK")) : (1 << 18);
-    int nchunk = (in_mapped && out_mapped) ? 1 : na / min_chunk;
+    int nchunk = ((in_mapped && out_mapped) || presort) ? 1 : na / min_chunk;
     if (nchunk < 1) nchunk = 1;
     if (nchunk > 8) nchunk = 8;
     int per = ((na + nchunk - 1) / nchunk + 255) & ~255;
@@ -486,6 +546,11 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
         } else {
             CU(cudaMemcpyAsync(b->d_xa + lo, x_a + lo, sizeof(double) * n, cudaMemcpyHostToDevice, s));
             a.x_a = b->d_xa + lo;
+            if (presort) {                               // single chunk: sort, score ascending, results back through perm
+                rc = sort_query(b, b->d_xa, na, s);
+                if (rc) return rc;
+                a.x_a = b->d_xsorted; a.perm = b->d_perm;
+            }
         }
         a.na = n; a.out_stride = n;
         if (out_mapped) {
@@ -611,6 +676,12 @@ int bqb_argmin_rows_device(bqb_batch *b, const double *d_v, long long stride, lo
 }
 
 unsigned long long bqb_launch_count(bqb_batch *b) { return b ? b->launches : 0; }
+
+int bqb_batch_set_presort(bqb_batch *b, int mode) {
+    if (!b || mode < 0 || mode > 2) return fail(BQB_EINVAL, "bqb_batch_set_presort: mode must be 0 (never), 1 (automatic) or 2 (always)");
+    b->presort = mode;
+    return 0;
+}
 
 int bqb_batch_set_cutoff(bqb_batch *b, double cut_arg) {
     if (!b || !(cut_arg > 0)) return fail(BQB_EINVAL, "bqb_batch_set_cutoff: cut_arg must be positive (INFINITY = dense)");

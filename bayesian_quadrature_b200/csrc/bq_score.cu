@@ -861,14 +861,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                     if (isinf(em)) st |= ST_EM_INF;                       // bq.py:524
                 }
             }
-            if (o_esm) o_esm[p] = esm;
+            const int po = a.perm ? a.perm[p] : p;          // the point's position in the caller's (unsorted) vector
+            if (o_esm) o_esm[po] = esm;
             if (EPI) {
                 const double evv = __dsub_rn(__dadd_rn(__dmul_rn(Zm, Zm), s_small[H_ZV]), esm);   // no FMA contraction: matches the host
-                a.ev[p] = evv;
-                if (evv < best_v) { best_v = evv; best_i = p; }   // p increases per lane: ties keep the first index
+                a.ev[po] = evv;
+                if (evv < best_v || (evv == best_v && po < best_i)) { best_v = evv; best_i = po; }   // ties keep the first index
             }
-            if (o_em) o_em[p] = em;
-            if (o_st) o_st[p] = st;
+            if (o_em) o_em[po] = em;
+            if (o_st) o_st[po] = st;
             if (st) {                                       // rare: shortcut / fallback / invalid points
                 if (a.flags) atomicOr(a.flags + inst, st);
                 if (a.cta_flags) atomicOr(&s_cta_st, st);

@@ -131,6 +131,41 @@ def test_band_skipping_equals_the_dense_algorithm(lib, ns, shuffle):
     b.close()
 
 
+@pytest.mark.parametrize("name,ns", [("c2", 64), ("c3", 256)])
+def test_presort_of_scattered_query_points(lib, name, ns):
+    """Query vectors in arbitrary order are sorted on the device by the host entry points, scored ascending and written
+    back through the permutation: bit-identical results to scoring the sorted vector, whatever the pre-sort mode, for
+    esm / em / status, for expected variance (pageable and page-locked arrays) and with invalid points in the vector."""
+    import torch
+    from bayesian_quadrature_b200 import synthetic
+    g = load_golden(name)
+    b, info = batch_of(lib, g)
+    rs = np.random.RandomState(3)
+    grid = synthetic.query_grid(ns, 50001)
+    grid[77] = g["x_s"][3]                             # a shortcut point
+    perm = rs.permutation(grid.size)
+    x = grid[perm]
+    esm_s, em_s, st_s = b.score_host(grid)             # sorted input: no sort
+    ref = (esm_s[0][perm], em_s[0][perm], st_s[0][perm])
+    for mode in (1, 0, 2):
+        b.set_presort(mode)
+        esm, em, st = b.score_host(x)
+        assert np.array_equal(esm[0], ref[0]) and np.array_equal(em[0], ref[1]) and np.array_equal(st[0], ref[2]), mode
+        ev, fl = b.expected_var_host(x)
+        ev_pin, fl_pin = b.expected_var_host(torch.from_numpy(x).pin_memory().numpy(), out=torch.empty(x.size, dtype=torch.float64).pin_memory().numpy())
+        want = info["Z_mean"][0] ** 2 + info["Z_var"][0] - ref[0]
+        assert np.array_equal(ev, want) and np.array_equal(ev_pin, want), mode
+        assert fl == fl_pin and (fl & lib.ST_SHORTCUT)
+    b.set_presort(1)
+    x_bad = x.copy()
+    x_bad[[5, 40000]] = [np.nan, np.inf]
+    esm, em, st = b.score_host(x_bad)
+    assert (st[0][[5, 40000]] == lib.ST_XA_BAD).all() and np.isnan(esm[0][[5, 40000]]).all()
+    ok = np.ones(x.size, bool); ok[[5, 40000]] = False
+    assert np.array_equal(esm[0][ok], ref[0][ok])
+    b.close()
+
+
 def test_hyper_set_batch_vs_reference(lib):
     """C4 semantics: one instance per hyper-parameter set, shared x_a, marginal loss and argmin."""
     import torch
