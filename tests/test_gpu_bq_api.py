@@ -186,6 +186,20 @@ def test_marginalize_shapes_and_choose_next():
     assert_close(loss_d.cpu().numpy(), np.mean(rows, axis=0), "marginal loss")
 
 
+def test_marginal_loss_of_shuffled_points_equals_the_sorted_one():
+    """choose_next / marginal_loss over query points in arbitrary order (random candidate sets): sorted on the device
+    for the scoring pass, loss returned in the caller's order -- bit-identical to the sorted call."""
+    from bayesian_quadrature_b200 import BQ, GaussianKernel, synthetic
+    bq = synthetic.make_bq(BQ, GaussianKernel, 64)
+    hyp = synthetic.hyper_sets(3)
+    grid = synthetic.query_grid(64, 20000)
+    perm = np.random.RandomState(5).permutation(grid.size)
+    loss_sorted, b1 = bq.marginal_loss(grid, hyp[:, :2], hyp[:, 2:], ["h", "w"])
+    loss_shuf, b2 = bq.marginal_loss(grid[perm], hyp[:, :2], hyp[:, 2:], ["h", "w"])
+    assert np.array_equal(loss_shuf.cpu().numpy(), loss_sorted.cpu().numpy()[perm])
+    b1.close(); b2.close()
+
+
 def test_batch_of_problems_rounds_match_the_oracle(oracle):
     """C5 semantics: independent problems advanced in lock-step; after every round each problem's scores and
     chosen point equal the oracle's for that problem's current observations and candidates."""
