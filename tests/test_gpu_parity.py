@@ -281,6 +281,46 @@ def test_setup_failures_are_reported(lib):
         lib.Batch(1, 10 ** 4)
 
 
+def test_capi_misuse_is_reported_not_ignored(lib):
+    """Argument / state errors come back as the reference's exception types (ValueError / NotImplementedError /
+    RuntimeError), never as silent no-ops."""
+    import torch
+    g = load_golden("fixture")
+    b = lib.Batch(2, 9)
+    with pytest.raises(lib.BQB200Error):                       # nothing set up yet (BQB_ESTATE)
+        b.score_host(np.zeros(3))
+    with pytest.raises(lib.BQB200Error):
+        b.draw_candidates(4)
+    with pytest.raises(NotImplementedError):                   # more than 16 candidates
+        b.setup([9, 9], [17, 2], np.tile(g["x_s"], (2, 1)), np.tile(g["l_s"], (2, 1)), np.zeros((2, 16)),
+                np.tile([15, 2.0, 0, 0.2, 1.3, 0], (2, 1)), np.tile([0.0, 10.0, 0.5], (2, 1)))
+    hyp, prior = np.tile([15, 2.0, 0, 0.2, 1.3, 0], (2, 1)), np.tile([0.0, 10.0, 0.5], (2, 1))
+    b.stage([9, 9], np.tile(g["x_s"], (2, 1)), np.tile(g["l_s"], (2, 1)), hyp, prior)
+    with pytest.raises(lib.BQB200Error):                       # generators not seeded
+        b.draw_candidates(4)
+    with pytest.raises(ValueError):
+        b.seed_candidates([1, 2, 3])
+    b.seed_candidates([1, 2])
+    with pytest.raises(NotImplementedError):
+        b.draw_candidates(17)
+    b.draw_candidates(10)
+    info = b.setup_device()
+    assert (info["status"] == 0).all()
+    with pytest.raises(ValueError):
+        b.set_cutoff(-1.0)
+    with pytest.raises(ValueError):
+        b.set_presort(3)
+    # appending beyond the batch's observation capacity (16 for ns <= 16) is refused, not dropped
+    far = torch.tensor([100.0, 200.0], dtype=torch.float64, device="cuda")
+    one = torch.ones(2, dtype=torch.float64, device="cuda")
+    for k in range(b.capacity - 9):
+        b.add_observations(far + 10.0 * k, one)
+    with pytest.raises(NotImplementedError):
+        b.add_observations(far + 1e4, one)
+    assert (b.get_staged()["ns"] == b.capacity).all()
+    b.close()
+
+
 def test_full_size_properties_c2(lib, oracle):
     """BASELINE configs[1] at full size (ns=64, 10^6 points): determinism, tiling independence,
     non-negativity, device argmin == host argmin, and a 4000-point subsample against the oracle."""
