@@ -86,6 +86,7 @@ struct bqb_batch {
     std::vector<double> h_hdr;
     bool ready = false;
     int ndb_max = 1;
+    int nb_max = 0, nrow_max = 0;      // largest ceil(ns / 8) and nc + 2 over the instances (sizes the kernels' shared memory)
     unsigned long long launches = 0;
 };
 
@@ -180,8 +181,13 @@ static int run_setup(bqb_batch *b, int check_max, cudaStream_t s) {
     CU(cudaMemcpyAsync(b->h_ns.data(), b->d_ns, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(b->h_nc.data(), b->d_nc, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    b->ndb_max = 1;
-    for (int i = 0; i < B; ++i) { const int d = (b->h_nc[i] + 2 + 7) / 8; if (d > b->ndb_max) b->ndb_max = d; }
+    b->ndb_max = 1; b->nb_max = 1; b->nrow_max = 2;
+    for (int i = 0; i < B; ++i) {
+        const int d = (b->h_nc[i] + 2 + 7) / 8, nbk = (b->h_ns[i] + 7) / 8, nr = b->h_nc[i] + 2;
+        if (d > b->ndb_max) b->ndb_max = d;
+        if (nbk > b->nb_max) b->nb_max = nbk;
+        if (nr > b->nrow_max) b->nrow_max = nr;
+    }
     b->ready = true;
     return 0;
 }
@@ -386,7 +392,7 @@ static int score_device_impl(bqb_batch *b, const double *d_x_a, long long xa_str
     if (na == 0) return 0;
     CU(cudaSetDevice(b->device));
     ScoreArgs a;
-    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
+    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr; a.nb_max = b->nb_max; a.nrow_max = b->nrow_max;
     a.models = b->d_models; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = xa_stride; a.na = na;
     a.esm = d_esm; a.em = d_em; a.status = d_status; a.out_stride = out_stride; a.exp_tab = b->d_tab;
     a.flags = d_flags; a.ndb_max = b->ndb_max; a.perm = d_perm;
@@ -409,7 +415,7 @@ int bqb_predict_device(bqb_batch *b, const double *d_x, long long x_stride, int 
     if (na == 0) return 0;
     CU(cudaSetDevice(b->device));
     ScoreArgs a;
-    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
+    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr; a.nb_max = b->nb_max; a.nrow_max = b->nrow_max;
     a.models = b->d_models; a.lay = b->lay; a.x_a = d_x; a.xa_stride = x_stride; a.na = na;
     a.esm = d_l_mean; a.em = d_v_log_l; a.status = nullptr; a.out_stride = out_stride; a.exp_tab = b->d_tab;
     a.flags = nullptr; a.ndb_max = b->ndb_max; a.predict = 1;
@@ -533,7 +539,7 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
     if (nchunk > 1) CU(cudaStreamSynchronize(b->pipe[0]));
     int zc_grid = 0;
     ScoreArgs a;
-    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
+    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr; a.nb_max = b->nb_max; a.nrow_max = b->nrow_max;
     a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.xa_stride = 0;
     a.em = nullptr; a.status = nullptr; a.exp_tab = b->d_tab; a.flags = zc ? nullptr : b->d_flags; a.inst0 = 0; a.ndb_max = b->ndb_max;
     a.cta_flags = zc ? b->h_cta_flags : nullptr;
@@ -631,7 +637,7 @@ int bqb_choose_step_device(bqb_batch *b, int inst, const double *d_x_a, int na, 
     CU(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
     ScoreArgs a;
-    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
+    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr; a.nb_max = b->nb_max; a.nrow_max = b->nrow_max;
     a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = 0; a.na = na;
     a.esm = d_esm; a.em = nullptr; a.status = nullptr; a.out_stride = na; a.exp_tab = b->d_tab; a.flags = nullptr;
     a.inst0 = 0; a.ndb_max = b->ndb_max;
@@ -654,7 +660,7 @@ int bqb_choose_step_exchange(bqb_batch *b, int inst, const double *d_x_a, int na
     CU(cudaSetDevice(b->device));
     cudaStream_t s = (cudaStream_t)stream;
     ScoreArgs a;
-    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr;
+    a.cut_arg = b->cut_arg; a.work = b->d_work_ctr; a.nb_max = b->nb_max; a.nrow_max = b->nrow_max;
     a.models = b->d_models + (size_t)inst * b->lay.total; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = 0; a.na = na;
     a.esm = d_esm; a.em = nullptr; a.status = nullptr; a.out_stride = na; a.exp_tab = b->d_tab; a.flags = nullptr;
     a.inst0 = 0; a.ndb_max = b->ndb_max;

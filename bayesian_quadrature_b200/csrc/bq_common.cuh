@@ -98,6 +98,8 @@ struct ScoreArgs {
     double *part_val = nullptr;         // [gridDim.x] per-CTA minimum of ev ...
     long long *part_idx = nullptr;      // ... and the first index attaining it (np.argmin semantics); may be null
     int chunk_frags = 0;                // streamed kernels: fragments per operand chunk (set by launch_score)
+    int nb_max = 0, nrow_max = 0;       // largest row-block count / nc + 2 over the batch's instances (0: unknown -> class maximum)
+    int nb_res = 0, nrow_res = 0;       // what the launch sizes its shared memory for (set by launch_score from the two above)
     const int *perm = nullptr;          // x_a is sorted: perm[p] = position of point p in the caller's vector (outputs go there)
     int predict = 0;                    // 1: prediction mode (esm <- gp_l.mean(x), em <- diag gp_log_l.cov(x))
     double cut_arg = 72.0;              // relevance cut-off of a cross-kernel exponent below its point's largest (+inf: dense)

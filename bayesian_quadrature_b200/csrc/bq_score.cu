@@ -30,6 +30,8 @@
 //
 // Grid: persistent CTAs (a multiple of the SM count); super-tiles are dealt round-robin with a
 // unit-granular remainder; gridDim.y = model instances (hyper-parameter sets or independent problems).
+#include <cstdlib>
+
 #include "bq_common.cuh"
 
 namespace bqb {
@@ -83,17 +85,17 @@ __device__ __forceinline__ void fetch_points(double *row, const double *__restri
 template <int KS, int NT, int WARPS, bool STREAM, int TABN>
 struct ScoreSmem {
     static constexpr int NBC = KS / 2;
-    static constexpr int TRI = NBC * (NBC + 1) * 32;       // doubles per triangular operand
-    static constexpr int DENSE = 3 * KS * 32;
     // resident: both triangles + the dense rows; streamed: two chunk buffers + the dense rows actually used
-    static __host__ __device__ constexpr int operands(int ndb_max, int chunk_frags) {
-        return STREAM ? 2 * chunk_frags * 32 + ndb_max * KS * 32 : 2 * TRI + DENSE;
+    // nb_res: row blocks actually needed by the launch's instances (<= KS / 2): the resident operands are sized at run time
+    static __host__ __device__ constexpr int operands(int ndb_max, int chunk_frags, int nb_res) {
+        return STREAM ? 2 * chunk_frags * 32 + ndb_max * KS * 32 : 2 * tri_frags(nb_res) * 32 + ndb_max * 2 * nb_res * 32;
     }
     // scratch per warp: padded rows 0 qs, 1 qt, 2 tm, 3 isclose, 4.. the dense rows; then two unpadded 32-point rows
     // holding the query points of this / the next super-tile (double buffer filled by cp.async)
-    static __host__ __device__ constexpr int scr(int ndb_max) { return (SCR_DENSE + 8 * ndb_max) * SCR_STRIDE + 64; }
-    static __host__ __device__ constexpr int doubles(int n_small, int ndb_max, int chunk_frags) {
-        return n_small + operands(ndb_max, chunk_frags) + WARPS * scr(ndb_max);     // dynamic part; the exp table is static
+    // nrow: dense rows kept per warp (largest nc + 2 of the launch's instances)
+    static __host__ __device__ constexpr int scr(int nrow) { return (SCR_DENSE + nrow) * SCR_STRIDE + 64; }
+    static __host__ __device__ constexpr int doubles(int n_small, int ndb_max, int chunk_frags, int nb_res, int nrow) {
+        return n_small + operands(ndb_max, chunk_frags, nb_res) + WARPS * scr(nrow);     // dynamic part; the exp table is static
     }
 };
 
@@ -527,9 +529,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     double *s_small = smem;
     double *s_ops = s_small + lay.n_small;                  // resident operands, or the two chunk buffers + dense rows
     double *s_af_l = s_ops;
-    double *s_af_d = STREAM ? s_ops + 2 * a.chunk_frags * 32 : s_af_l + SM::TRI;
-    double *s_af_t = s_af_d + SM::DENSE;                    // (resident only)
-    double *s_scr = s_ops + SM::operands(a.ndb_max, a.chunk_frags);
+    // Shared memory is sized for what the launch's instances need (row blocks, dense rows) in the large classes; the
+    // ns <= 64 kernels sit at their register limit and keep the class maxima as compile-time constants.
+    constexpr bool RT_SIZES = KS > 16;
+    const int nb_res = RT_SIZES ? a.nb_res : KS / 2, nrow_res = RT_SIZES ? a.nrow_res : 8 * a.ndb_max;
+    double *s_af_d = STREAM ? s_ops + 2 * a.chunk_frags * 32 : s_af_l + tri_frags(nb_res) * 32;
+    double *s_af_t = s_af_d + a.ndb_max * 2 * nb_res * 32;            // (resident only)
+    double *s_scr = s_ops + SM::operands(a.ndb_max, a.chunk_frags, nb_res);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int inst = a.inst0 + blockIdx.y;
@@ -570,7 +576,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     const double cut_l = a.cut_arg / fabs(nhl), cut_tl = a.cut_arg / fabs(s_small[H_NHTL]);
     unsigned long long n_kstep = 0;                         // (row block, k-step) products executed by this warp (a.work)
     const int tol2_hi = __double2hiint(s_small[H_TOL2MAX]) + 1;
-    double *scr = s_scr + warp * SM::scr(a.ndb_max);        // rows: 0 qs, 1 qt, 2 tm, 3 isclose, 4.. dense rows, then x_a
+    double *scr = s_scr + warp * SM::scr(nrow_res);        // rows: 0 qs, 1 qt, 2 tm, 3 isclose, 4.. dense rows, then x_a
 
     const double *xa = a.x_a + (size_t)inst * a.xa_stride;
     double *o_esm = a.esm ? a.esm + (size_t)inst * a.out_stride : nullptr;   // optional when the fused epilogue writes ev
@@ -598,7 +604,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     long long best_i = 0x7fffffffffffffffLL;
 
     int xb = 0;                                             // xrows + 32 xb holds this super-tile's points
-    double *xrows = scr + (SCR_DENSE + 8 * a.ndb_max) * SCR_STRIDE;   // two 32-point rows
+    double *xrows = scr + (SCR_DENSE + nrow_res) * SCR_STRIDE;        // two 32-point rows
     if (n_it > 0) fetch_points(xrows, xa, (long long)tile_u(0) * UNIT + warp * (8 * NT * tile_n(0)), a.na, lane);
     async_commit();
 
@@ -715,10 +721,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                                         }
                                 }
                             }
+                            if (!RT_SIZES || db * 8 + pq < nrow_res) {      // only the nc + 2 rows that exist have a scratch row
 #pragma unroll
-                            for (int nt = 0; nt < NT; ++nt)
-                                *reinterpret_cast<double2 *>(scr + (SCR_DENSE + db * 8 + pq) * SCR_STRIDE + col0 + nt * 8 + 2 * kq) =
-                                    make_double2(c0[nt] + e0[nt], c1[nt] + e1[nt]);
+                                for (int nt = 0; nt < NT; ++nt)
+                                    *reinterpret_cast<double2 *>(scr + (SCR_DENSE + db * 8 + pq) * SCR_STRIDE + col0 + nt * 8 + 2 * kq) =
+                                        make_double2(c0[nt] + e0[nt], c1[nt] + e1[nt]);
+                            }
                         }
                     }
                     park_q<NT>(q0, q1, scr, 0, col0, kq, pq);
@@ -906,10 +914,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 constexpr size_t SMEM_LIMIT = 227 * 1024;      // per-CTA opt-in maximum on sm_100 (static + dynamic)
 constexpr size_t SMEM_STATIC_MISC = 256;       // chunk table, mbarriers
 
+// Row blocks the resident operands are sized for / dense rows kept in scratch: what the launch's instances need (set by
+// the C-ABI layer from the batch's counts), or the class maximum when unknown
+template <int KS>
+static int res_rows(const ScoreArgs &a) { return (KS > 16 && a.nb_max > 0 && a.nb_max < KS / 2) ? a.nb_max : KS / 2; }
+template <int KS>
+static int dense_rows(const ScoreArgs &a) {
+    return (KS > 16 && a.nrow_max > 0 && a.nrow_max < 8 * a.ndb_max) ? a.nrow_max : 8 * a.ndb_max;
+}
+
 // Bytes of shared memory (static + dynamic) an instantiation needs for this launch
 template <int KS, int NT, int WARPS, bool STREAM, int TABN>
 static size_t smem_need(const ScoreArgs &a, int chunk_frags) {
-    return sizeof(double) * (TABN + ScoreSmem<KS, NT, WARPS, STREAM, TABN>::doubles(a.lay.n_small, a.ndb_max, chunk_frags)) +
+    return sizeof(double) * (TABN + ScoreSmem<KS, NT, WARPS, STREAM, TABN>::doubles(a.lay.n_small, a.ndb_max, chunk_frags,
+                                                                                    res_rows<KS>(a), dense_rows<KS>(a))) +
            SMEM_STATIC_MISC;
 }
 
@@ -917,13 +935,15 @@ template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN
 static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     a.chunk_frags = 0;
+    a.nb_res = res_rows<KS>(a);
+    a.nrow_res = dense_rows<KS>(a);
     if (STREAM) {       // the largest chunk buffers that fit
         int cf = CHUNK_FRAGS_MAX;
         while (cf >= 2 * KS && smem_need<KS, NT, WARPS, STREAM, TABN>(a, cf) > SMEM_LIMIT) cf -= 16;
         if (cf < 2 * KS) return cudaErrorInvalidConfiguration;      // a slab chunk holds at least two whole row blocks
         a.chunk_frags = cf;
     }
-    const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small, a.ndb_max, a.chunk_frags);
+    const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small, a.ndb_max, a.chunk_frags, a.nb_res, a.nrow_res);
     auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
@@ -980,7 +1000,12 @@ BQB_LAUNCH_DECL(128) {
     return launch_cfg<32, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
 }
 #elif BQB_SCORE_CLASS == 160
-BQB_LAUNCH_DECL(160) { return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x); }
+BQB_LAUNCH_DECL(160) {       // resident while the instances' operands fit (ns <= 136 ... 144 depending on the candidates), then streamed
+    static const bool force_stream = getenv("BQB_FORCE_STREAM") && atoi(getenv("BQB_FORCE_STREAM"));      // tuning aid
+    if (!force_stream && smem_need<40, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
+        return launch_cfg<40, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
+    return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
+}
 #elif BQB_SCORE_CLASS == 256
 BQB_LAUNCH_DECL(256) { return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x); }
 #else

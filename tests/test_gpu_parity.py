@@ -56,7 +56,8 @@ def test_capi_vs_reference_fixture(lib, name):
     b.close()
 
 
-@pytest.mark.parametrize("ns,seed", [(1, 0), (2, 1), (9, 2), (16, 3), (17, 4), (40, 5), (64, 6), (65, 7), (100, 8), (128, 9), (150, 10), (256, 11)])
+@pytest.mark.parametrize("ns,seed", [(1, 0), (2, 1), (9, 2), (16, 3), (17, 4), (40, 5), (64, 6), (65, 7), (100, 8), (128, 9), (136, 12), (144, 13),
+                                     (150, 10), (256, 11)])
 def test_capi_vs_oracle_random(lib, oracle, ns, seed):
     """Seeded random problems of every capacity class, random + edge query points."""
     rs = np.random.RandomState(seed)
