@@ -466,7 +466,7 @@ class BQ(object):
             x_d = torch.from_numpy(x_a).to(dev)
             # points in arbitrary order defeat the kernels' band skipping: score them in ascending order
             perm = None
-            if x_a.shape[0] >= 8192 and not _looks_sorted(x_a):
+            if x_a.shape[0] >= 8192 and self.ns > 64 and not _looks_sorted(x_a):      # (pays from the ns <= 128 class up)
                 x_d, perm = torch.sort(x_d)
             loss = torch.zeros(x_a.shape[0], dtype=torch.float64, device=dev)
             esm = torch.empty(n, x_a.shape[0], dtype=torch.float64, device=dev)

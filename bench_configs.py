@@ -144,6 +144,26 @@ def c5(n_prob=16384, ns=128, na=4096):
             "frac_fp64_peak": wf * n / (kbest * 1e-3) * 1e-12 / PEAK, "chosen_index_hist_head": np.bincount(idxs.cpu().numpy())[:4].tolist()}
 
 
+def scattered(ns=256, na=10 ** 6):
+    """Query points in arbitrary order through the host API (BQ.expected_Z_var): with and without the device pre-sort."""
+    from bayesian_quadrature_b200 import BQ, GaussianKernel
+    bq = synthetic.make_bq(BQ, GaussianKernel, ns)
+    grid = synthetic.query_grid(ns, na)
+    x = np.random.RandomState(0).permutation(grid)
+    out = {"config": "scattered query points, host API", "ns": ns, "na": na}
+    model = bq._device_model()
+    for label, mode, pts in (("sorted_ms", 1, grid), ("shuffled_presort_ms", 1, x), ("shuffled_no_presort_ms", 0, x)):
+        model.batch.set_presort(mode)
+        ts = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            bq.expected_Z_var(pts)
+            ts.append((time.perf_counter() - t0) * 1e3)
+        out[label] = min(ts)
+    model.batch.set_presort(1)
+    return out
+
+
 def c5_rounds(n_prob=16384, ns=128, na=4096, rounds=20, device_resident=True):
     """C5 as BASELINE.json states it: 16384 independent problems, 128 observations each, 20 rounds of
     score -> deterministic argmin -> add_observation -> re-init, all problems on this GPU.  device_resident=True keeps
@@ -200,6 +220,7 @@ def c5_rounds(n_prob=16384, ns=128, na=4096, rounds=20, device_resident=True):
 if __name__ == "__main__":
     which = [a.lower() for a in sys.argv[1:]] or ["c1", "c2", "c3", "c4", "c5", "c5r"]
     runs = {"c1": lambda: single("C1", 8, 200), "c2": lambda: single("C2", 64, 10 ** 6), "c3": lambda: single("C3", 256, 10 ** 7),
-            "c4": c4, "c5": c5, "c5r": c5_rounds, "c5rh": lambda: c5_rounds(device_resident=False)}
+            "c4": c4, "c5": c5, "c5r": c5_rounds, "c5rh": lambda: c5_rounds(device_resident=False),
+            "scat": scattered, "scat64": lambda: scattered(64)}
     for k in which:
         print(json.dumps(runs[k]()), flush=True)

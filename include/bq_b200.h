@@ -202,7 +202,7 @@ int bqb_batch_set_cutoff(bqb_batch *b, double cut_arg);
  * domain).  The HOST entry points (bqb_score_host with a shared x_a, bqb_expected_var_host) therefore sort vectors of
  * >= 8192 points that do not look sorted (a sampled test on the host) on the device (CUB radix sort, 0.2 ms per 10^6
  * points), score them in ascending order and write every result to its original position.  mode: 0 never, 1 automatic
- * (default), 2 always.  The DEVICE entry points never sort: pass sorted vectors for full speed. */
+ * (default: batches of capacity >= 128 observations, where the sort pays), 2 always.  The DEVICE entry points never sort: pass sorted vectors for full speed. */
 int bqb_batch_set_presort(bqb_batch *b, int mode);
 /* Executed-work counter of the scoring kernel: returns in *dmma_out (may be NULL) the number of DMMA.8x8x4
  * instructions (512 flop each) executed by the launches since the last call, then clears it; enable = 1 keeps

@@ -190,9 +190,9 @@ def test_marginal_loss_of_shuffled_points_equals_the_sorted_one():
     """choose_next / marginal_loss over query points in arbitrary order (random candidate sets): sorted on the device
     for the scoring pass, loss returned in the caller's order -- bit-identical to the sorted call."""
     from bayesian_quadrature_b200 import BQ, GaussianKernel, synthetic
-    bq = synthetic.make_bq(BQ, GaussianKernel, 64)
+    bq = synthetic.make_bq(BQ, GaussianKernel, 100)
     hyp = synthetic.hyper_sets(3)
-    grid = synthetic.query_grid(64, 20000)
+    grid = synthetic.query_grid(100, 20000)
     perm = np.random.RandomState(5).permutation(grid.size)
     loss_sorted, b1 = bq.marginal_loss(grid, hyp[:, :2], hyp[:, 2:], ["h", "w"])
     loss_shuf, b2 = bq.marginal_loss(grid[perm], hyp[:, :2], hyp[:, 2:], ["h", "w"])

@@ -128,3 +128,17 @@ def test_batched_candidate_filter_equals_the_scalar_one():
     filter_candidates_batch(xc, x_s, ns, 0.5)
     assert np.array_equal(np.isnan(xc), np.isnan(ref))
     assert np.array_equal(np.nan_to_num(xc), np.nan_to_num(ref))
+
+
+def test_looks_sorted_heuristic():
+    """The sampled sortedness test that decides whether query points are sorted on the device first: grids pass,
+    shuffled / reversed / NaN-carrying vectors do not (only speed depends on it, never results)."""
+    from bayesian_quadrature_b200.bq import _looks_sorted
+    rs = np.random.RandomState(0)
+    grid = np.linspace(-50, 50, 100001)
+    assert _looks_sorted(grid) and _looks_sorted(np.zeros(10000)) and _looks_sorted(np.array([1.0]))
+    assert not _looks_sorted(grid[::-1]) and not _looks_sorted(rs.permutation(grid))
+    bad = grid.copy()
+    bad[0] = np.nan
+    assert not _looks_sorted(bad)
+    assert not _looks_sorted(np.concatenate([grid[50000:], grid[:50000]]))      # two sorted halves in the wrong order
