@@ -103,6 +103,7 @@ struct ScoreArgs {
     const int *perm = nullptr;          // x_a is sorted: perm[p] = position of point p in the caller's vector (outputs go there)
     int predict = 0;                    // 1: prediction mode (esm <- gp_l.mean(x), em <- diag gp_log_l.cov(x))
     double cut_arg = 72.0;              // relevance cut-off of a cross-kernel exponent below its point's largest (+inf: dense)
+    int force_wide = 0;                 // band-relative kernels: every warp takes the wide (windowed) path (tests)
     unsigned long long *work = nullptr; // optional counter: DMMA instructions executed (all warps, atomically added)
 };
 

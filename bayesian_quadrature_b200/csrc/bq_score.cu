@@ -243,13 +243,11 @@ template <int N> __device__ __forceinline__ void async_wait() { asm volatile("cp
 // time (B fragments are registers) and leaves early at the row block's diagonal, so the row-block loop
 // around it can stay rolled: the instruction footprint is KS DMMAs, not KS^2/2.
 template <int KS, int NT>
-__device__ __forceinline__ void row_block(const double *af, int lim, const double (&bf)[KS][NT], double (&q0)[NT],
-                                          double (&q1)[NT], typename KMask<KS>::type mask) {
+__device__ __forceinline__ void row_block_acc(const double *af, int lim, const double (&bf)[KS][NT], double (&c0)[NT],
+                                              double (&c1)[NT], double (&e0)[NT], double (&e1)[NT],
+                                              typename KMask<KS>::type mask) {
     using mask_t = typename KMask<KS>::type;
     constexpr bool DUAL = (NT == 1);    // NT == 1: split even / odd k-steps into two chains to cover the DMMA latency
-    double c0[NT], c1[NT], e0[NT], e1[NT];
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
 #pragma unroll
     for (int ks = 0; ks < KS; ks += 2) {
         if (ks >= lim) break;
@@ -263,12 +261,26 @@ __device__ __forceinline__ void row_block(const double *af, int lim, const doubl
             }
         }
     }
+}
+template <int NT>
+__device__ __forceinline__ void row_block_finish(const double (&c0)[NT], const double (&c1)[NT], const double (&e0)[NT],
+                                                 const double (&e1)[NT], double (&q0)[NT], double (&q1)[NT]) {
+    constexpr bool DUAL = (NT == 1);
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
         const double r0 = DUAL ? c0[nt] + e0[nt] : c0[nt], r1 = DUAL ? c1[nt] + e1[nt] : c1[nt];
         q0[nt] = fma(r0, r0, q0[nt]);
         q1[nt] = fma(r1, r1, q1[nt]);
     }
+}
+template <int KS, int NT>
+__device__ __forceinline__ void row_block(const double *af, int lim, const double (&bf)[KS][NT], double (&q0)[NT],
+                                          double (&q1)[NT], typename KMask<KS>::type mask) {
+    double c0[NT], c1[NT], e0[NT], e1[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
+    row_block_acc<KS, NT>(af, lim, bf, c0, c1, e0, e1, mask);
+    row_block_finish<NT>(c0, c1, e0, e1, q0, q1);
 }
 
 // Two consecutive row blocks at once (rolled loops): the B fragment of a k-step feeds both, which doubles the number
@@ -364,22 +376,79 @@ __device__ __forceinline__ void mask_groups(mask_t mask, int &g0, int &kend) {
     kend = (64 - __clzll((long long)m) + 3) & ~3;
 }
 
-// Row blocks [rb0, rb1) of a triangular operand whose fragment (rb, ks) sits at base[(tri_frags(rb) + ks) * 32]
-template <int KS, int NT>
-__device__ __forceinline__ void row_blocks_rolled(const double *base, int rb0, int rb1, const double (&bf)[KS][NT],
-                                                  double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask) {
-    using mask_t = typename KMask<KS>::type;
+// ---- BAND-RELATIVE register tile (template parameter BK > 0 of the kernel).  The cross-kernel tile of a sub-tile holds
+// only KB = BK k-steps starting at the warp's band start k0 (a multiple of 8 k-steps, from the relevance mask of the
+// warp's 32 points): bf[j] is k-step k0 + j, the relevance mask is shifted down by k0 and the A-fragment pointers are
+// advanced by k0 fragments, so every loop below runs unchanged on relative indices.  The register tile no longer grows
+// with the capacity class (KB NT doubles instead of KS NT), which is what lets 16 warps share an SM.
+//
+// A warp whose band does not fit (scattered query points, length scales of many observation spacings, cut_arg = inf)
+// takes the WIDE path: the band is walked in windows of KB k-steps *inside* the row-block loop, the window's exponentials
+// being regenerated for every row block (accumulators must see the whole band before they are squared).  Slow -- the
+// exponentials are recomputed n / 8 times -- but it keeps every launch correct for any input without a second kernel.
+template <int NT>
+struct Wide {
+    bool on;                      // this warp's band exceeds the register tile in this pass
+    unsigned long long mask;      // absolute relevance mask of the warp
+    int kbeg, kend;               // band [kbeg, kend) in k-steps, kbeg a multiple of 8
+    double x[NT];
+    double C;
+    int dmax, kq;
+    const double *s_xs, *s_tab;
+};
+// window [kw, kw + KB) of the absolute mask, as a relative mask
+template <int KB>
+__device__ __forceinline__ typename KMask<KB>::type window_mask(unsigned long long mask, int kw) {
+    const unsigned long long m = mask >> kw;
+    return (typename KMask<KB>::type)(KB >= 64 ? m : (m & ((1ull << (KB & 63)) - 1)));
+}
+// one row block on the wide path; af[ks * 32] = fragment (rb, ks) with ABSOLUTE ks, lim = 2 rb + 2
+template <int KB, int NT, int TABN>
+__device__ __forceinline__ void wide_row_block(const double *af, int lim, const Wide<NT> &w, double (&bf)[KB][NT],
+                                               double (&q0)[NT], double (&q1)[NT]) {
+    double c0[NT], c1[NT], e0[NT], e1[NT], tmd[NT];
+    int cld[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
+    const int kstop = min(w.kend, lim);
+#pragma unroll 1
+    for (int kw = w.kbeg; kw < kstop; kw += KB) {
+        const typename KMask<KB>::type rm = window_mask<KB>(w.mask, kw);
+        if (!rm) continue;
+        gen_exps<KB, NT, TABN, false>(bf, w.x, w.C, w.dmax, rm, w.kq, w.s_xs + 4 * kw, nullptr, w.s_tab, tmd, 0, cld);
+        row_block_acc<KB, NT>(af + kw * 32, lim - kw, bf, c0, c1, e0, e1, rm);
+    }
+    row_block_finish<NT>(c0, c1, e0, e1, q0, q1);
+}
+
+// Row blocks [rb0, rb1) of a triangular operand whose fragment (rb, ks) sits at base[(tri_frags(rb) + ks) * 32].
+// KS is the size of the register tile bf, k0 its first k-step (0 for the absolute tile) and `mask` is relative to k0.
+template <int KS, int NT, int TABN, bool REL>
+__device__ __forceinline__ void row_blocks_rolled(const double *base, int rb0, int rb1, double (&bf)[KS][NT],
+                                                  double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask, int k0,
+                                                  const Wide<NT> &w) {
+    if constexpr (REL) {
+        if (w.on) {
+            const int kfirst = __ffsll((long long)w.mask) - 1;
+#pragma unroll 1
+            for (int rb = max(rb0, kfirst >> 1); rb < rb1; ++rb)
+                wide_row_block<KS, NT, TABN>(base + tri_frags(rb) * 32, 2 * rb + 2, w, bf, q0, q1);
+            return;
+        }
+    }
     if (!mask) return;
     int g0, kend;
     mask_groups(mask, g0, kend);
+    const int kfirst = k0 + __ffsll((long long)(unsigned long long)mask) - 1;      // first relevant k-step (absolute)
     int rb = rb0;
 #pragma unroll 1
     for (; rb + 1 < rb1; rb += 2) {
         // rows above the first relevant k-step see none of it (lower-triangular operand): 2 rb + 4 k-steps at most
-        if (2 * rb + 4 < (int)(8 * sizeof(mask_t)) && !(mask & (((mask_t)1 << (2 * rb + 4)) - 1))) continue;
-        row_block_pair<KS, NT>(base + tri_frags(rb) * 32, base + tri_frags(rb + 1) * 32, 2 * rb + 2, bf, q0, q1, mask, g0, kend);
+        if (2 * rb + 4 <= kfirst) continue;
+        row_block_pair<KS, NT>(base + (tri_frags(rb) + k0) * 32, base + (tri_frags(rb + 1) + k0) * 32, 2 * rb + 2 - k0, bf, q0, q1,
+                               mask, g0, kend);
     }
-    if (rb < rb1) row_block<KS, NT>(base + tri_frags(rb) * 32, 2 * rb + 2, bf, q0, q1, mask);
+    if (rb < rb1) row_block<KS, NT>(base + (tri_frags(rb) + k0) * 32, 2 * rb + 2 - k0, bf, q0, q1, mask);
 }
 
 // (row block, k-step) products a triangular pass executes for a relevance mask: sum over row blocks rb < nb of
@@ -396,13 +465,14 @@ __device__ __forceinline__ unsigned count_ksteps(typename KMask<KS>::type mask, 
 
 // Lower-triangular pass with shared-memory resident operands: q += (rows of (A . B))^2.
 // ROLLED = false unrolls the row-block loop as well (exact trip counts, no early-exit branches).
-template <int KS, int NT, bool ALIGN, bool ROLLED>
-__device__ __forceinline__ void tri_pass(const double *af_res, const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT],
-                                         int nb, int lane, typename KMask<KS>::type mask) {
+template <int KS, int NT, int TABN, bool ALIGN, bool ROLLED, bool REL>
+__device__ __forceinline__ void tri_pass(const double *af_res, double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT],
+                                         int nb, int lane, typename KMask<KS>::type mask, int k0, const Wide<NT> &w) {
     using mask_t = typename KMask<KS>::type;
+    static_assert(ROLLED || !REL, "the band-relative tile needs the rolled row-block loop");
     if (ALIGN) __syncthreads();                                 // all warps of the CTA enter the DMMA phase together
     if constexpr (ROLLED) {
-        row_blocks_rolled<KS, NT>(af_res + lane, 0, nb, bf, q0, q1, mask);
+        row_blocks_rolled<KS, NT, TABN, REL>(af_res + lane, 0, nb, bf, q0, q1, mask, k0, w);
     } else {
 #pragma unroll
         for (int rb = 0; rb < KS / 2; ++rb) {      // lim is a compile-time constant after unrolling: the early exit folds away
@@ -456,31 +526,41 @@ __device__ __forceinline__ void slab_issue(const double *__restrict__ op, const 
         bulk_g2s(st.buf + b * st.stride + lane * p.W * 32, op + (size_t)(tri_frags(rb0 + lane) + p.klo) * 32, (unsigned)(p.W * 256),
                  st.bar + b);
 }
-// row blocks [rb0, rb1) of a slab chunk that starts at row block rb0
-template <int KS, int NT>
-__device__ __forceinline__ void slab_rows(const double *buf, const SlabPlan &p, int rb0, int rb1, const double (&bf)[KS][NT],
-                                          double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask, int lane) {
-    using mask_t = typename KMask<KS>::type;
+// row blocks [rb0, rb1) of a slab chunk that starts at row block rb0 (register tile: see row_blocks_rolled)
+template <int KS, int NT, int TABN, bool REL>
+__device__ __forceinline__ void slab_rows(const double *buf, const SlabPlan &p, int rb0, int rb1, double (&bf)[KS][NT],
+                                          double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask, int lane, int k0,
+                                          const Wide<NT> &w) {
+    if constexpr (REL) {
+        if (w.on) {
+            const int kfirst = __ffsll((long long)w.mask) - 1;
+#pragma unroll 1
+            for (int rb = max(rb0, kfirst >> 1); rb < rb1; ++rb)
+                wide_row_block<KS, NT, TABN>(buf + ((rb - rb0) * p.W - p.klo) * 32 + lane, 2 * rb + 2, w, bf, q0, q1);
+            return;
+        }
+    }
     if (!mask) return;
     int g0, kend;
     mask_groups(mask, g0, kend);
+    const int kfirst = k0 + __ffsll((long long)(unsigned long long)mask) - 1;
     int rb = rb0;
 #pragma unroll 1
     for (; rb + 1 < rb1; rb += 2) {
-        if (2 * rb + 4 < (int)(8 * sizeof(mask_t)) && !(mask & (((mask_t)1 << (2 * rb + 4)) - 1))) continue;
-        const double *afA = buf + ((rb - rb0) * p.W - p.klo) * 32 + lane;       // afA[ks * 32] = fragment (rb, ks)
-        row_block_pair<KS, NT>(afA, afA + p.W * 32, 2 * rb + 2, bf, q0, q1, mask, g0, kend);
+        if (2 * rb + 4 <= kfirst) continue;
+        const double *afA = buf + ((rb - rb0) * p.W - p.klo + k0) * 32 + lane;       // afA[j * 32] = fragment (rb, k0 + j)
+        row_block_pair<KS, NT>(afA, afA + p.W * 32, 2 * rb + 2 - k0, bf, q0, q1, mask, g0, kend);
     }
-    if (rb < rb1) row_block<KS, NT>(buf + ((rb - rb0) * p.W - p.klo) * 32 + lane, 2 * rb + 2, bf, q0, q1, mask);
+    if (rb < rb1) row_block<KS, NT>(buf + ((rb - rb0) * p.W - p.klo + k0) * 32 + lane, 2 * rb + 2 - k0, bf, q0, q1, mask);
 }
 // The DMMAs of one operand for one sub-tile.  `res`: the whole slab already sits in the (contiguous) buffers, fetched once
 // per super-tile on barrier 0 -- the first sub-tile waits for it.  Otherwise the slab is streamed for this sub-tile in
 // chunks: chunks 0 and 1 were issued by the caller, chunk c lives in buffer c & 1 and chunk c + 2 is issued once every
 // warp is done with chunk c.
-template <int KS, int NT>
+template <int KS, int NT, int TABN, bool REL>
 __device__ __forceinline__ void slab_pass(const double *__restrict__ op, const SlabPlan &p, bool res, bool first_sub, Stream &st,
-                                          const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT], int nb, int lane, int warp,
-                                          typename KMask<KS>::type mask) {
+                                          double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT], int nb, int lane, int warp,
+                                          typename KMask<KS>::type mask, int k0, const Wide<NT> &w) {
     const int nch = res ? (p.nchunk ? 1 : 0) : p.nchunk;
     const int R = res ? nb - p.rb_first : p.R;
 #pragma unroll 1
@@ -491,10 +571,34 @@ __device__ __forceinline__ void slab_pass(const double *__restrict__ op, const S
             st.phase ^= 1u << b;
         }
         const int rb0 = p.rb_first + c * R;
-        slab_rows<KS, NT>(st.buf + b * st.stride, p, rb0, min(nb, rb0 + R), bf, q0, q1, mask, lane);
+        slab_rows<KS, NT, TABN, REL>(st.buf + b * st.stride, p, rb0, min(nb, rb0 + R), bf, q0, q1, mask, lane, k0, w);
         if (!res) {
             __syncthreads();                                    // every warp is done with buffer b
             if (warp == 0 && c + 2 < nch) slab_issue(op, p, c + 2, nb, st, b, lane);
+        }
+    }
+}
+
+// Dense candidate / g rows of one dense row block: acc += A(db, k0 + j) . bf[j] over the relevant exp groups of the (relative)
+// mask.  af[j * 32] = fragment (db, k0 + j); nk = k-steps that exist from the tile start on (fragments past it are not read).
+template <int KB, int NT>
+__device__ __forceinline__ void dense_acc(const double *af, int nk, const double (&bf)[KB][NT], typename KMask<KB>::type mask,
+                                          double (&c0)[NT], double (&c1)[NT], double (&e0)[NT], double (&e1)[NT]) {
+    using mask_t = typename KMask<KB>::type;
+    constexpr int GK = (NT == 1) ? 8 : 4;          // the groups of gen_exps: all of a relevant group's B fragments exist
+#pragma unroll
+    for (int g = 0; g < KB / GK; ++g) {
+        if ((mask >> (GK * g)) & (((mask_t)1 << GK) - 1)) {     // warp-uniform: a real branch around GK DMMAs
+            double fa[GK];
+#pragma unroll
+            for (int j = 0; j < GK; ++j) fa[j] = (GK * g + j < nk) ? af[(GK * g + j) * 32] : 0.0;
+#pragma unroll
+            for (int j = 0; j < GK; j += 2)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    dmma(c0[nt], c1[nt], fa[j], bf[GK * g + j][nt]);
+                    dmma(e0[nt], e1[nt], fa[j + 1], bf[GK * g + j + 1][nt]);     // 2 chains: the dense rows are few
+                }
         }
     }
 }
@@ -516,9 +620,14 @@ __device__ __forceinline__ void park_q(double (&q0)[NT], double (&q1)[NT], doubl
 // MODE 0: esm / em / status.  MODE 1: additionally the fused expected-variance + argmin epilogue.  MODE 2: prediction --
 // the same passes, but the tail returns the posterior mean of gp_l (BQ.l_mean, bq.py:177-200) in `esm` and the
 // posterior variance of gp_log_l (the factor of BQ.l_var, bq.py:202-231) in `em`: no shortcut, no jitter pattern.
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, int MODE>
+// BK > 0: band-relative register tile of BK k-steps (see row_blocks_rolled); BK = 0: the tile covers all KS k-steps.
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, int BK, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a) {
     constexpr bool EPI = MODE == 1, PRED = MODE == 2;
+    constexpr bool REL = BK > 0;
+    constexpr int KB = REL ? BK : KS;                       // k-steps of the register tile
+    static_assert(!REL || (BK % 8 == 0 && BK <= KS), "band tile: whole exp groups, no larger than the class");
+    using rmask_t = typename KMask<KB>::type;
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     constexpr bool LOCKSTEP = STREAM || ALIGN;              // warps must keep reaching the CTA barriers
     constexpr int THREADS = WARPS * 32;
@@ -650,6 +759,24 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
             res_tl = (nb - plan_tl.rb_first) * plan_tl.W <= 2 * a.chunk_frags;
         }
 
+        // band-relative tile: where this warp's band starts in each kernel, and whether it fits the register tile
+        int k0_l = 0, k0_tl = 0;
+        Wide<NT> wd_l, wd_tl;
+        wd_l.on = wd_tl.on = false;
+        if constexpr (REL) {
+            auto band = [&](mask_t m, int &k0, Wide<NT> &w, double C, int dmax) {
+                w.mask = m; w.C = C; w.dmax = dmax; w.kq = lane & 3; w.s_xs = s_xs; w.s_tab = s_tab;
+                w.kbeg = w.kend = 0;
+                if (!m) return;
+                const int lo = __ffsll((long long)(unsigned long long)m) - 1, hi = 64 - __clzll((long long)(unsigned long long)m);
+                w.kbeg = lo & ~7; w.kend = hi;
+                w.on = (hi - w.kbeg > KB) || a.force_wide;
+                k0 = w.on ? 0 : w.kbeg;
+            };
+            band(wmask_l, k0_l, wd_l, Cl, dmax_l);
+            band(wmask_tl, k0_tl, wd_tl, Ctl, dmax_tl);
+        }
+
         constexpr int NPH = STREAM ? 2 : 1;              // STREAM: pass 0 = K_l, pass 1 = K_tl; otherwise both per sub-tile
 #pragma unroll
         for (int ph = 0; ph < NPH; ++ph) {
@@ -677,13 +804,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                     const double v = xrow[col0 + nt * 8 + pq];      // points past na were filled with 0
                     x[nt] = isfinite(v) ? v : 0.0;       // invalid x_a is reported by the tail (ST_XA_BAD)
                 }
-                double bf[KS][NT];
+                double bf[KB][NT];
                 double q0[NT], q1[NT], tm[NT];
                 int close[NT];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = tm[nt] = 0.0; close[nt] = 0; }
                 mask_t mask = wmask_l;
                 const mask_t mask_tl = wmask_tl;
+                if constexpr (REL) {
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) wd_l.x[nt] = wd_tl.x[nt] = x[nt];
+                }
                 if constexpr (STREAM) {
                     if (!res && plan.nchunk && warp == 0) {                 // chunked: first two chunks, under the exp phase
                         slab_issue(op, plan, 0, nb, strm, 0, lane);
@@ -694,9 +825,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                 if (do_l) {
                     // ---- K_l: cross-kernel fragments, triangular rows then the dense candidate / g rows
                     if (ALIGN) __syncthreads();          // all warps enter the exp phase together (DMMA / DFMA mixing costs pipe throughput)
-                    gen_exps<KS, NT, TABN, false>(bf, x, Cl, dmax_l, mask, kq, s_xs, s_atl, s_tab, tm, tol2_hi, close);
-                    if constexpr (STREAM) slab_pass<KS, NT>(op, plan, res, sub == 0, strm, bf, q0, q1, nb, lane, warp, mask);
-                    else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_l, bf, q0, q1, nb, lane, mask);
+                    // relative mask of the register tile (empty on the wide path, which generates its windows itself)
+                    const rmask_t rm_l = REL ? (wd_l.on ? (rmask_t)0 : (rmask_t)(mask >> k0_l)) : (rmask_t)mask;
+                    gen_exps<KB, NT, TABN, false>(bf, x, Cl, dmax_l, rm_l, kq, s_xs + 4 * k0_l, s_atl, s_tab, tm, tol2_hi, close);
+                    if constexpr (STREAM)
+                        slab_pass<KB, NT, TABN, REL>(op, plan, res, sub == 0, strm, bf, q0, q1, nb, lane, warp, rm_l, k0_l, wd_l);
+                    else tri_pass<KB, NT, TABN, ALIGN, ROLLED, REL>(s_af_l, bf, q0, q1, nb, lane, rm_l, k0_l, wd_l);
                     if (a.work) n_kstep += count_ksteps<KS>(mask, nb) + ndb * __popcll((unsigned long long)mask);
 #pragma unroll
                     for (int db = 0; db < 3; ++db) {
@@ -705,21 +839,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                             double c0[NT], c1[NT], e0[NT], e1[NT];
 #pragma unroll
                             for (int nt = 0; nt < NT; ++nt) { c0[nt] = c1[nt] = e0[nt] = e1[nt] = 0.0; }
-                            constexpr int GK = (NT == 1) ? 8 : 4;          // the groups of gen_exps: all of a relevant group's
-#pragma unroll                                                             // B fragments exist; mask bits past nks are clear
-                            for (int g = 0; g < KS / GK; ++g) {
-                                if ((mask >> (GK * g)) & (((mask_t)1 << GK) - 1)) {     // warp-uniform: a real branch around GK DMMAs
-                                    double fa[GK];
-#pragma unroll
-                                    for (int j = 0; j < GK; ++j) fa[j] = (GK * g + j < nks) ? af[(GK * g + j) * 32] : 0.0;
-#pragma unroll
-                                    for (int j = 0; j < GK; j += 2)
-#pragma unroll
-                                        for (int nt = 0; nt < NT; ++nt) {
-                                            dmma(c0[nt], c1[nt], fa[j], bf[GK * g + j][nt]);
-                                            dmma(e0[nt], e1[nt], fa[j + 1], bf[GK * g + j + 1][nt]);     // 2 chains: the dense rows are few
-                                        }
+                            if (REL && wd_l.on) {                          // wide band: window by window (exponentials regenerated)
+#pragma unroll 1
+                                for (int kw = wd_l.kbeg; kw < wd_l.kend; kw += KB) {
+                                    const rmask_t rw = window_mask<KB>(wd_l.mask, kw);
+                                    if (!rw) continue;
+                                    gen_exps<KB, NT, TABN, false>(bf, x, Cl, dmax_l, rw, kq, s_xs + 4 * kw, s_atl, s_tab, tm, tol2_hi, close);
+                                    dense_acc<KB, NT>(af + kw * 32, nks - kw, bf, rw, c0, c1, e0, e1);
                                 }
+                            } else {
+                                dense_acc<KB, NT>(af + k0_l * 32, nks - k0_l, bf, rm_l, c0, c1, e0, e1);
                             }
                             if (!RT_SIZES || db * 8 + pq < nrow_res) {      // only the nc + 2 rows that exist have a scratch row
 #pragma unroll
@@ -738,12 +867,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                     for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
                     if (ALIGN) __syncthreads();
                     mask = mask_tl;
-                    gen_exps<KS, NT, TABN, true>(bf, x, Ctl, dmax_tl, mask, kq, s_xs, s_atl, s_tab, tm, tol2_hi, close);
+                    const rmask_t rm_tl = REL ? (wd_tl.on ? (rmask_t)0 : (rmask_t)(mask >> k0_tl)) : (rmask_t)mask;
+                    if (REL && wd_tl.on) {                   // wide band: gp_log_l.mean and the isclose pre-filter, window by window
+#pragma unroll 1
+                        for (int kw = wd_tl.kbeg; kw < wd_tl.kend; kw += KB) {
+                            const rmask_t rw = window_mask<KB>(wd_tl.mask, kw);
+                            if (!rw) continue;
+                            int cw[NT];
+                            gen_exps<KB, NT, TABN, true>(bf, x, Ctl, dmax_tl, rw, kq, s_xs + 4 * kw, s_atl + 4 * kw, s_tab, tm, tol2_hi, cw);
+#pragma unroll
+                            for (int nt = 0; nt < NT; ++nt) close[nt] |= cw[nt];
+                        }
+                    } else {
+                        gen_exps<KB, NT, TABN, true>(bf, x, Ctl, dmax_tl, rm_tl, kq, s_xs + 4 * k0_tl, s_atl + 4 * k0_tl, s_tab, tm, tol2_hi,
+                                                     close);
+                    }
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
                         if (close[nt]) close[nt] = isclose_exact(x[nt], s_xs, s_tol, nsp, kq);
-                    if constexpr (STREAM) slab_pass<KS, NT>(op, plan, res, sub == 0, strm, bf, q0, q1, nb, lane, warp, mask);
-                    else tri_pass<KS, NT, ALIGN, ROLLED>(s_af_t, bf, q0, q1, nb, lane, mask);
+                    if constexpr (STREAM)
+                        slab_pass<KB, NT, TABN, REL>(op, plan, res, sub == 0, strm, bf, q0, q1, nb, lane, warp, rm_tl, k0_tl, wd_tl);
+                    else tri_pass<KB, NT, TABN, ALIGN, ROLLED, REL>(s_af_t, bf, q0, q1, nb, lane, rm_tl, k0_tl, wd_tl);
                     if (a.work) n_kstep += count_ksteps<KS>(mask, nb);
                     park_q<NT>(q0, q1, scr, 1, col0, kq, pq);
 #pragma unroll
@@ -911,6 +1055,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     }
 }
 
+#ifndef BQB_REL_DEFAULT
+#define BQB_REL_DEFAULT 0
+#endif
 constexpr size_t SMEM_LIMIT = 227 * 1024;      // per-CTA opt-in maximum on sm_100 (static + dynamic)
 constexpr size_t SMEM_STATIC_MISC = 256;       // chunk table, mbarriers
 
@@ -931,7 +1078,7 @@ static size_t smem_need(const ScoreArgs &a, int chunk_frags) {
            SMEM_STATIC_MISC;
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, int MODE>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, int BK, int MODE>
 static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     a.chunk_frags = 0;
@@ -944,7 +1091,7 @@ static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream
         a.chunk_frags = cf;
     }
     const size_t bytes = sizeof(double) * SM::doubles(a.lay.n_small, a.ndb_max, a.chunk_frags, a.nb_res, a.nrow_res);
-    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, MODE>;
+    auto kern = bq_score_kernel<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, BK, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     const int n_units = (a.na + 8 * NT * WARPS - 1) / (8 * NT * WARPS);
@@ -957,12 +1104,24 @@ static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, int BK = 0>
 static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     // the fused expected-variance / argmin epilogue is a separate instantiation so that plain scoring keeps its registers
-    if (a.predict) return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, 2>(a, n_inst, sm_count, stream, grid_x);
-    if (a.ev) return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, 1>(a, n_inst, sm_count, stream, grid_x);
-    return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, 0>(a, n_inst, sm_count, stream, grid_x);
+    if (a.predict) return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, BK, 2>(a, n_inst, sm_count, stream, grid_x);
+    if (a.ev) return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, BK, 1>(a, n_inst, sm_count, stream, grid_x);
+    return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, BK, 0>(a, n_inst, sm_count, stream, grid_x);
+}
+
+// Tuning switch of the large classes: BQB_REL = 0 absolute register tile (8 warps), 1 band-relative tile of 24 k-steps with
+// 16 warps per CTA, 2 the same with 12 warps.  BQB_FORCE_WIDE = 1 sends every warp down the wide path (tests).
+static int rel_variant() {
+    const char *e = getenv("BQB_REL");
+    return e ? atoi(e) : BQB_REL_DEFAULT;
+}
+static ScoreArgs with_env(ScoreArgs a) {
+    const char *e = getenv("BQB_FORCE_WIDE");
+    a.force_wide = (e && atoi(e)) ? 1 : 0;
+    return a;
 }
 
 // nsp_cap selects the instantiation: 16, 64, 128 (operands resident), 160 and 256 (operands streamed).  The tilings
@@ -995,6 +1154,17 @@ BQB_LAUNCH_DECL(16) { return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a
 BQB_LAUNCH_DECL(64) { return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x); }
 #elif BQB_SCORE_CLASS == 128
 BQB_LAUNCH_DECL(128) {
+    const int rv = rel_variant();
+    if (rv == 1) {
+        if (smem_need<32, 1, 16, false, 512>(a, 0) <= SMEM_LIMIT)
+            return launch_cfg<32, 1, 16, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+        return launch_cfg<32, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    }
+    if (rv == 2) {
+        if (smem_need<32, 1, 12, false, 512>(a, 0) <= SMEM_LIMIT)
+            return launch_cfg<32, 1, 12, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+        return launch_cfg<32, 1, 12, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    }
     if (smem_need<32, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
         return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
     return launch_cfg<32, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
@@ -1002,12 +1172,28 @@ BQB_LAUNCH_DECL(128) {
 #elif BQB_SCORE_CLASS == 160
 BQB_LAUNCH_DECL(160) {       // resident while the instances' operands fit (ns <= 136 ... 144 depending on the candidates), then streamed
     static const bool force_stream = getenv("BQB_FORCE_STREAM") && atoi(getenv("BQB_FORCE_STREAM"));      // tuning aid
+    const int rv = rel_variant();
+    if (rv == 1) {
+        if (!force_stream && smem_need<40, 1, 16, false, 512>(a, 0) <= SMEM_LIMIT)
+            return launch_cfg<40, 1, 16, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+        return launch_cfg<40, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    }
+    if (rv == 2) {
+        if (!force_stream && smem_need<40, 1, 12, false, 512>(a, 0) <= SMEM_LIMIT)
+            return launch_cfg<40, 1, 12, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+        return launch_cfg<40, 1, 12, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    }
     if (!force_stream && smem_need<40, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
         return launch_cfg<40, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
     return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
 }
 #elif BQB_SCORE_CLASS == 256
-BQB_LAUNCH_DECL(256) { return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x); }
+BQB_LAUNCH_DECL(256) {
+    const int rv = rel_variant();
+    if (rv == 1) return launch_cfg<64, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    if (rv == 2) return launch_cfg<64, 1, 12, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
+}
 #else
 #error "BQB_SCORE_CLASS must be 16, 64, 128, 160 or 256"
 #endif
