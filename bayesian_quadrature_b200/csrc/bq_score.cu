@@ -190,7 +190,7 @@ __device__ __forceinline__ void gen_masks(double xv, bool valid, double cut_l, d
 template <int KS, int NT, int TABN, bool TL>
 __device__ __forceinline__ void gen_exps(double (&bf)[KS][NT], const double (&x)[NT], double C, int d2max_hi,
                                          typename KMask<KS>::type mask, int kq, const double *s_xs, const double *s_atl,
-                                         const double *s_tab, double (&tm)[NT], int tol2_hi, int (&close)[NT]) {
+                                         const double *s_tab, double (&tm)[NT], int tol2_hi, int (&close)[NT], int nkv = KS) {
     using mask_t = typename KMask<KS>::type;
     // 8 independent exp chains per branch-free group: with one CTA of 8 warps per SM (two warps per scheduler) the
     // NT = 1 exp phase was latency bound at 4 (ncu: 47 % of its stalls on fixed-latency dependencies)
@@ -214,7 +214,9 @@ __device__ __forceinline__ void gen_exps(double (&bf)[KS][NT], const double (&x)
                         bf[ks][nt] = e;
                         if (TL) {
                             minhi[nt] = min(minhi[nt], __double2hiint(d2));
-                            tm[nt] = fma(s_atl[4 * ks + kq], e, tm[nt]);
+                            // nkv: k-steps of the tile that exist (a band-relative tile may reach past the class capacity:
+                            // such elements are generated from padding and never multiplied, but must not enter the mean)
+                            if (ks < nkv) tm[nt] = fma(s_atl[4 * ks + kq], e, tm[nt]);
                         }
                     }
                 }
@@ -376,6 +378,86 @@ __device__ __forceinline__ void mask_groups(mask_t mask, int &g0, int &kend) {
     kend = (64 - __clzll((long long)m) + 3) & ~3;
 }
 
+// The rectangular part of a band-relative pass: row-block pairs that lie wholly below the band see all of its NG groups of
+// four k-steps (bf[0 .. 4 NG)), so the loop needs no diagonal tests, no jump table and no per-pair address arithmetic: per
+// pair 8 NG fragment loads, 8 NG NT DMMAs in four independent chains per point tile (the first DMMA of a chain starts
+// from a zero accumulator), four adds and four FMAs.  ncu on the generic loop (ns = 256): 14.5 instructions per DMMA,
+// among them ~40 of address arithmetic and 17 accumulator clears per pair; this loop issues ~3.5 per DMMA.
+// pA: fragment (rb, k0) of the pair's first row block (lane included); the second row block starts sAB doubles later, the
+// next pair sNext doubles later, and both distances grow by dAB / dNext per pair (resident triangles: rows get longer;
+// slabs: constant row pitch).
+__device__ __forceinline__ void dmma_z(double &c0, double &c1, double a, double b) {      // D = A B (zero accumulator)
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+                 : "=d"(c0), "=d"(c1) : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+template <int KS, int NT, int NG>
+__device__ __forceinline__ void rect_pairs(const double *pA, int npair, int sAB, int sNext, int dAB, int dNext,
+                                           const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT]) {
+    static_assert(4 * NG <= KS, "groups of the register tile");
+#pragma unroll 1
+    for (int i = 0; i < npair; ++i) {
+        const double *pB = pA + sAB;
+        double a0[NT], a1[NT], b0[NT], b1[NT], c0[NT], c1[NT], d0[NT], d1[NT];   // (a, b): block A even / odd k; (c, d): block B
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            double fa[4], fb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { fa[j] = pA[(4 * g + j) * 32]; fb[j] = pB[(4 * g + j) * 32]; }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                if (g == 0) {
+                    dmma_z(a0[nt], a1[nt], fa[0], bf[0][nt]);
+                    dmma_z(c0[nt], c1[nt], fb[0], bf[0][nt]);
+                    dmma_z(b0[nt], b1[nt], fa[1], bf[1][nt]);
+                    dmma_z(d0[nt], d1[nt], fb[1], bf[1][nt]);
+                } else {
+                    dmma(a0[nt], a1[nt], fa[0], bf[4 * g][nt]);
+                    dmma(c0[nt], c1[nt], fb[0], bf[4 * g][nt]);
+                    dmma(b0[nt], b1[nt], fa[1], bf[4 * g + 1][nt]);
+                    dmma(d0[nt], d1[nt], fb[1], bf[4 * g + 1][nt]);
+                }
+                dmma(a0[nt], a1[nt], fa[2], bf[4 * g + 2][nt]);
+                dmma(c0[nt], c1[nt], fb[2], bf[4 * g + 2][nt]);
+                dmma(b0[nt], b1[nt], fa[3], bf[4 * g + 3][nt]);
+                dmma(d0[nt], d1[nt], fb[3], bf[4 * g + 3][nt]);
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const double rA0 = a0[nt] + b0[nt], rA1 = a1[nt] + b1[nt], rB0 = c0[nt] + d0[nt], rB1 = c1[nt] + d1[nt];
+            q0[nt] = fma(rA0, rA0, q0[nt]);
+            q1[nt] = fma(rA1, rA1, q1[nt]);
+            q0[nt] = fma(rB0, rB0, q0[nt]);
+            q1[nt] = fma(rB1, rB1, q1[nt]);
+        }
+        pA += sNext;
+        sAB += dAB;
+        sNext += dNext;
+    }
+}
+template <int KS, int NT>
+__device__ __forceinline__ void rect_dispatch(int ng, const double *pA, int npair, int sAB, int sNext, int dAB, int dNext,
+                                              const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT]) {
+    switch (ng) {
+#define BQB_RECT(N)                                                                                          \
+    case N:                                                                                                  \
+        if constexpr (4 * (N) <= KS) rect_pairs<KS, NT, (4 * (N) <= KS ? (N) : 1)>(pA, npair, sAB, sNext, dAB, dNext, bf, q0, q1); \
+        break;
+        BQB_RECT(1) BQB_RECT(2) BQB_RECT(3) BQB_RECT(4) BQB_RECT(5) BQB_RECT(6) BQB_RECT(7) BQB_RECT(8)
+#undef BQB_RECT
+        default: break;
+    }
+}
+// The band of a relative mask is "plain" when its groups of four k-steps are 0 .. ng-1 without holes: every bf of
+// those groups has been generated, so the rectangular loop may multiply them all.
+template <typename mask_t>
+__device__ __forceinline__ bool plain_band(mask_t mask, int g0, int kend) {
+    unsigned long long m = mask;
+    m |= m >> 1; m |= m >> 2; m &= 0x1111111111111111ull;            // bit 4 g: group g relevant
+    const unsigned long long want = (kend >= 64 ? ~0ull : ((1ull << kend) - 1)) & 0x1111111111111111ull;
+    return g0 == 0 && m == want;
+}
+
 // ---- BAND-RELATIVE register tile (template parameter BK > 0 of the kernel).  The cross-kernel tile of a sub-tile holds
 // only KB = BK k-steps starting at the warp's band start k0 (a multiple of 8 k-steps, from the relevance mask of the
 // warp's 32 points): bf[j] is k-step k0 + j, the relevance mask is shifted down by k0 and the A-fragment pointers are
@@ -441,12 +523,23 @@ __device__ __forceinline__ void row_blocks_rolled(const double *base, int rb0, i
     mask_groups(mask, g0, kend);
     const int kfirst = k0 + __ffsll((long long)(unsigned long long)mask) - 1;      // first relevant k-step (absolute)
     int rb = rb0;
+    // REL: pairs from rbf on lie below the band (2 rb + 2 - k0 >= kend) and take the rectangular loop
+    const bool rect = REL && plain_band(mask, g0, kend);
+    const int rbf = rect ? min(rb1, max(rb0, ((k0 + kend) >> 1) & ~1)) : rb1;
 #pragma unroll 1
-    for (; rb + 1 < rb1; rb += 2) {
+    for (; rb + 1 < rbf; rb += 2) {
         // rows above the first relevant k-step see none of it (lower-triangular operand): 2 rb + 4 k-steps at most
         if (2 * rb + 4 <= kfirst) continue;
         row_block_pair<KS, NT>(base + (tri_frags(rb) + k0) * 32, base + (tri_frags(rb + 1) + k0) * 32, 2 * rb + 2 - k0, bf, q0, q1,
                                mask, g0, kend);
+    }
+    if constexpr (REL) {
+        if (rect && rb + 1 < rb1) {
+            const int npair = (rb1 - rb) >> 1;
+            rect_dispatch<KS, NT>(kend >> 2, base + (tri_frags(rb) + k0) * 32, npair, (2 * rb + 2) * 32, (4 * rb + 6) * 32, 128, 256, bf,
+                                  q0, q1);
+            rb += 2 * npair;
+        }
     }
     if (rb < rb1) row_block<KS, NT>(base + (tri_frags(rb) + k0) * 32, 2 * rb + 2 - k0, bf, q0, q1, mask);
 }
@@ -545,11 +638,21 @@ __device__ __forceinline__ void slab_rows(const double *buf, const SlabPlan &p, 
     mask_groups(mask, g0, kend);
     const int kfirst = k0 + __ffsll((long long)(unsigned long long)mask) - 1;
     int rb = rb0;
+    const bool rect = REL && plain_band(mask, g0, kend);
+    const int rbf = rect ? min(rb1, max(rb0, ((k0 + kend) >> 1) & ~1)) : rb1;
 #pragma unroll 1
-    for (; rb + 1 < rb1; rb += 2) {
+    for (; rb + 1 < rbf; rb += 2) {
         if (2 * rb + 4 <= kfirst) continue;
         const double *afA = buf + ((rb - rb0) * p.W - p.klo + k0) * 32 + lane;       // afA[j * 32] = fragment (rb, k0 + j)
         row_block_pair<KS, NT>(afA, afA + p.W * 32, 2 * rb + 2 - k0, bf, q0, q1, mask, g0, kend);
+    }
+    if constexpr (REL) {
+        if (rect && rb + 1 < rb1) {
+            const int npair = (rb1 - rb) >> 1;
+            rect_dispatch<KS, NT>(kend >> 2, buf + ((rb - rb0) * p.W - p.klo + k0) * 32 + lane, npair, p.W * 32, 2 * p.W * 32, 0, 0, bf, q0,
+                                  q1);
+            rb += 2 * npair;
+        }
     }
     if (rb < rb1) row_block<KS, NT>(buf + ((rb - rb0) * p.W - p.klo + k0) * 32 + lane, 2 * rb + 2 - k0, bf, q0, q1, mask);
 }
@@ -769,9 +872,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                 w.kbeg = w.kend = 0;
                 if (!m) return;
                 const int lo = __ffsll((long long)(unsigned long long)m) - 1, hi = 64 - __clzll((long long)(unsigned long long)m);
-                w.kbeg = lo & ~7; w.kend = hi;
-                w.on = (hi - w.kbeg > KB) || a.force_wide;
-                k0 = w.on ? 0 : w.kbeg;
+                w.kbeg = lo & ~7; w.kend = hi;                    // wide path: windows from a whole exp group
+                w.on = (hi - (lo & ~3) > KB) || a.force_wide;
+                k0 = w.on ? 0 : (lo & ~3);                        // the band's first group of four k-steps is group 0 of the tile
             };
             band(wmask_l, k0_l, wd_l, Cl, dmax_l);
             band(wmask_tl, k0_tl, wd_tl, Ctl, dmax_tl);
@@ -874,13 +977,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                             const rmask_t rw = window_mask<KB>(wd_tl.mask, kw);
                             if (!rw) continue;
                             int cw[NT];
-                            gen_exps<KB, NT, TABN, true>(bf, x, Ctl, dmax_tl, rw, kq, s_xs + 4 * kw, s_atl + 4 * kw, s_tab, tm, tol2_hi, cw);
+                            gen_exps<KB, NT, TABN, true>(bf, x, Ctl, dmax_tl, rw, kq, s_xs + 4 * kw, s_atl + 4 * kw, s_tab, tm, tol2_hi, cw,
+                                                         KS - kw);
 #pragma unroll
                             for (int nt = 0; nt < NT; ++nt) close[nt] |= cw[nt];
                         }
                     } else {
                         gen_exps<KB, NT, TABN, true>(bf, x, Ctl, dmax_tl, rm_tl, kq, s_xs + 4 * k0_tl, s_atl + 4 * k0_tl, s_tab, tm, tol2_hi,
-                                                     close);
+                                                     close, KS - k0_tl);
                     }
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
