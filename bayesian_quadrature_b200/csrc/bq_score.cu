@@ -40,6 +40,9 @@ namespace bqb {
 // STREAM: the triangular operands are streamed through two chunk buffers of `chunk_frags` fragments (256 B each);
 // launch_score picks the largest size (<= CHUNK_FRAGS_MAX) that fits next to the resident pieces.
 constexpr int CHUNK_FRAGS_MAX = 256;
+#ifndef BQB_REL_GK
+#define BQB_REL_GK 4          // k-steps per branch-free exp group of the band-relative kernels
+#endif
 
 // ---- mbarrier + bulk-copy (TMA) primitives of the operand stream
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -187,14 +190,14 @@ __device__ __forceinline__ void gen_masks(double xv, bool valid, double cut_l, d
 // np.isclose(x_a, x_s, atol=1e-4) (bq.py:456): the high word of the point's smallest d^2 (its nearest observation is
 // always in a relevant k-step) against an upper bound of every tolerance^2 -- non-negative doubles order like their
 // bits; the exact test runs afterwards only for the rare points that pass (isclose_exact).
-template <int KS, int NT, int TABN, bool TL>
+template <int NT> __host__ __device__ constexpr int exp_group() { return NT == 1 ? 8 : 4; }
+template <int KS, int NT, int TABN, bool TL, int GK = exp_group<NT>()>
 __device__ __forceinline__ void gen_exps(double (&bf)[KS][NT], const double (&x)[NT], double C, int d2max_hi,
                                          typename KMask<KS>::type mask, int kq, const double *s_xs, const double *s_atl,
                                          const double *s_tab, double (&tm)[NT], int tol2_hi, int (&close)[NT], int nkv = KS) {
     using mask_t = typename KMask<KS>::type;
     // 8 independent exp chains per branch-free group: with one CTA of 8 warps per SM (two warps per scheduler) the
     // NT = 1 exp phase was latency bound at 4 (ncu: 47 % of its stalls on fixed-latency dependencies)
-    constexpr int GK = (NT == 1) ? 8 : 4;
     int minhi[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) minhi[nt] = 0x7fffffff;
@@ -337,7 +340,8 @@ __device__ __forceinline__ void pair_group(const double *afA, const double *afB,
 // [g0, kend): first relevant group of four k-steps and the end (a multiple of 4) of the last one, from the mask.  The
 // groups are entered through a jump table at g0 and left at kend or at the diagonal: with a band of 2-4 groups out of up
 // to 16, testing every group of every row-block pair cost more than the DMMAs (ncu, ns = 256).
-template <int KS, int NT>
+// PLAIN: the band is groups 0 .. kend / 4 - 1 without holes (plain_band): straight-line code from group 0, no jump table.
+template <int KS, int NT, bool PLAIN = false>
 __device__ __forceinline__ void row_block_pair(const double *afA, const double *afB, int limA, const double (&bf)[KS][NT],
                                                double (&q0)[NT], double (&q1)[NT], typename KMask<KS>::type mask, int g0, int kend) {
     using mask_t = typename KMask<KS>::type;
@@ -354,11 +358,21 @@ __device__ __forceinline__ void row_block_pair(const double *afA, const double *
                 pair_group<KS, NT, 4 * (G)>(afA, afB, limA, bf, a0, a1, b0, b1, c0, c1, d0, d1);                         \
         }                                                                                                                \
         [[fallthrough]];
-    switch (g0) {
-        BQB_GRP(0) BQB_GRP(1) BQB_GRP(2) BQB_GRP(3) BQB_GRP(4) BQB_GRP(5) BQB_GRP(6) BQB_GRP(7)
-        BQB_GRP(8) BQB_GRP(9) BQB_GRP(10) BQB_GRP(11) BQB_GRP(12) BQB_GRP(13) BQB_GRP(14) BQB_GRP(15)
-        default: break;
+#define BQB_GRP_PLAIN(G)                                                                                                 \
+    if constexpr (4 * (G) < KS) {                                                                                        \
+        if (4 * (G) < kstop) {                                                                                           \
+            pair_group<KS, NT, 4 * (G)>(afA, afB, limA, bf, a0, a1, b0, b1, c0, c1, d0, d1);
+    if constexpr (PLAIN) {      // nested: group G + 1 only if group G ran
+        BQB_GRP_PLAIN(0) BQB_GRP_PLAIN(1) BQB_GRP_PLAIN(2) BQB_GRP_PLAIN(3) BQB_GRP_PLAIN(4) BQB_GRP_PLAIN(5) BQB_GRP_PLAIN(6) BQB_GRP_PLAIN(7)
+        }} }} }} }} }} }} }} }}
+    } else {
+        switch (g0) {
+            BQB_GRP(0) BQB_GRP(1) BQB_GRP(2) BQB_GRP(3) BQB_GRP(4) BQB_GRP(5) BQB_GRP(6) BQB_GRP(7)
+            BQB_GRP(8) BQB_GRP(9) BQB_GRP(10) BQB_GRP(11) BQB_GRP(12) BQB_GRP(13) BQB_GRP(14) BQB_GRP(15)
+            default: break;
+        }
     }
+#undef BQB_GRP_PLAIN
 #undef BQB_GRP
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -378,11 +392,11 @@ __device__ __forceinline__ void mask_groups(mask_t mask, int &g0, int &kend) {
     kend = (64 - __clzll((long long)m) + 3) & ~3;
 }
 
-// The rectangular part of a band-relative pass: row-block pairs that lie wholly below the band see all of its NG groups of
-// four k-steps (bf[0 .. 4 NG)), so the loop needs no diagonal tests, no jump table and no per-pair address arithmetic: per
-// pair 8 NG fragment loads, 8 NG NT DMMAs in four independent chains per point tile (the first DMMA of a chain starts
-// from a zero accumulator), four adds and four FMAs.  ncu on the generic loop (ns = 256): 14.5 instructions per DMMA,
-// among them ~40 of address arithmetic and 17 accumulator clears per pair; this loop issues ~3.5 per DMMA.
+// The rectangular part of a band-relative pass: row-block pairs that lie wholly below the band see all of it, here as NP
+// pairs of k-steps (bf[0 .. 2 NP)), so the loop needs no diagonal tests, no jump table and no per-pair address
+// arithmetic: per row-block pair 4 NP fragment loads, 4 NP NT DMMAs in four independent chains per point tile (the first
+// DMMA of a chain starts from a zero accumulator), four adds and four FMAs.  ncu on the generic loop (ns = 256): 14.5
+// instructions per DMMA, among them ~40 of address arithmetic and 17 accumulator clears per pair; this loop issues ~3.5.
 // pA: fragment (rb, k0) of the pair's first row block (lane included); the second row block starts sAB doubles later, the
 // next pair sNext doubles later, and both distances grow by dAB / dNext per pair (resident triangles: rows get longer;
 // slabs: constant row pitch).
@@ -390,36 +404,30 @@ __device__ __forceinline__ void dmma_z(double &c0, double &c1, double a, double 
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
                  : "=d"(c0), "=d"(c1) : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
 }
-template <int KS, int NT, int NG>
+template <int KS, int NT, int NP>        // NP: pairs of k-steps (bf[0 .. 2 NP))
 __device__ __forceinline__ void rect_pairs(const double *pA, int npair, int sAB, int sNext, int dAB, int dNext,
                                            const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT]) {
-    static_assert(4 * NG <= KS, "groups of the register tile");
+    static_assert(2 * NP <= KS, "k-step pairs of the register tile");
 #pragma unroll 1
     for (int i = 0; i < npair; ++i) {
         const double *pB = pA + sAB;
         double a0[NT], a1[NT], b0[NT], b1[NT], c0[NT], c1[NT], d0[NT], d1[NT];   // (a, b): block A even / odd k; (c, d): block B
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            double fa[4], fb[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { fa[j] = pA[(4 * g + j) * 32]; fb[j] = pB[(4 * g + j) * 32]; }
+        for (int u = 0; u < NP; ++u) {
+            const double fa0 = pA[(2 * u) * 32], fa1 = pA[(2 * u + 1) * 32], fb0 = pB[(2 * u) * 32], fb1 = pB[(2 * u + 1) * 32];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                if (g == 0) {
-                    dmma_z(a0[nt], a1[nt], fa[0], bf[0][nt]);
-                    dmma_z(c0[nt], c1[nt], fb[0], bf[0][nt]);
-                    dmma_z(b0[nt], b1[nt], fa[1], bf[1][nt]);
-                    dmma_z(d0[nt], d1[nt], fb[1], bf[1][nt]);
+                if (u == 0) {
+                    dmma_z(a0[nt], a1[nt], fa0, bf[0][nt]);
+                    dmma_z(c0[nt], c1[nt], fb0, bf[0][nt]);
+                    dmma_z(b0[nt], b1[nt], fa1, bf[1][nt]);
+                    dmma_z(d0[nt], d1[nt], fb1, bf[1][nt]);
                 } else {
-                    dmma(a0[nt], a1[nt], fa[0], bf[4 * g][nt]);
-                    dmma(c0[nt], c1[nt], fb[0], bf[4 * g][nt]);
-                    dmma(b0[nt], b1[nt], fa[1], bf[4 * g + 1][nt]);
-                    dmma(d0[nt], d1[nt], fb[1], bf[4 * g + 1][nt]);
+                    dmma(a0[nt], a1[nt], fa0, bf[2 * u][nt]);
+                    dmma(c0[nt], c1[nt], fb0, bf[2 * u][nt]);
+                    dmma(b0[nt], b1[nt], fa1, bf[2 * u + 1][nt]);
+                    dmma(d0[nt], d1[nt], fb1, bf[2 * u + 1][nt]);
                 }
-                dmma(a0[nt], a1[nt], fa[2], bf[4 * g + 2][nt]);
-                dmma(c0[nt], c1[nt], fb[2], bf[4 * g + 2][nt]);
-                dmma(b0[nt], b1[nt], fa[3], bf[4 * g + 3][nt]);
-                dmma(d0[nt], d1[nt], fb[3], bf[4 * g + 3][nt]);
             }
         }
 #pragma unroll
@@ -436,14 +444,15 @@ __device__ __forceinline__ void rect_pairs(const double *pA, int npair, int sAB,
     }
 }
 template <int KS, int NT>
-__device__ __forceinline__ void rect_dispatch(int ng, const double *pA, int npair, int sAB, int sNext, int dAB, int dNext,
+__device__ __forceinline__ void rect_dispatch(int np, const double *pA, int npair, int sAB, int sNext, int dAB, int dNext,
                                               const double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT]) {
-    switch (ng) {
+    switch (np) {
 #define BQB_RECT(N)                                                                                          \
     case N:                                                                                                  \
-        if constexpr (4 * (N) <= KS) rect_pairs<KS, NT, (4 * (N) <= KS ? (N) : 1)>(pA, npair, sAB, sNext, dAB, dNext, bf, q0, q1); \
+        if constexpr (2 * (N) <= KS) rect_pairs<KS, NT, (2 * (N) <= KS ? (N) : 1)>(pA, npair, sAB, sNext, dAB, dNext, bf, q0, q1); \
         break;
         BQB_RECT(1) BQB_RECT(2) BQB_RECT(3) BQB_RECT(4) BQB_RECT(5) BQB_RECT(6) BQB_RECT(7) BQB_RECT(8)
+        BQB_RECT(9) BQB_RECT(10) BQB_RECT(11) BQB_RECT(12) BQB_RECT(13) BQB_RECT(14) BQB_RECT(15) BQB_RECT(16)
 #undef BQB_RECT
         default: break;
     }
@@ -525,18 +534,23 @@ __device__ __forceinline__ void row_blocks_rolled(const double *base, int rb0, i
     int rb = rb0;
     // REL: pairs from rbf on lie below the band (2 rb + 2 - k0 >= kend) and take the rectangular loop
     const bool rect = REL && plain_band(mask, g0, kend);
-    const int rbf = rect ? min(rb1, max(rb0, ((k0 + kend) >> 1) & ~1)) : rb1;
+    const int kend2 = (64 - __clzll((long long)(unsigned long long)mask) + 1) & ~1;      // band end rounded to a pair of k-steps
+    const int rbf = rect ? min(rb1, max(rb0, ((k0 + kend2) >> 1) & ~1)) : rb1;
 #pragma unroll 1
     for (; rb + 1 < rbf; rb += 2) {
         // rows above the first relevant k-step see none of it (lower-triangular operand): 2 rb + 4 k-steps at most
         if (2 * rb + 4 <= kfirst) continue;
-        row_block_pair<KS, NT>(base + (tri_frags(rb) + k0) * 32, base + (tri_frags(rb + 1) + k0) * 32, 2 * rb + 2 - k0, bf, q0, q1,
-                               mask, g0, kend);
+        if (REL && rect)
+            row_block_pair<KS, NT, REL>(base + (tri_frags(rb) + k0) * 32, base + (tri_frags(rb + 1) + k0) * 32, 2 * rb + 2 - k0, bf, q0, q1,
+                                        mask, g0, kend);
+        else
+            row_block_pair<KS, NT>(base + (tri_frags(rb) + k0) * 32, base + (tri_frags(rb + 1) + k0) * 32, 2 * rb + 2 - k0, bf, q0, q1,
+                                   mask, g0, kend);
     }
     if constexpr (REL) {
         if (rect && rb + 1 < rb1) {
             const int npair = (rb1 - rb) >> 1;
-            rect_dispatch<KS, NT>(kend >> 2, base + (tri_frags(rb) + k0) * 32, npair, (2 * rb + 2) * 32, (4 * rb + 6) * 32, 128, 256, bf,
+            rect_dispatch<KS, NT>(kend2 >> 1, base + (tri_frags(rb) + k0) * 32, npair, (2 * rb + 2) * 32, (4 * rb + 6) * 32, 128, 256, bf,
                                   q0, q1);
             rb += 2 * npair;
         }
@@ -639,17 +653,19 @@ __device__ __forceinline__ void slab_rows(const double *buf, const SlabPlan &p, 
     const int kfirst = k0 + __ffsll((long long)(unsigned long long)mask) - 1;
     int rb = rb0;
     const bool rect = REL && plain_band(mask, g0, kend);
-    const int rbf = rect ? min(rb1, max(rb0, ((k0 + kend) >> 1) & ~1)) : rb1;
+    const int kend2 = (64 - __clzll((long long)(unsigned long long)mask) + 1) & ~1;
+    const int rbf = rect ? min(rb1, max(rb0, ((k0 + kend2) >> 1) & ~1)) : rb1;
 #pragma unroll 1
     for (; rb + 1 < rbf; rb += 2) {
         if (2 * rb + 4 <= kfirst) continue;
         const double *afA = buf + ((rb - rb0) * p.W - p.klo + k0) * 32 + lane;       // afA[j * 32] = fragment (rb, k0 + j)
-        row_block_pair<KS, NT>(afA, afA + p.W * 32, 2 * rb + 2 - k0, bf, q0, q1, mask, g0, kend);
+        if (REL && rect) row_block_pair<KS, NT, REL>(afA, afA + p.W * 32, 2 * rb + 2 - k0, bf, q0, q1, mask, g0, kend);
+        else row_block_pair<KS, NT>(afA, afA + p.W * 32, 2 * rb + 2 - k0, bf, q0, q1, mask, g0, kend);
     }
     if constexpr (REL) {
         if (rect && rb + 1 < rb1) {
             const int npair = (rb1 - rb) >> 1;
-            rect_dispatch<KS, NT>(kend >> 2, buf + ((rb - rb0) * p.W - p.klo + k0) * 32 + lane, npair, p.W * 32, 2 * p.W * 32, 0, 0, bf, q0,
+            rect_dispatch<KS, NT>(kend2 >> 1, buf + ((rb - rb0) * p.W - p.klo + k0) * 32 + lane, npair, p.W * 32, 2 * p.W * 32, 0, 0, bf, q0,
                                   q1);
             rb += 2 * npair;
         }
@@ -684,11 +700,10 @@ __device__ __forceinline__ void slab_pass(const double *__restrict__ op, const S
 
 // Dense candidate / g rows of one dense row block: acc += A(db, k0 + j) . bf[j] over the relevant exp groups of the (relative)
 // mask.  af[j * 32] = fragment (db, k0 + j); nk = k-steps that exist from the tile start on (fragments past it are not read).
-template <int KB, int NT>
+template <int KB, int NT, int GK = exp_group<NT>()>
 __device__ __forceinline__ void dense_acc(const double *af, int nk, const double (&bf)[KB][NT], typename KMask<KB>::type mask,
                                           double (&c0)[NT], double (&c1)[NT], double (&e0)[NT], double (&e1)[NT]) {
-    using mask_t = typename KMask<KB>::type;
-    constexpr int GK = (NT == 1) ? 8 : 4;          // the groups of gen_exps: all of a relevant group's B fragments exist
+    using mask_t = typename KMask<KB>::type;       // GK: the groups of gen_exps -- all of a relevant group's B fragments exist
 #pragma unroll
     for (int g = 0; g < KB / GK; ++g) {
         if ((mask >> (GK * g)) & (((mask_t)1 << GK) - 1)) {     // warp-uniform: a real branch around GK DMMAs
@@ -731,6 +746,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     constexpr int KB = REL ? BK : KS;                       // k-steps of the register tile
     static_assert(!REL || (BK % 8 == 0 && BK <= KS), "band tile: whole exp groups, no larger than the class");
     using rmask_t = typename KMask<KB>::type;
+    // exp groups of the fast path: with 16 warps per SM the latency of four chains is covered by the other warps, and a band
+    // of 8-14 k-steps wastes fewer exponentials on groups of 4 than on groups of 8
+    constexpr int GKK = REL ? BQB_REL_GK : exp_group<NT>();
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     constexpr bool LOCKSTEP = STREAM || ALIGN;              // warps must keep reaching the CTA barriers
     constexpr int THREADS = WARPS * 32;
@@ -873,8 +891,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                 if (!m) return;
                 const int lo = __ffsll((long long)(unsigned long long)m) - 1, hi = 64 - __clzll((long long)(unsigned long long)m);
                 w.kbeg = lo & ~7; w.kend = hi;                    // wide path: windows from a whole exp group
-                w.on = (hi - (lo & ~3) > KB) || a.force_wide;
-                k0 = w.on ? 0 : (lo & ~3);                        // the band's first group of four k-steps is group 0 of the tile
+                // fast path: the band fits the tile and has no holes (sorted observations and the interval criterion of
+                // gen_masks give contiguous masks; anything else is walked pair by pair on the wide path, which never
+                // touches a fragment outside [lo & ~1, hi + 1) -- all a slab holds)
+                const unsigned long long mb = (unsigned long long)m >> lo;
+                w.on = (hi - (lo & ~1) > KB) || (mb & (mb + 1)) != 0 || a.force_wide;
+                k0 = w.on ? 0 : (lo & ~1);                        // even: row blocks end on even k-steps; the band starts in group 0
             };
             band(wmask_l, k0_l, wd_l, Cl, dmax_l);
             band(wmask_tl, k0_tl, wd_tl, Ctl, dmax_tl);
@@ -930,7 +952,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                     if (ALIGN) __syncthreads();          // all warps enter the exp phase together (DMMA / DFMA mixing costs pipe throughput)
                     // relative mask of the register tile (empty on the wide path, which generates its windows itself)
                     const rmask_t rm_l = REL ? (wd_l.on ? (rmask_t)0 : (rmask_t)(mask >> k0_l)) : (rmask_t)mask;
-                    gen_exps<KB, NT, TABN, false>(bf, x, Cl, dmax_l, rm_l, kq, s_xs + 4 * k0_l, s_atl, s_tab, tm, tol2_hi, close);
+                    gen_exps<KB, NT, TABN, false, GKK>(bf, x, Cl, dmax_l, rm_l, kq, s_xs + 4 * k0_l, s_atl, s_tab, tm, tol2_hi, close);
                     if constexpr (STREAM)
                         slab_pass<KB, NT, TABN, REL>(op, plan, res, sub == 0, strm, bf, q0, q1, nb, lane, warp, rm_l, k0_l, wd_l);
                     else tri_pass<KB, NT, TABN, ALIGN, ROLLED, REL>(s_af_l, bf, q0, q1, nb, lane, rm_l, k0_l, wd_l);
@@ -951,7 +973,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                                     dense_acc<KB, NT>(af + kw * 32, nks - kw, bf, rw, c0, c1, e0, e1);
                                 }
                             } else {
-                                dense_acc<KB, NT>(af + k0_l * 32, nks - k0_l, bf, rm_l, c0, c1, e0, e1);
+                                dense_acc<KB, NT, GKK>(af + k0_l * 32, nks - k0_l, bf, rm_l, c0, c1, e0, e1);
                             }
                             if (!RT_SIZES || db * 8 + pq < nrow_res) {      // only the nc + 2 rows that exist have a scratch row
 #pragma unroll
@@ -983,8 +1005,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                             for (int nt = 0; nt < NT; ++nt) close[nt] |= cw[nt];
                         }
                     } else {
-                        gen_exps<KB, NT, TABN, true>(bf, x, Ctl, dmax_tl, rm_tl, kq, s_xs + 4 * k0_tl, s_atl + 4 * k0_tl, s_tab, tm, tol2_hi,
-                                                     close, KS - k0_tl);
+                        gen_exps<KB, NT, TABN, true, GKK>(bf, x, Ctl, dmax_tl, rm_tl, kq, s_xs + 4 * k0_tl, s_atl + 4 * k0_tl, s_tab, tm,
+                                                          tol2_hi, close, KS - k0_tl);
                     }
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)

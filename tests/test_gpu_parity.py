@@ -132,6 +132,44 @@ def test_band_skipping_equals_the_dense_algorithm(lib, ns, shuffle):
     b.close()
 
 
+@pytest.mark.parametrize("ns", [100, 128, 150, 200, 256])
+def test_register_tile_variants_agree(lib, ns, monkeypatch):
+    """The large capacity classes have three scoring kernels (bq_score.cu: BQB_REL = 0 absolute register tile, 1 / 2 the
+    band-relative tile with 16 / 12 warps) and, inside the band-relative ones, a fast path (band fits the tile) and a
+    wide path (windows regenerated per row block).  All of them compute the same sums over the same relevant k-steps in
+    a different order: scores agree to ~1e-13, statuses exactly -- on a grid (narrow hulls: fast path), on unsorted
+    scattered points without the pre-sort (hulls as wide as the domain: wide path), with every warp forced down the wide
+    path, and with the dense cut-off."""
+    from bayesian_quadrature_b200 import synthetic
+    rs = np.random.RandomState(1000 + ns)
+    x_s, l_s = synthetic.observations(ns)
+    x_c = np.array([x_s.max() + 1.1, x_s.max() + 2.9])
+    opt = synthetic.options(ns)
+    b = lib.Batch(1, ns)
+    info = b.setup([ns], [x_c.size], x_s[None], l_s[None], x_c[None],
+                   np.array([synthetic.PARAMS_TL + synthetic.PARAMS_L]), np.array([[opt["x_mean"], opt["x_var"], 0.5]]))
+    assert info["status"][0] == 0
+    b.set_presort(0)
+    grid = synthetic.query_grid(ns, 30011)
+    scattered = rs.uniform(grid[0], grid[-1], 5003)
+    ref = {}
+    for rel, wide, cut in (("0", "0", 72.0), ("1", "0", 72.0), ("2", "0", 72.0), ("1", "1", 72.0), ("2", "1", 72.0),
+                           ("1", "0", float("inf"))):
+        monkeypatch.setenv("BQB_REL", rel)
+        monkeypatch.setenv("BQB_FORCE_WIDE", wide)
+        b.set_cutoff(cut)
+        for name, x_a in (("grid", grid), ("scattered", scattered)):
+            esm, em, st = b.score_host(x_a)
+            if name not in ref:
+                ref[name] = (esm[0].copy(), em[0].copy(), st[0].copy())
+                continue
+            tag = "%s ns=%d rel=%s wide=%s cut=%g" % (name, ns, rel, wide, cut)
+            assert (st[0] == ref[name][2]).all(), tag
+            assert_close(esm[0], ref[name][0], "esm " + tag, rtol=1e-11, atol=1e-300)
+            assert_close(em[0], ref[name][1], "em " + tag, rtol=1e-11, atol=1e-300)
+    b.close()
+
+
 @pytest.mark.parametrize("name,ns", [("c2", 64), ("c3", 256)])
 def test_presort_of_scattered_query_points(lib, name, ns):
     """Query vectors in arbitrary order are sorted on the device by the host entry points, scored ascending and written
