@@ -1182,7 +1182,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 }
 
 #ifndef BQB_REL_DEFAULT
-#define BQB_REL_DEFAULT 0
+#define BQB_REL_DEFAULT 1
 #endif
 constexpr size_t SMEM_LIMIT = 227 * 1024;      // per-CTA opt-in maximum on sm_100 (static + dynamic)
 constexpr size_t SMEM_STATIC_MISC = 256;       // chunk table, mbarriers
@@ -1238,8 +1238,10 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
     return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, BK, 0>(a, n_inst, sm_count, stream, grid_x);
 }
 
-// Tuning switch of the large classes: BQB_REL = 0 absolute register tile (8 warps), 1 band-relative tile of 24 k-steps with
-// 16 warps per CTA, 2 the same with 12 warps.  BQB_FORCE_WIDE = 1 sends every warp down the wide path (tests).
+// Kernel choice of the large classes (environment, read at every launch): BQB_REL = 1 (default) band-relative register tile
+// of 24 k-steps with 16 warps per CTA, 0 the absolute tile with 8 warps (the previous kernels, kept for A/B runs and as the
+// cross-check of tests/test_gpu_parity.py).  12 warps at 166 registers measured the same at ns = 128 and 7 % slower at
+// ns = 256.  BQB_FORCE_WIDE = 1 sends every warp down the wide path (tests).
 static int rel_variant() {
     const char *e = getenv("BQB_REL");
     return e ? atoi(e) : BQB_REL_DEFAULT;
@@ -1286,11 +1288,6 @@ BQB_LAUNCH_DECL(128) {
             return launch_cfg<32, 1, 16, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
         return launch_cfg<32, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
     }
-    if (rv == 2) {
-        if (smem_need<32, 1, 12, false, 512>(a, 0) <= SMEM_LIMIT)
-            return launch_cfg<32, 1, 12, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
-        return launch_cfg<32, 1, 12, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
-    }
     if (smem_need<32, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
         return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
     return launch_cfg<32, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
@@ -1304,11 +1301,6 @@ BQB_LAUNCH_DECL(160) {       // resident while the instances' operands fit (ns <
             return launch_cfg<40, 1, 16, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
         return launch_cfg<40, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
     }
-    if (rv == 2) {
-        if (!force_stream && smem_need<40, 1, 12, false, 512>(a, 0) <= SMEM_LIMIT)
-            return launch_cfg<40, 1, 12, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
-        return launch_cfg<40, 1, 12, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
-    }
     if (!force_stream && smem_need<40, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
         return launch_cfg<40, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
     return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
@@ -1317,7 +1309,6 @@ BQB_LAUNCH_DECL(160) {       // resident while the instances' operands fit (ns <
 BQB_LAUNCH_DECL(256) {
     const int rv = rel_variant();
     if (rv == 1) return launch_cfg<64, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
-    if (rv == 2) return launch_cfg<64, 1, 12, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
     return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
 }
 #else

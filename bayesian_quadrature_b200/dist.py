@@ -37,6 +37,28 @@ def cyclic_shard(x, world_size, rank, block):
     return np.ascontiguousarray(x.reshape(-1, world_size, block)[:, rank, :]).ravel()
 
 
+#: block of the interleaved shards of the sharded BQ calls below
+SHARD_BLOCK = 4096
+
+
+def interleaved_indices(n, world_size, rank, block=SHARD_BLOCK):
+    """Global indices (ascending) of rank's shard of a vector of ANY length n under block-interleaved sharding: blocks of
+    `block` consecutive points are dealt round-robin (block j to rank j % W; the last block may be short).  Like
+    cyclic_shard, every rank gets the same mix of cheap and expensive query points -- contiguous shards leave the ranks that
+    hold the observed region with several times the work of the others under band skipping -- but no divisibility is
+    required.  Local index i is global index ((i // block) * W + rank) * block + i % block."""
+    n, W, block = int(n), int(world_size), int(block)
+    nblk = (n + block - 1) // block
+    mine = np.arange(rank, nblk, W, dtype=np.int64)
+    idx = (mine[:, None] * block + np.arange(block, dtype=np.int64)[None, :]).ravel()
+    return idx[idx < n]
+
+
+def interleaved_global(i, world_size, rank, block=SHARD_BLOCK):
+    """Global index of local index i of rank's interleaved shard."""
+    return ((int(i) // block) * int(world_size) + int(rank)) * block + int(i) % block
+
+
 def combine_argmin(pairs):
     """pairs: [W, 2] array of (local min, global index of its first occurrence); NaN mins never win.
     Returns (min, index) with ties resolved to the smallest global index — np.argmin semantics."""
@@ -119,18 +141,28 @@ class PairExchange(object):
         return float(o[0]), int(o[1])
 
 
-def all_gather_scores(local, n_total):
-    """Concatenate the ranks' contiguous shards (shard_bounds order) into the full score vector."""
+def all_gather_scores(local, n_total, block=0):
+    """The full score vector from the ranks' shards: contiguous shards in shard_bounds order (block = 0), or
+    block-interleaved shards (interleaved_indices) scattered back to their global positions."""
     W, _ = world()
     if W == 1:
         return local
-    sizes = [shard_bounds(n_total, W, r) for r in range(W)]
-    pad = max(hi - lo for lo, hi in sizes)
+    if block:
+        index = [interleaved_indices(n_total, W, r, block) for r in range(W)]
+        sizes = [ix.size for ix in index]
+    else:
+        sizes = [hi - lo for lo, hi in (shard_bounds(n_total, W, r) for r in range(W))]
+    pad = max(max(sizes), 1)
     buf = torch.zeros(pad, dtype=local.dtype, device=local.device)
     buf[: local.numel()] = local
     out = torch.empty(W * pad, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, buf)
-    return torch.cat([out[r * pad: r * pad + (hi - lo)] for r, (lo, hi) in enumerate(sizes)])
+    if not block:
+        return torch.cat([out[r * pad: r * pad + sizes[r]] for r in range(W)])
+    full = torch.empty(n_total, dtype=local.dtype, device=local.device)
+    for r in range(W):
+        full[torch.from_numpy(index[r]).to(local.device)] = out[r * pad: r * pad + sizes[r]]
+    return full
 
 
 def all_reduce_loss(partial_sum, n_samples_total):
@@ -147,26 +179,28 @@ def all_reduce_loss(partial_sum, n_samples_total):
 
 def expected_Z_var_sharded(bq, x_a):
     """``bq.expected_Z_var(x_a)`` with the query points sharded across ranks (C2 / C3): each rank scores its
-    contiguous shard on its GPU, the shards are all-gathered, every rank returns the full vector."""
+    block-interleaved shard (interleaved_indices: balanced work under band skipping) on its GPU, the shards are
+    all-gathered and scattered back, every rank returns the full vector."""
     W, rank = world()
     x_a = np.ascontiguousarray(x_a, dtype=np.float64)
-    lo, hi = shard_bounds(x_a.shape[0], W, rank)
+    mine = interleaved_indices(x_a.shape[0], W, rank)
+    m = mine.size
     dev = torch.device("cuda", bq.device)
     model = bq._device_model()
-    x_d = torch.from_numpy(x_a[lo:hi]).to(dev)
-    esm = torch.empty(max(hi - lo, 1), dtype=torch.float64, device=dev)
+    x_d = torch.from_numpy(x_a[mine]).to(dev)
+    esm = torch.empty(max(m, 1), dtype=torch.float64, device=dev)
     ev = torch.empty_like(esm)
     pair = torch.empty(2, dtype=torch.float64, device=dev)
-    if hi > lo:
-        model.batch.choose_step_device(x_d, esm[: hi - lo], ev[: hi - lo], pair, offset=lo)
-    return all_gather_scores(ev[: hi - lo], x_a.shape[0]).cpu().numpy()
+    if m:
+        model.batch.choose_step_device(x_d, esm[:m], ev[:m], pair, offset=0)
+    return all_gather_scores(ev[:m], x_a.shape[0], block=SHARD_BLOCK).cpu().numpy()
 
 
 def choose_next_sharded(bq, x_a, hypers_tl, hypers_l, params, shard="points"):
     """Deterministic ``choose_next`` (first minimiser of the marginal loss, bq.py:660-663) over the hyper-parameter
     samples ``hypers_tl`` / ``hypers_l`` (as returned by ``bq.sample_hypers``; identical on every rank).
 
-    shard="points"  (C2/C3/C4-by-points): every rank scores its shard of ``x_a`` under ALL samples; the mean over
+    shard="points"  (C2/C3/C4-by-points): every rank scores its block-interleaved shard of ``x_a`` under ALL samples; the mean over
                     samples is taken in sample order on the device (bit-identical to one GPU); the ranks exchange one
                     (min, first global index) pair each.
     shard="samples" (C4-by-samples): every rank scores ALL points under its contiguous subset of samples; the partial
@@ -177,14 +211,15 @@ def choose_next_sharded(bq, x_a, hypers_tl, hypers_l, params, shard="points"):
     n = len(hypers_tl)
     dev = torch.device("cuda", bq.device)
     if shard == "points":
-        lo, hi = shard_bounds(x_a.shape[0], W, rank)
-        if hi > lo:
-            loss, batch = bq.marginal_loss(x_a[lo:hi], hypers_tl, hypers_l, params)
-            mn, idx = batch.argmin_device(loss)
+        mine = interleaved_indices(x_a.shape[0], W, rank)
+        if mine.size:
+            loss, batch = bq.marginal_loss(x_a[mine], hypers_tl, hypers_l, params)
+            mn, idx = batch.argmin_device(loss)         # first local minimiser = smallest global index among this rank's
             batch.close()
+            idx = interleaved_global(idx, W, rank)
         else:
             mn, idx = float("inf"), 0
-        mn, idx = all_argmin(mn, idx, lo, device=dev)
+        mn, idx = all_argmin(mn, idx, 0, device=dev)
     elif shard == "samples":
         lo, hi = shard_bounds(n, W, rank)
         total = torch.zeros(x_a.shape[0], dtype=torch.float64, device=dev)

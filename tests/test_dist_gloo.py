@@ -43,6 +43,25 @@ def test_cyclic_shard_and_its_index_map():
         bqdist.cyclic_shard(x, 7, 0, 1000)
 
 
+def test_interleaved_shards_partition_any_length():
+    """Block-interleaved shards (the sharded BQ calls): a partition of 0 .. n-1 for any n, ascending within a rank
+    (so the first local minimiser is the rank's smallest global one), balanced to within one block, and
+    interleaved_global is the index map."""
+    for n in (0, 1, 4095, 4096, 4097, 100003):
+        for W in (1, 2, 3, 8):
+            for blk in (4096, 1000):
+                parts = [bqdist.interleaved_indices(n, W, r, blk) for r in range(W)]
+                allidx = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+                assert np.array_equal(np.sort(allidx), np.arange(n))
+                sizes = [p.size for p in parts]
+                assert max(sizes) - min(sizes) <= blk
+                for r, p in enumerate(parts):
+                    assert (np.diff(p) > 0).all()
+                    for i in (0, p.size // 2, p.size - 1):
+                        if 0 <= i < p.size:
+                            assert bqdist.interleaved_global(i, W, r, blk) == p[i]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -63,6 +82,14 @@ def _worker(rank, world, port, n, q):
         local = torch.from_numpy(full[lo:hi].copy())
         gathered = bqdist.all_gather_scores(local, n)
         ok_gather = bool((gathered.numpy() == full).all())
+        for blk in (4, 4096):                                   # block-interleaved shards scattered back
+            mine = bqdist.interleaved_indices(n, world, rank, blk)
+            g2 = bqdist.all_gather_scores(torch.from_numpy(full[mine].copy()), n, block=blk)
+            ok_gather = ok_gather and bool((g2.numpy() == full).all())
+            li = int(np.argmin(full[mine])) if mine.size else 0
+            mn2, idx2 = bqdist.all_argmin(float(full[mine].min()) if mine.size else float("inf"),
+                                          bqdist.interleaved_global(li, world, rank, blk) if mine.size else 0, 0)
+            ok_gather = ok_gather and idx2 == int(np.argmin(full)) and mn2 == full.min()
         mn, idx = bqdist.all_argmin(float(local.min()), int(local.argmin()), lo)
         ok_argmin = (idx == int(np.argmin(full))) and (mn == full.min())
         part = torch.from_numpy(full[lo:hi].copy()).sum().reshape(1)

@@ -134,8 +134,8 @@ def test_band_skipping_equals_the_dense_algorithm(lib, ns, shuffle):
 
 @pytest.mark.parametrize("ns", [100, 128, 150, 200, 256])
 def test_register_tile_variants_agree(lib, ns, monkeypatch):
-    """The large capacity classes have three scoring kernels (bq_score.cu: BQB_REL = 0 absolute register tile, 1 / 2 the
-    band-relative tile with 16 / 12 warps) and, inside the band-relative ones, a fast path (band fits the tile) and a
+    """The large capacity classes have two scoring kernels (bq_score.cu: BQB_REL = 0 absolute register tile, 1 the
+    band-relative tile with 16 warps, the default) and, inside the band-relative one, a fast path (band fits the tile) and a
     wide path (windows regenerated per row block).  All of them compute the same sums over the same relevant k-steps in
     a different order: scores agree to ~1e-13, statuses exactly -- on a grid (narrow hulls: fast path), on unsorted
     scattered points without the pre-sort (hulls as wide as the domain: wide path), with every warp forced down the wide
@@ -153,8 +153,7 @@ def test_register_tile_variants_agree(lib, ns, monkeypatch):
     grid = synthetic.query_grid(ns, 30011)
     scattered = rs.uniform(grid[0], grid[-1], 5003)
     ref = {}
-    for rel, wide, cut in (("0", "0", 72.0), ("1", "0", 72.0), ("2", "0", 72.0), ("1", "1", 72.0), ("2", "1", 72.0),
-                           ("1", "0", float("inf"))):
+    for rel, wide, cut in (("0", "0", 72.0), ("1", "0", 72.0), ("1", "1", 72.0), ("1", "0", float("inf"))):
         monkeypatch.setenv("BQB_REL", rel)
         monkeypatch.setenv("BQB_FORCE_WIDE", wide)
         b.set_cutoff(cut)
