@@ -1286,7 +1286,8 @@ BQB_LAUNCH_DECL(128) {
     if (rv == 1) {
         if (smem_need<32, 1, 16, false, 512>(a, 0) <= SMEM_LIMIT)
             return launch_cfg<32, 1, 16, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
-        return launch_cfg<32, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+        if (smem_need<32, 1, 16, true, 2048>(a, 2 * 32) <= SMEM_LIMIT)
+            return launch_cfg<32, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
     }
     if (smem_need<32, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
         return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
@@ -1299,7 +1300,8 @@ BQB_LAUNCH_DECL(160) {       // resident while the instances' operands fit (ns <
     if (rv == 1) {
         if (!force_stream && smem_need<40, 1, 16, false, 512>(a, 0) <= SMEM_LIMIT)
             return launch_cfg<40, 1, 16, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
-        return launch_cfg<40, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+        if (smem_need<40, 1, 16, true, 2048>(a, 2 * 40) <= SMEM_LIMIT)
+            return launch_cfg<40, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
     }
     if (!force_stream && smem_need<40, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
         return launch_cfg<40, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
@@ -1308,7 +1310,9 @@ BQB_LAUNCH_DECL(160) {       // resident while the instances' operands fit (ns <
 #elif BQB_SCORE_CLASS == 256
 BQB_LAUNCH_DECL(256) {
     const int rv = rel_variant();
-    if (rv == 1) return launch_cfg<64, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    // (with >= 13 candidates the scratch rows of 16 warps leave no room for the chunk buffers: the 8-warp kernel takes over)
+    if (rv == 1 && smem_need<64, 1, 16, true, 2048>(a, 2 * 64) <= SMEM_LIMIT)
+        return launch_cfg<64, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
     return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
 }
 #else

@@ -94,6 +94,35 @@ def test_capi_vs_oracle_random(lib, oracle, ns, seed):
     b.close()
 
 
+@pytest.mark.parametrize("ns,nc", [(64, 16), (100, 9), (128, 16), (150, 12), (200, 7), (256, 16)])
+def test_many_candidates_vs_oracle(lib, oracle, ns, nc):
+    """Up to NC_MAX = 16 candidates: two or three dense row blocks in the scoring kernels (and, in the resident classes,
+    the fall-back to the streamed kernel when the scratch rows no longer fit).  A sorted grid (narrow bands: the fast
+    path of the band-relative kernels) and unsorted scattered points (wide path) against the oracle."""
+    rs = np.random.RandomState(77 + ns)
+    x_s = np.linspace(-0.55 * ns, 0.55 * ns, ns) + rs.uniform(-0.2, 0.2, ns)
+    l_s = np.exp(-0.5 * (x_s / (0.3 * np.ptp(x_s))) ** 2) * rs.uniform(0.5, 1.5, ns) * 0.3 + 1e-3
+    left = x_s.min() - 1.1 * (1 + np.arange(nc // 2))
+    right = x_s.max() + 1.1 * (1 + np.arange(nc - nc // 2))
+    x_c = np.sort(np.concatenate([left, right]))
+    ptl, pl = (4.0, 1.3, 0.0), (0.5, 1.0, 0.0)
+    mu, var, thresh = 0.2, float(np.ptp(x_s) ** 2 / 4), 0.5
+    m = oracle.OracleModel(x_s, l_s, x_c, ptl, pl, mu, var, thresh)
+    b = lib.Batch(1, ns)
+    info = b.setup([ns], [nc], x_s[None], l_s[None], x_c[None], np.array([ptl + pl]), np.array([[mu, var, thresh]]))
+    assert info["status"][0] == 0
+    assert_close(info["Z_mean"][0], m.Z_mean(), "Z_mean")
+    lo, hi = x_c.min() - 4, x_c.max() + 4
+    for name, x_a in (("grid", np.linspace(lo, hi, 4001)),
+                      ("scattered", np.concatenate([rs.uniform(lo, hi, 1500), x_c, x_c + 0.49, x_c - 0.25, x_s[:5]]))):
+        esm, em, st = b.score_host(x_a)
+        o_esm, o_em, o_st = m.esm_and_em(x_a)
+        assert ((st[0] & 3) == (o_st & 3)).all(), name
+        assert_close(esm[0], o_esm, "%s esm ns=%d nc=%d" % (name, ns, nc))
+        assert_close(em[0], o_em, "%s em ns=%d nc=%d" % (name, ns, nc))
+    b.close()
+
+
 @pytest.mark.parametrize("ns,shuffle", [(64, False), (64, True), (128, True), (150, False), (256, True), (256, False)])
 def test_band_skipping_equals_the_dense_algorithm(lib, ns, shuffle):
     """The scoring kernels skip cross-kernel k-steps whose elements are below e^-72 of their point's leading element
