@@ -14,6 +14,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 #: bq_score.cu is compiled once per observation-capacity class (its instantiations only) plus once as the dispatcher,
 #: so that the classes build in parallel
 SCORE_CLASSES = [16, 64, 128, 160, 256]
+#: ... and the band-relative kernels of the large classes in units of their own
+REL_CLASSES = [128, 160, 256]
 
 
 def _nvcc():
@@ -35,6 +37,7 @@ def _units():
         if src == "bq_score.cu":
             units.append((src, base + ".o", []))
             units += [(src, "%s_%d.o" % (base, c), ["-DBQB_SCORE_CLASS=%d" % c]) for c in SCORE_CLASSES]
+            units += [(src, "%s_%d_rel.o" % (base, c), ["-DBQB_SCORE_CLASS=%d" % c, "-DBQB_SCORE_REL=1"]) for c in REL_CLASSES]
         else:
             units.append((src, base + ".o", []))
     return units

@@ -1242,11 +1242,11 @@ static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cuda
 // of 24 k-steps with 16 warps per CTA, 0 the absolute tile with 8 warps (the previous kernels, kept for A/B runs and as the
 // cross-check of tests/test_gpu_parity.py).  12 warps at 166 registers measured the same at ns = 128 and 7 % slower at
 // ns = 256.  BQB_FORCE_WIDE = 1 sends every warp down the wide path (tests).
-static int rel_variant() {
+[[maybe_unused]] static int rel_variant() {
     const char *e = getenv("BQB_REL");
     return e ? atoi(e) : BQB_REL_DEFAULT;
 }
-static ScoreArgs with_env(ScoreArgs a) {
+[[maybe_unused]] static ScoreArgs with_env(ScoreArgs a) {
     const char *e = getenv("BQB_FORCE_WIDE");
     a.force_wide = (e && atoi(e)) ? 1 : 0;
     return a;
@@ -1259,6 +1259,9 @@ static ScoreArgs with_env(ScoreArgs a) {
 // This file is compiled once per capacity class (-DBQB_SCORE_CLASS=16|64|128|160|256: the instantiations of that class
 // only, so that the classes build in parallel) and once without the macro (the dispatcher).
 #define BQB_LAUNCH_DECL(C) cudaError_t launch_score_##C(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x)
+// band-relative kernels of a class: a translation unit of their own (-DBQB_SCORE_REL=1) so that the build stays parallel;
+// returns cudaErrorInvalidConfiguration, without launching, when their shared memory does not fit this launch
+#define BQB_LAUNCH_REL_DECL(C) cudaError_t launch_score_rel_##C(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x)
 #ifndef BQB_SCORE_CLASS
 BQB_LAUNCH_DECL(16);
 BQB_LAUNCH_DECL(64);
@@ -1275,44 +1278,69 @@ cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStrea
         default: return cudaErrorInvalidValue;
     }
 }
+#elif defined(BQB_SCORE_REL)
+#if BQB_SCORE_CLASS == 128
+BQB_LAUNCH_REL_DECL(128) {
+    if (smem_need<32, 1, 16, false, 512>(a, 0) <= SMEM_LIMIT)
+        return launch_cfg<32, 1, 16, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    if (smem_need<32, 1, 16, true, 2048>(a, 2 * 32) <= SMEM_LIMIT)
+        return launch_cfg<32, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    return cudaErrorInvalidConfiguration;
+}
+#elif BQB_SCORE_CLASS == 160
+BQB_LAUNCH_REL_DECL(160) {      // resident only up to ns = 128 here (the scratch of 16 warps), streamed above
+    static const bool force_stream = getenv("BQB_FORCE_STREAM") && atoi(getenv("BQB_FORCE_STREAM"));      // tuning aid
+    if (!force_stream && smem_need<40, 1, 16, false, 512>(a, 0) <= SMEM_LIMIT)
+        return launch_cfg<40, 1, 16, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    if (smem_need<40, 1, 16, true, 2048>(a, 2 * 40) <= SMEM_LIMIT)
+        return launch_cfg<40, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    return cudaErrorInvalidConfiguration;
+}
+#elif BQB_SCORE_CLASS == 256
+BQB_LAUNCH_REL_DECL(256) {      // (with >= 13 candidates the scratch rows of 16 warps leave no room for the chunk buffers)
+    if (smem_need<64, 1, 16, true, 2048>(a, 2 * 64) <= SMEM_LIMIT)
+        return launch_cfg<64, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    return cudaErrorInvalidConfiguration;
+}
+#else
+#error "band-relative kernels exist for the classes 128, 160 and 256"
+#endif
 #elif BQB_SCORE_CLASS == 16
 BQB_LAUNCH_DECL(16) { return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a, n_inst, sm_count, stream, grid_x); }
 #elif BQB_SCORE_CLASS == 64
 // (rolled pairs, free-running warps and 4 x 4-warp CTAs were all slower with band skipping: 0.31 / 0.37 / 0.34 / 0.47 ms vs 0.28)
+// (the band-relative loops <16, NT=1, 16 warps, BK=16> measured 0.364 ms against 0.286: at ns = 64 the band is most of the tile)
 BQB_LAUNCH_DECL(64) { return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x); }
 #elif BQB_SCORE_CLASS == 128
+BQB_LAUNCH_REL_DECL(128);
 BQB_LAUNCH_DECL(128) {
-    const int rv = rel_variant();
-    if (rv == 1) {
-        if (smem_need<32, 1, 16, false, 512>(a, 0) <= SMEM_LIMIT)
-            return launch_cfg<32, 1, 16, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
-        if (smem_need<32, 1, 16, true, 2048>(a, 2 * 32) <= SMEM_LIMIT)
-            return launch_cfg<32, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    if (rel_variant() == 1) {
+        const cudaError_t e = launch_score_rel_128(a, n_inst, sm_count, stream, grid_x);
+        if (e != cudaErrorInvalidConfiguration) return e;
     }
     if (smem_need<32, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
         return launch_cfg<32, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
     return launch_cfg<32, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
 }
 #elif BQB_SCORE_CLASS == 160
-BQB_LAUNCH_DECL(160) {       // resident while the instances' operands fit (ns <= 136 ... 144 depending on the candidates), then streamed
+BQB_LAUNCH_REL_DECL(160);
+BQB_LAUNCH_DECL(160) {       // absolute tile: resident while the instances' operands fit (ns <= 136 ... 144 depending on the candidates), then streamed
     static const bool force_stream = getenv("BQB_FORCE_STREAM") && atoi(getenv("BQB_FORCE_STREAM"));      // tuning aid
-    const int rv = rel_variant();
-    if (rv == 1) {
-        if (!force_stream && smem_need<40, 1, 16, false, 512>(a, 0) <= SMEM_LIMIT)
-            return launch_cfg<40, 1, 16, 1, false, 512, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
-        if (smem_need<40, 1, 16, true, 2048>(a, 2 * 40) <= SMEM_LIMIT)
-            return launch_cfg<40, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    if (rel_variant() == 1) {
+        const cudaError_t e = launch_score_rel_160(a, n_inst, sm_count, stream, grid_x);
+        if (e != cudaErrorInvalidConfiguration) return e;
     }
     if (!force_stream && smem_need<40, 2, 8, false, 512>(a, 0) <= SMEM_LIMIT)
         return launch_cfg<40, 2, 8, 1, false, 512, false, true>(a, n_inst, sm_count, stream, grid_x);
     return launch_cfg<40, 2, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
 }
 #elif BQB_SCORE_CLASS == 256
+BQB_LAUNCH_REL_DECL(256);
 BQB_LAUNCH_DECL(256) {
-    const int rv = rel_variant();
-    // (with >= 13 candidates the scratch rows of 16 warps leave no room for the chunk buffers: the 8-warp kernel takes over)
-    if (rv == 1 && smem_need<64, 1, 16, true, 2048>(a, 2 * 64) <= SMEM_LIMIT)
-        return launch_cfg<64, 1, 16, 1, true, 2048, false, true, 24>(with_env(a), n_inst, sm_count, stream, grid_x);
+    if (rel_variant() == 1) {
+        const cudaError_t e = launch_score_rel_256(a, n_inst, sm_count, stream, grid_x);
+        if (e != cudaErrorInvalidConfiguration) return e;
+    }
     return launch_cfg<64, 1, 8, 1, true, 2048, false, true>(a, n_inst, sm_count, stream, grid_x);
 }
 #else
