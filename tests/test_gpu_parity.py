@@ -444,3 +444,58 @@ def test_full_size_properties_c2(lib, oracle):
     assert_close(em[0].cpu().numpy()[sub], o_em, "c2 subsample em")
     assert ((s[sub] & 3) == (o_st & 3)).all()
     b.close()
+
+
+def test_full_size_properties_c3(lib, oracle, monkeypatch):
+    """BASELINE configs[2] at full size (ns=256, 10^7 points) on one GPU, through the band-relative streamed kernel:
+    determinism, tiling independence, non-negativity, the reference at the fixture's grid points, device argmin == host
+    argmin == the reference's choice, agreement with the absolute-tile kernel (BQB_REL=0) over all 10^7 points, and a
+    300-point subsample against the oracle."""
+    import torch
+    from bayesian_quadrature_b200 import synthetic
+    g = load_golden("c3")
+    b, info = batch_of(lib, g)
+    na = int(g["na_full"])
+    grid = synthetic.query_grid(256, na)
+    dev = torch.device("cuda", 0)
+    x_d = torch.from_numpy(grid).to(dev)
+    esm = torch.empty(1, na, dtype=torch.float64, device=dev)
+    em = torch.empty_like(esm)
+    st = torch.empty(1, na, dtype=torch.int32, device=dev)
+    b.score_device(x_d, esm, em, st)
+    esm2 = torch.empty_like(esm)
+    b.score_device(x_d, esm2)
+    cut = na // 3 + 5
+    esm3 = torch.empty_like(esm)
+    b.score_device(x_d[:cut], esm3[:, :cut])
+    b.score_device(x_d[cut:], esm3[:, cut:])
+    torch.cuda.synchronize()
+    assert torch.equal(esm, esm2) and torch.equal(esm, esm3)
+    monkeypatch.setenv("BQB_REL", "0")                           # the absolute-tile kernel: same sums, other order
+    esm_abs = torch.empty_like(esm)
+    b.score_device(x_d, esm_abs)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("BQB_REL")
+    e, e_abs = esm[0].cpu().numpy(), esm_abs[0].cpu().numpy()
+    s = st[0].cpu().numpy()
+    assert (e >= 0).all() and np.isfinite(e).all()
+    assert not (s & ~(lib.ST_SHORTCUT | lib.ST_NOTPD)).any()
+    assert_close(e, e_abs, "c3 band-relative vs absolute tile", rtol=1e-11, atol=1e-300)
+    k = g["grid_idx"].size
+    assert_close(e[g["grid_idx"]], g["esm"][:k], "c3 full-grid esm at fixture indices")
+    assert_close(em[0].cpu().numpy()[g["grid_idx"]], g["em"][:k], "c3 full-grid em at fixture indices")
+    ev, pair = torch.empty(na, dtype=torch.float64, device=dev), torch.empty(2, dtype=torch.float64, device=dev)
+    esm_f = torch.empty(na, dtype=torch.float64, device=dev)
+    b.choose_step_device(x_d, esm_f, ev, pair, offset=0)
+    pr, ev_h = pair.cpu().numpy(), ev.cpu().numpy()
+    assert torch.equal(esm_f, esm[0])
+    assert pr[0] == ev_h.min() and int(pr[1]) == int(np.argmin(ev_h))
+    gi = g["grid_idx"]                                           # among the fixture's points: the reference's choice
+    assert int(gi[int(np.argmin(ev_h[gi]))]) == int(gi[int(np.argmax(g["esm"][:k]))])
+    sub = np.random.RandomState(6).choice(na, 300, replace=False)
+    m = oracle.OracleModel(g["x_s"], g["l_s"], g["x_c"], g["params_tl"], g["params_l"], float(g["x_mean"]),
+                           float(g["x_var"]), float(g["candidate_thresh"]))
+    o_esm, o_em, o_st = m.esm_and_em(grid[sub])
+    assert_close(e[sub], o_esm, "c3 subsample esm")
+    assert ((s[sub] & 3) == (o_st & 3)).all()
+    b.close()
