@@ -27,6 +27,9 @@
 //     exponentiated (gen_exps) nor multiplied (mask-predicated / jump-table DMMA loops), and the streamed
 //     variants fetch only the rows and columns of the operands that the CTA's masks touch.  The setup kernel
 //     sorts the observations, so the band is contiguous.  cut_arg = +inf makes every k-step relevant.
+//   * BAND-RELATIVE TILE (classes 128 / 160 / 256, template parameter BK): the register tile holds BK = 24 k-steps from
+//     the warp's band start instead of all KS (128 registers, 16 warps per SM); row-block pairs below the band run a
+//     branch-free rectangular loop (rect_pairs), bands that do not fit walk windows inside the row-block loop (Wide).
 //
 // Grid: persistent CTAs (a multiple of the SM count); super-tiles are dealt round-robin with a
 // unit-granular remainder; gridDim.y = model instances (hyper-parameter sets or independent problems).
