@@ -31,6 +31,7 @@ SYMBOLS = {
     "bqb_batch_destroy": (None, [_vp]),
     "bqb_batch_setup": (ctypes.c_int, [_vp, _ip, _ip, _dp, _dp, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, _vp]),
     "bqb_batch_stage": (ctypes.c_int, [_vp, _ip, _dp, _dp, ctypes.c_int, _dp, _dp, _vp]),
+    "bqb_batch_set_hypers": (ctypes.c_int, [_vp, _dp, _vp]),
     "bqb_batch_setup_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "bqb_batch_seed_candidates": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint), _vp]),
     "bqb_batch_rng_get": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint), _ip]),
@@ -104,6 +105,16 @@ def device_count():
     return n.value
 
 
+def ns_capacity(ns):
+    """Padded observation capacity class the library uses for `ns` observations; NotImplementedError beyond the device limit."""
+    cap = load().bqb_ns_capacity(int(ns))
+    if cap == EUNSUPPORTED:
+        raise NotImplementedError("%d observations per instance exceed the device limit" % ns)
+    if cap < 0:
+        raise ValueError("invalid number of observations: %s" % ns)
+    return cap
+
+
 def _d(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
@@ -175,6 +186,11 @@ class Batch(object):
         hyp, prior = _d(hyp).reshape(B, 6), _d(prior).reshape(B, 3)
         _check(load().bqb_batch_stage(self._h, ns.ctypes.data_as(_ip), _pd(x_s), _pd(l_s), x_s.shape[1], _pd(hyp), _pd(prior),
                                       _vp(stream) if stream else None), "bqb_batch_stage")
+
+    def set_hypers(self, hyp, stream=None):
+        """Replace the hyper-parameters [n_inst, 6] of the staged instances (the next setup_device uses them)."""
+        hyp = _d(hyp).reshape(self.n_inst, 6)
+        _check(load().bqb_batch_set_hypers(self._h, _pd(hyp), _vp(stream) if stream else None), "bqb_batch_set_hypers")
 
     def setup_device(self, check_max=False, stream=None):
         _check(load().bqb_batch_setup_device(self._h, int(check_max), _vp(stream) if stream else None), "bqb_batch_setup_device")

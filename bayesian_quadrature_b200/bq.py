@@ -54,20 +54,52 @@ def _raise_setup(status):
 
 
 class _DeviceModel(object):
-    """The device-resident factors of ONE (data, candidates, hyper-parameter) state."""
+    """The device-resident factors of ONE BQ object: a single-instance batch handle that lives as long as the
+    observation capacity class does.  ``refresh`` re-stages the data only when observations / candidates / prior
+    changed and otherwise just replaces the six hyper-parameters and re-runs the setup kernel on the same buffers
+    (what one evaluation of the hyper-parameter log-density costs, bq.py:533-552)."""
 
-    def __init__(self, key, x_s, l_s, x_c, params_tl, params_l, x_mean, x_var, thresh, device, check_max=False):
-        self.key = key
+    def __init__(self, device):
+        self.device = device
+        self.batch = None
+        self.cap = None
+        self.data_key = None
+        self.key = None          # (data_key, hyper-parameters) the factors on the device belong to
+        self.guarded = False     # the bq.py:942-947 guard was evaluated for `key`
+        self.status = None
+        self.Z_mean = self.Z_var = self.log_lh = None
+        self.l_c = None
+
+    def close(self):
+        if self.batch is not None:
+            self.batch.close()
+        self.batch, self.key, self.data_key = None, None, None
+
+    def refresh(self, data_key, x_s, l_s, x_c, hyp, prior, check_max):
+        key = (data_key, tuple(float(v) for v in hyp))
+        if key == self.key and (self.guarded or not check_max):
+            return self
         ns, nc = x_s.shape[0], x_c.shape[0]
-        self.batch = _lib.Batch(1, ns, device=device)
-        hyp = np.concatenate([np.asarray(params_tl, dtype=DTYPE), np.asarray(params_l, dtype=DTYPE)])
-        info = self.batch.setup([ns], [nc], x_s[None], l_s[None], x_c[None] if nc else np.zeros((1, 0)),
-                                hyp[None], np.array([[x_mean, x_var, thresh]]), check_max=check_max)
+        cap = _lib.ns_capacity(ns)
+        if self.batch is None or cap != self.cap:
+            self.close()
+            self.batch, self.cap = _lib.Batch(1, cap, device=self.device), cap
+        hyp = np.asarray(hyp, dtype=DTYPE).reshape(1, 6)
+        self.key = None
+        if data_key != self.data_key:
+            info = self.batch.setup([ns], [nc], x_s[None], l_s[None], x_c[None] if nc else np.zeros((1, 0)), hyp,
+                                    np.asarray(prior, dtype=DTYPE).reshape(1, 3), check_max=check_max)
+            self.data_key = data_key
+        else:
+            self.batch.set_hypers(hyp)
+            info = self.batch.setup_device(check_max=check_max)
+        self.key, self.guarded = key, bool(check_max)
         self.status = int(info["status"][0])
         self.Z_mean = float(info["Z_mean"][0])
         self.Z_var = float(info["Z_var"][0])
         self.log_lh = float(info["log_lh"][0])
         self.l_c = np.array(info["l_c"][0, :nc])
+        return self
 
 
 class _PinnedPool(object):
@@ -127,7 +159,7 @@ class BQ(object):
         self.gp_log_l = self.gp_l = None
         self.x_c = self.l_c = self.nc = None
         self.x_sc = self.l_sc = self.nsc = None
-        self._approx_x = self._approx_px = None
+        self._approx_cache = None
         self._reset_device_state()
 
     def _reset_device_state(self):
@@ -167,8 +199,10 @@ class BQ(object):
         self._choose_candidates(params_l)
         self.gp_l = GP(kernel(*params_l[:-1]), self.x_sc, self.l_sc, s=params_l[-1])
         self.gp_l.jitter = np.zeros(self.nsc, dtype=DTYPE)
-        self._approx_x = self._make_approx_x()
-        self._approx_px = self._make_approx_px()
+        # the 1000-point approximation grid (bq.py:170-171) is only read by the trapezoid path and by pickling:
+        # built on first access (properties below), so that init / add_observation do not pay for it every round
+        self._approx_cache = None
+        self._approx_spec = (self._approx_bound(-1), self._approx_bound(+1))     # as of init, like the reference's grid
         self.initialized = True
 
     def _choose_candidates(self, params_l=None):
@@ -186,33 +220,34 @@ class BQ(object):
         self.nc = self.x_c.shape[0]
         if params_l is None:
             params_l = self.gp_l.params
-        model = self._build_device_model(self.gp_log_l.params, np.asarray(params_l, dtype=DTYPE), check_max=False)
-        self.l_c = model.l_c
+        self.l_c = self._log_l_values(self.gp_log_l.params, np.asarray(params_l, dtype=DTYPE), check_max=False)
         self.x_sc = np.array(np.concatenate([self.x_s, self.x_c]))
         self.l_sc = np.array(np.concatenate([self.l_s, self.l_c]))
         self.nsc = self.ns + self.nc
 
     # ------------------------------------------------------------------ device model cache
-    def _state_key(self, params_tl, params_l):
-        return (self.x_s.tobytes(), self.l_s.tobytes(), self.x_c.tobytes(), tuple(float(p) for p in params_tl),
-                tuple(float(p) for p in params_l), float(self.options["x_mean"][0]), float(self.options["x_cov"][0, 0]),
-                self.options["candidate_thresh"], self.device)
+    def _data_key(self):
+        return (self.x_s.tobytes(), self.l_s.tobytes(), self.x_c.tobytes(), float(self.options["x_mean"][0]),
+                float(self.options["x_cov"][0, 0]), self.options["candidate_thresh"], self.device)
 
-    def _build_device_model(self, params_tl, params_l, check_max):
-        key = self._state_key(params_tl, params_l)
-        if self._dev_model is not None and self._dev_model.key == key:
-            model = self._dev_model
-        else:
+    def _refresh_device(self, params_tl, params_l, check_max):
+        """Device factors for (current data, the given parameters); returns the model whatever its setup status."""
+        if self._dev_model is None or self._dev_model.device != self.device:
             if self._dev_model is not None:
-                self._dev_model.batch.close()
-            model = _DeviceModel(key, self.x_s, self.l_s, self.x_c, params_tl, params_l,
-                                 float(self.options["x_mean"][0]), float(self.options["x_cov"][0, 0]),
-                                 self.options["candidate_thresh"], self.device, check_max=check_max)
-            self._dev_model = model
-        if model.status != _lib.SETUP_OK:
-            self._dev_model = None
+                self._dev_model.close()
+            self._dev_model = _DeviceModel(self.device)
+        hyp = np.concatenate([np.asarray(params_tl, dtype=DTYPE), np.asarray(params_l, dtype=DTYPE)])
+        prior = (float(self.options["x_mean"][0]), float(self.options["x_cov"][0, 0]), self.options["candidate_thresh"])
+        return self._dev_model.refresh(self._data_key(), self.x_s, self.l_s, self.x_c, hyp, prior, check_max)
+
+    def _log_l_values(self, params_tl, params_l, check_max):
+        """l_c = exp(gp_log_l.mean(x_c)) from the device (bq.py:985 / :942-950).  Only gp_log_l is involved, as in the
+        reference: a gp_l Gram matrix that is not positive definite under the *current* gp_l parameters is not an
+        error here (l_c is computed before K_l is factorised) -- it surfaces when the gp_l factors are used."""
+        model = self._refresh_device(params_tl, params_l, check_max)
+        if model.status not in (_lib.SETUP_OK, _lib.SETUP_KL_NOTPD):
             _raise_setup(model.status)
-        return model
+        return model.l_c
 
     def _device_model(self):
         """Device factors for the *current* state; rebuilt only when data or parameters changed
@@ -220,11 +255,14 @@ class BQ(object):
         self._require_exact("device model")
         if not self.initialized and self.gp_l is None:
             raise RuntimeError("BQ object is not initialized: call init() first")
-        return self._build_device_model(self.gp_log_l.params, self.gp_l.params, check_max=False)
+        model = self._refresh_device(self.gp_log_l.params, self.gp_l.params, check_max=False)
+        if model.status != _lib.SETUP_OK:
+            _raise_setup(model.status)
+        return model
 
     def _invalidate_device(self):
         if self._dev_model is not None:
-            self._dev_model.batch.close()
+            self._dev_model.close()
         self._dev_model = None
 
     # ------------------------------------------------------------------ mean / variance of l (host GPs)
@@ -361,22 +399,43 @@ class BQ(object):
     # ------------------------------------------------------------------ hyper-parameters (host)
     def _make_llh_params(self, params):
         """Joint log marginal likelihood of both GPs as a function of the parameter vector
-        (bq.py:533-552); invalid parameters map to -inf."""
+        (bq.py:533-552); invalid parameters map to -inf.
+
+        The reference evaluates it as _set_gp_log_l_params (l_c refreshed, "GP mean is too large" guard) ->
+        _set_gp_l_params -> gp_log_l.log_lh + gp_l.log_lh.  Here ONE run of the setup kernel on the object's
+        resident device buffers (only the six hyper-parameters are uploaded) yields l_c, the guard and both log
+        likelihoods; the host GP objects are left in exactly the state the reference's sequence leaves them in."""
         nparam = len(params)
 
         def f(x):
             if x is None or np.isnan(x).any():
                 return -np.inf
+            new_tl = dict(zip(params, x[:nparam]))
+            new_l = dict(zip(params, x[nparam:]))
             try:
-                self._set_gp_log_l_params(dict(zip(params, x[:nparam])))
-                self._set_gp_l_params(dict(zip(params, x[nparam:])))
-            except (ValueError, np.linalg.LinAlgError):
+                for p, v in new_tl.items():                  # bq.py:934-936 (ValueError from the first invalid value)
+                    self.gp_log_l.set_param(p, v)
+            except ValueError:
                 return -np.inf
+            self.gp_log_l.jitter.fill(0)
+            names = list(self.gp_l.K.names) + ["s"]
+            trial_l, l_ok = self.gp_l.params, True
+            for p, v in new_l.items():                       # would gp_l.set_param accept every value?  (gp.py setters)
+                l_ok = l_ok and p in names and ((v >= 0) if p == "s" else (v > 0))
+                if l_ok:
+                    trial_l[names.index(p)] = v
+            # one device pass under (new gp_log_l parameters, the gp_l parameters the reference would have at log_lh time)
+            model = self._refresh_device(self.gp_log_l.params, trial_l if l_ok else self.gp_l.params, check_max=True)
+            if model.status not in (_lib.SETUP_OK, _lib.SETUP_KL_NOTPD):
+                return -np.inf                               # LinAlgError of bq.py:945-947 / gp_log_l.Kxx: gp_l untouched
+            self._retarget_gp_l(model.l_c)                   # bq.py:949-957
             try:
-                llh = self.gp_log_l.log_lh + self.gp_l.log_lh
-            except (ValueError, np.linalg.LinAlgError):
+                self._set_gp_l_params(new_l)                 # bq.py:959-965
+            except ValueError:
                 return -np.inf
-            return llh
+            if model.status != _lib.SETUP_OK:
+                return -np.inf                               # gp_l.Kxx not positive definite: gp_l.log_lh is -inf
+            return model.log_lh
         return f
 
     def _current_params(self, params):
@@ -516,9 +575,15 @@ class BQ(object):
         mean (bq.py:659-681).  Like the reference, ties within ``np.isclose`` of the minimum are
         broken with ``np.random.choice``; ``deterministic=True`` returns the first minimiser instead."""
         x_a = self._check_x_a(x_a)
-        state = deepcopy(self.__getstate__())
-        hypers_tl, hypers_l = self.sample_hypers(params, n=n, nburn=1)
-        self.__setstate__(state)
+        # the reference deep-copies the whole pickled state around the sampling (bq.py:622, :655); all that the sampler
+        # can change are the two parameter vectors, the candidate values they imply and the jitter records
+        saved = (self.gp_log_l.params, self.gp_l.params, self.l_c, self.gp_log_l.jitter.copy(), self.gp_l.jitter.copy())
+        try:
+            hypers_tl, hypers_l = self.sample_hypers(params, n=n, nburn=1)
+        finally:
+            self.gp_log_l.params, self.gp_l.params = saved[0], saved[1]
+            self._retarget_gp_l(saved[2])
+            self.gp_log_l.jitter[:], self.gp_l.jitter[:] = saved[3], saved[4]
         loss_d, batch = self.marginal_loss(x_a, hypers_tl, hypers_l, params)
         try:
             if deterministic:
@@ -553,18 +618,21 @@ class BQ(object):
         self.init(self.gp_log_l.params, self.gp_l.params)
 
     # ------------------------------------------------------------------ parameter setters
+    def _retarget_gp_l(self, l_c):
+        """bq.py:949-957: new candidate values, gp_l retargeted at (x_sc, l_sc), jitter cleared."""
+        self.l_c = l_c
+        self.l_sc = np.array(np.concatenate([self.l_s, self.l_c]))
+        self.gp_l.x = self.x_sc
+        self.gp_l.y = self.l_sc
+        self.gp_l.jitter.fill(0)
+
     def _set_gp_log_l_params(self, params):
         """bq.py:933-957: set parameters of the GP over log l, recompute the candidate values
         l_c = exp(mean(x_c)) (on device, with the "GP mean is too large" guard) and retarget gp_l."""
         for p, v in params.items():
             self.gp_log_l.set_param(p, v)
         self.gp_log_l.jitter.fill(0)
-        model = self._build_device_model(self.gp_log_l.params, self.gp_l.params, check_max=True)
-        self.l_c = model.l_c
-        self.l_sc = np.array(np.concatenate([self.l_s, self.l_c]))
-        self.gp_l.x = self.x_sc
-        self.gp_l.y = self.l_sc
-        self.gp_l.jitter.fill(0)
+        self._retarget_gp_l(self._log_l_values(self.gp_log_l.params, self.gp_l.params, check_max=True))
 
     def _set_gp_l_params(self, params):
         """bq.py:959-965."""
@@ -573,12 +641,28 @@ class BQ(object):
         self.gp_l.jitter.fill(0)
 
     # ------------------------------------------------------------------ approximation grid (state only)
+    def _approx(self):
+        if not self.initialized and self.gp_l is None:
+            return None, None
+        if self._approx_cache is None:
+            x = np.linspace(self._approx_spec[0], self._approx_spec[1], 1000)
+            self._approx_cache = (x, self._make_approx_px(x))
+        return self._approx_cache
+
+    def _approx_bound(self, side):
+        if self.options["wrapped"]:
+            return side * np.pi * self.gp_log_l.K.p
+        return (self.x_sc.min() - self.gp_log_l.K.w) if side < 0 else (self.x_sc.max() + self.gp_log_l.K.w)
+
+    _approx_x = property(lambda self: self._approx()[0])
+    _approx_px = property(lambda self: self._approx()[1])
+
     def _make_approx_x(self, xmin=None, xmax=None, n=1000):
         """bq.py:993-1006 (kept because the grid is part of the pickled state)."""
         if xmin is None:
-            xmin = -np.pi * self.gp_log_l.K.p if self.options["wrapped"] else self.x_sc.min() - self.gp_log_l.K.w
+            xmin = self._approx_bound(-1)
         if xmax is None:
-            xmax = np.pi * self.gp_log_l.K.p if self.options["wrapped"] else self.x_sc.max() + self.gp_log_l.K.w
+            xmax = self._approx_bound(+1)
         return np.linspace(xmin, xmax, n)
 
     def _make_approx_px(self, x=None):
@@ -701,12 +785,12 @@ class BQ(object):
             self.nsc = self.x_sc.shape[0]
             self.x_c, self.l_c = self.x_sc[self.ns:], self.l_sc[self.ns:]
             self.nc = self.nsc - self.ns
-            self._approx_x, self._approx_px = state["_approx_x"], state["_approx_px"]
+            self._approx_cache = (state["_approx_x"], state["_approx_px"])
         else:
             self.gp_log_l = self.gp_l = None
             self.x_c = self.l_c = self.nc = None
             self.x_sc = self.l_sc = self.nsc = None
-            self._approx_x = self._approx_px = None
+            self._approx_cache = None
 
     def __copy__(self):
         new = type(self).__new__(type(self))

@@ -83,7 +83,7 @@ struct bqb_batch {
     int *h_cta_flags = nullptr;        // pinned, mapped: per-CTA status words of the zero-copy scoring launch
     double *d_red_val = nullptr;
     long long *d_red_idx = nullptr;
-    std::vector<double> h_hdr;
+    std::vector<double> h_hdr, h_lc;   // per-instance headers and l_c rows fetched by the last setup
     bool ready = false;
     int ndb_max = 1;
     int nb_max = 0, nrow_max = 0;      // largest ceil(ns / 8) and nc + 2 over the instances (sizes the kernels' shared memory)
@@ -128,7 +128,9 @@ int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     for (int j = 0; j < 2048; ++j) tab[j] = (double)exp2l((long double)j / 2048);
     for (int j = 0; j < 512; ++j) tab[2048 + j] = (double)exp2l((long double)j / 512);
     CU(cudaMemcpy(b->d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
-    b->n_cap = ((ns_max + 7) & ~7) + NC_MAX;     // leading dimension of the setup scratch matrices
+    // leading dimension of the setup scratch matrices: sized for the capacity CLASS, because bqb_batch_stage and
+    // bqb_batch_add_observations let ns grow up to bqb_batch_capacity(), not just up to ns_max
+    b->n_cap = cap + NC_MAX;
     b->work_stride = 4 * (size_t)b->n_cap * b->n_cap + 32 * (size_t)b->n_cap;
     b->work_inst = n_inst < 2048 ? n_inst : 2048;
     CU(cudaMalloc(&b->d_work, sizeof(double) * b->work_stride * b->work_inst));
@@ -143,6 +145,7 @@ int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     CU(cudaMalloc(&b->d_red_idx, sizeof(long long) * 4096));
     if (getenv("BQB_DENSE") && atoi(getenv("BQB_DENSE"))) b->cut_arg = INFINITY;
     b->h_hdr.resize((size_t)n_inst * H_COUNT);
+    b->h_lc.resize((size_t)n_inst * NC_MAX);
     b->h_ns.resize(n_inst);
     b->h_nc.resize(n_inst);
     *out = b;
@@ -178,6 +181,8 @@ static int run_setup(bqb_batch *b, int check_max, cudaStream_t s) {
     // headers back to the host (Z_mean, Z_var, log_lh, status)
     CU(cudaMemcpy2DAsync(b->h_hdr.data(), sizeof(double) * H_COUNT, b->d_models, sizeof(double) * b->lay.total,
                          sizeof(double) * H_COUNT, B, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpy2DAsync(b->h_lc.data(), sizeof(double) * NC_MAX, b->d_models + b->lay.off_lc, sizeof(double) * b->lay.total,
+                         sizeof(double) * NC_MAX, B, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(b->h_ns.data(), b->d_ns, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(b->h_nc.data(), b->d_nc, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -228,6 +233,17 @@ int bqb_batch_setup(bqb_batch *b, const int *ns, const int *nc, const double *x_
     CU(cudaMemcpyAsync(b->d_nc, nc, sizeof(int) * B, cudaMemcpyHostToDevice, s));
     if (x_c) CU(cudaMemcpyAsync(b->d_xc, x_c, sizeof(double) * (size_t)B * NC_MAX, cudaMemcpyHostToDevice, s));
     return run_setup(b, check_max, s);
+}
+
+int bqb_batch_set_hypers(bqb_batch *b, const double *hyp, void *stream) {
+    if (!b || !hyp) return fail(BQB_EINVAL, "bqb_batch_set_hypers: null argument");
+    if (!b->staged) return fail(BQB_ESTATE, "bqb_batch_set_hypers: nothing staged (bqb_batch_stage / bqb_batch_setup first)");
+    CU(cudaSetDevice(b->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(b->d_hyp, hyp, sizeof(double) * (size_t)b->n_inst * 6, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));          // the host array may be pageable and is free to change after this call
+    b->ready = false;
+    return 0;
 }
 
 int bqb_batch_setup_device(bqb_batch *b, int check_max, void *stream) {
@@ -324,11 +340,7 @@ int bqb_batch_info(bqb_batch *b, double *Z_mean, double *Z_var, double *log_lh, 
         if (log_lh) log_lh[i] = h[H_LOGLH];
         if (status) status[i] = (int)h[H_STATUS];
     }
-    if (l_c) {
-        CU(cudaSetDevice(b->device));
-        CU(cudaMemcpy2D(l_c, sizeof(double) * NC_MAX, b->d_models + b->lay.off_lc, sizeof(double) * b->lay.total,
-                        sizeof(double) * NC_MAX, b->n_inst, cudaMemcpyDeviceToHost));
-    }
+    if (l_c) memcpy(l_c, b->h_lc.data(), sizeof(double) * b->h_lc.size());
     return 0;
 }
 

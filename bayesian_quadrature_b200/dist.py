@@ -165,6 +165,20 @@ def all_gather_scores(local, n_total, block=0):
     return full
 
 
+def raise_together(err, device=None):
+    """Collective error check: every rank calls it with its own exception (or None) BEFORE entering the data
+    collectives; if any rank failed, all ranks raise (the failing ones their own exception), so that a setup failure
+    or a bad-score flag on one shard cannot leave the other ranks waiting in an all-gather / all-reduce."""
+    W, rank = world()
+    if W > 1:
+        flag = torch.tensor([1.0 if err is not None else 0.0], dtype=torch.float64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if flag.item() and err is None:
+            err = RuntimeError("sharded call aborted: another rank failed (see its exception)")
+    if err is not None:
+        raise err
+
+
 def all_reduce_loss(partial_sum, n_samples_total):
     """C4 sharded by hyper-parameter sample: every rank holds the SUM of -esm over its samples;
     the marginal loss is the all-reduced sum divided by the total number of samples."""
@@ -210,29 +224,35 @@ def choose_next_sharded(bq, x_a, hypers_tl, hypers_l, params, shard="points"):
     x_a = np.ascontiguousarray(x_a, dtype=np.float64)
     n = len(hypers_tl)
     dev = torch.device("cuda", bq.device)
+    if shard not in ("points", "samples"):
+        raise ValueError("shard must be 'points' or 'samples'")
+    err = None
     if shard == "points":
-        mine = interleaved_indices(x_a.shape[0], W, rank)
-        if mine.size:
-            loss, batch = bq.marginal_loss(x_a[mine], hypers_tl, hypers_l, params)
-            mn, idx = batch.argmin_device(loss)         # first local minimiser = smallest global index among this rank's
-            batch.close()
-            idx = interleaved_global(idx, W, rank)
-        else:
-            mn, idx = float("inf"), 0
+        mn, idx = float("inf"), 0
+        try:
+            mine = interleaved_indices(x_a.shape[0], W, rank)
+            if mine.size:
+                loss, batch = bq.marginal_loss(x_a[mine], hypers_tl, hypers_l, params)
+                try:
+                    mn, idx = batch.argmin_device(loss)     # first local minimiser = smallest global index among this rank's
+                finally:
+                    batch.close()
+                idx = interleaved_global(idx, W, rank)
+        except Exception as e:                              # noqa: BLE001 -- re-raised on every rank below
+            err = e
+        raise_together(err, device=dev)
         mn, idx = all_argmin(mn, idx, 0, device=dev)
-    elif shard == "samples":
+    else:
         lo, hi = shard_bounds(n, W, rank)
         total = torch.zeros(x_a.shape[0], dtype=torch.float64, device=dev)
-        batch = None
-        if hi > lo:
-            loss, batch = bq.marginal_loss(x_a, hypers_tl[lo:hi], hypers_l[lo:hi], params)
-            total += loss * (hi - lo)
+        try:
+            if hi > lo:
+                loss, batch = bq.marginal_loss(x_a, hypers_tl[lo:hi], hypers_l[lo:hi], params)
+                batch.close()
+                total += loss * (hi - lo)
+        except Exception as e:                              # noqa: BLE001
+            err = e
+        raise_together(err, device=dev)
         loss = all_reduce_loss(total, n)
-        if batch is None:
-            from . import _lib
-            batch = _lib.Batch(1, 1, device=bq.device)
-        mn, idx = batch.argmin_device(loss)
-        batch.close()
-    else:
-        raise ValueError("shard must be 'points' or 'samples'")
+        mn, idx = bq._device_model().batch.argmin_device(loss)      # the object's own resident batch: any rank, even one without samples
     return x_a[idx], idx, mn

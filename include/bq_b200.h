@@ -90,6 +90,11 @@ int bqb_batch_setup(bqb_batch *b, const int *ns, const int *nc, const double *x_
  * stored with the batch's own row stride bqb_batch_capacity(), so observations can be appended in place). */
 int bqb_batch_stage(bqb_batch *b, const int *ns, const double *x_s, const double *l_s, int in_stride,
                     const double *hyp, const double *prior, void *stream);
+/* Replaces the hyper-parameters hyp [n_inst][6] (HOST pointer) of a staged batch and nothing else: the next
+ * bqb_batch_setup_device refactorises the same observations and candidates under them.  This is what one evaluation of
+ * the hyper-parameter log-density costs (BQ._make_llh_params, bq.py:533-552: _set_gp_log_l_params :933-957 +
+ * _set_gp_l_params :959-965 + gp.log_lh) -- no buffer is reallocated, nothing but 48 bytes per instance is uploaded. */
+int bqb_batch_set_hypers(bqb_batch *b, const double *hyp, void *stream);
 /* The setup half: runs the setup kernel on whatever is staged on the device (after bqb_batch_stage /
  * bqb_batch_add_observations / bqb_batch_draw_candidates).  Stands in for BQ.init (bq.py:132-171) of every
  * instance.  Synchronises `stream`. */

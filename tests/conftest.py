@@ -37,6 +37,21 @@ def assert_close(got, want, what="", rtol=RTOL, atol=ATOL):
             what, int(bad.sum()), bad.size, rtol, atol, i, got.flat[i], want.flat[i]))
 
 
+def truth_err(got, truth):
+    fin = np.isfinite(truth) & (truth != 0)
+    assert (np.isinf(got) == np.isinf(truth)).all()
+    return np.abs(got[fin] - truth[fin]) / np.abs(truth[fin])
+
+
+def truth_bound(g):
+    """Relative error allowed against the multi-precision truth: the parity tolerance, twice what the reference itself
+    shows on the fixture, or a tenth of the a-priori forward-error scale cond * eps of a backward-stable solve -- the
+    errors of two stable float64 algorithms on one ill-conditioned problem are unrelated samples from that scale (the C
+    restatement is 12x the reference on fixture d and 2x better on b), so the reference's sample alone is no bound."""
+    cond = max(float(g["cond_K_tl"]), float(g["cond_K_l"]))
+    return max(RTOL, 2 * float(g["ref_err_esm"]), 0.1 * cond * np.finfo(np.float64).eps)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle as orc
