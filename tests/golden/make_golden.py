@@ -256,13 +256,36 @@ def main_edge():
     # ---- 8. sampler and choose_next under a fixed numpy seed (bq.py:565-598, :659-681; util_c.pyx:25-148).  Two runs from the
     #      same seed: one calls choose_next, the other sample_hypers at the same RNG position (marginalize's shape probe,
     #      bq.py:626-633, consumes no random numbers), so the fixture holds the sampled sets AND the point chosen from them.
+    #      max_cond: the worst condition number among the proposals the chain evaluated.  The slice sampler's window
+    #      (2 * nparam, bq.py:567) takes it into regions where K_tl is numerically singular and the log likelihood is
+    #      rounding noise; there an accept / reject decision of the reference is not a property of the model and no
+    #      other implementation can be asked to repeat it.
+    def traced(bq):
+        log = []
+        orig = bq._make_llh_params
+
+        def patched(params):
+            f = orig(params)
+
+            def g(x):
+                v = f(x)
+                if np.isfinite(v):
+                    log.append(max(np.linalg.cond(bq.gp_log_l.Kxx), np.linalg.cond(bq.gp_l.Kxx)))
+                return v
+            return g
+        bq._make_llh_params = patched
+        return log
+
     for name, make, x_a, n in (
             ("choose_fixture", lambda: fixture_bq(BQ, gp, (15, 2, 0.), (0.2, 1.3, 0.)), np.linspace(-10, 10, 200), 20),
-            ("choose_c2", lambda: synth_bq(BQ, gp, 64, synthetic.PARAMS_TL, synthetic.PARAMS_L)[0], synthetic.query_grid(64, 1500), 6)):
+            # seed 8738: the first seed >= 8728 whose ns = 64 chain keeps every evaluated proposal below cond 1e9 (with 8728
+            # itself the chain evaluates proposals of cond 2.9e15, 27 of the 32 seeds 8728..8759 go beyond 1e13)
+            ("choose_c2", lambda: synth_bq(BQ, gp, 64, synthetic.PARAMS_TL, synthetic.PARAMS_L, seed=8738)[0],
+             synthetic.query_grid(64, 1500), 6)):
         bq = make()
         chosen = bq.choose_next(x_a, n=n, params=["h", "w"])
-        state_after = np.random.get_state()[1][:4].copy()
         bq = make()
+        log = traced(bq)
         h_tl, h_l = bq.sample_hypers(["h", "w"], n=n, nburn=1)
         # the marginal loss and tie set those samples give (bq.py:660-665), for diagnosis when the chosen point differs
         bq = make()
@@ -274,19 +297,22 @@ def main_edge():
         loss = (-esm).mean(axis=0)
         close = np.nonzero(np.isclose(loss, loss.min()))[0]
         np.savez(os.path.join(OUT, name + ".npz"), x_s=bq.x_s, l_s=bq.l_s, x_c=bq.x_c, x_a=x_a, n=n, chosen=chosen,
-                 hypers_tl=h_tl, hypers_l=h_l, loss=loss, tie_set=close, ns=bq.ns)
-        print("%s: chosen %.6f, %d samples, tie set of %d points, argmin %d" % (name, chosen, n, close.size, int(np.argmin(loss))))
+                 hypers_tl=h_tl, hypers_l=h_l, loss=loss, tie_set=close, ns=bq.ns, max_cond=max(log), n_eval=len(log))
+        print("%s: chosen %.6f, %d samples, tie set of %d points, argmin %d, max cond over %d evaluated proposals %.3g" % (
+            name, chosen, n, close.size, int(np.argmin(loss)), len(log), max(log)))
 
     # ---- 9. sample_hypers from several seeds on the ns = 64 workload (a proposal whose K_l is not positive
     #      definite must not poison the following evaluations)
-    seeds = np.array([1, 2, 3, 4, 5, 6])
-    out_tl, out_l = [], []
+    seeds = np.array([1, 2, 3, 4, 5, 6, 8738, 8743])
+    out_tl, out_l, conds = [], [], []
     for sd in seeds:
         bq, _ = synth_bq(BQ, gp, 64, synthetic.PARAMS_TL, synthetic.PARAMS_L, seed=int(sd))
+        log = traced(bq)
         a, b = bq.sample_hypers(["h", "w"], n=4, nburn=2)
-        out_tl.append(a); out_l.append(b)
-    np.savez(os.path.join(OUT, "sample_hypers_c2.npz"), seeds=seeds, hypers_tl=np.array(out_tl), hypers_l=np.array(out_l))
-    print("sample_hypers_c2: %d seeds x 4 samples" % seeds.size)
+        out_tl.append(a); out_l.append(b); conds.append(max(log))
+    np.savez(os.path.join(OUT, "sample_hypers_c2.npz"), seeds=seeds, hypers_tl=np.array(out_tl), hypers_l=np.array(out_l),
+             max_cond=np.array(conds))
+    print("sample_hypers_c2: %d seeds x 4 samples, max cond per seed %s" % (seeds.size, np.array(conds)))
 
 
 if __name__ == "__main__":
