@@ -575,12 +575,23 @@ __device__ __forceinline__ unsigned count_ksteps(typename KMask<KS>::type mask, 
 
 // Lower-triangular pass with shared-memory resident operands: q += (rows of (A . B))^2.
 // ROLLED = false unrolls the row-block loop as well (exact trip counts, no early-exit branches).
-template <int KS, int NT, int TABN, bool ALIGN, bool ROLLED, bool REL>
+// Phase alignment of the ns <= 64 kernels: the warps of a barrier group enter the exp and the DMMA phases together
+// (DMMA / DFMA mixing on an SMSP costs pipe throughput).  ALIGN = 0: free running; 1: the whole CTA (__syncthreads);
+// N >= 2: groups of N consecutive warps on their own named barrier, so that the groups of a CTA drift apart and one
+// group's latency-bound phases (relevance masks, per-point tail) overlap the other groups' pipe-bound ones.
+template <int ALIGN>
+__device__ __forceinline__ void phase_sync() {
+    if constexpr (ALIGN == 1) __syncthreads();
+    else if constexpr (ALIGN > 1)
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 5) / ALIGN), "n"(ALIGN * 32) : "memory");
+}
+
+template <int KS, int NT, int TABN, int ALIGN, bool ROLLED, bool REL>
 __device__ __forceinline__ void tri_pass(const double *af_res, double (&bf)[KS][NT], double (&q0)[NT], double (&q1)[NT],
                                          int nb, int lane, typename KMask<KS>::type mask, int k0, const Wide<NT> &w) {
     using mask_t = typename KMask<KS>::type;
     static_assert(ROLLED || !REL, "the band-relative tile needs the rolled row-block loop");
-    if (ALIGN) __syncthreads();                                 // all warps of the CTA enter the DMMA phase together
+    phase_sync<ALIGN>();                                        // the warps of a barrier group enter the DMMA phase together
     if constexpr (ROLLED) {
         row_blocks_rolled<KS, NT, TABN, REL>(af_res + lane, 0, nb, bf, q0, q1, mask, k0, w);
     } else {
@@ -742,7 +753,7 @@ __device__ __forceinline__ void park_q(double (&q0)[NT], double (&q1)[NT], doubl
 // the same passes, but the tail returns the posterior mean of gp_l (BQ.l_mean, bq.py:177-200) in `esm` and the
 // posterior variance of gp_log_l (the factor of BQ.l_var, bq.py:202-231) in `em`: no shortcut, no jitter pattern.
 // BK > 0: band-relative register tile of BK k-steps (see row_blocks_rolled); BK = 0: the tile covers all KS k-steps.
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, int BK, int MODE>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, int ALIGN, bool ROLLED, int BK, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a) {
     constexpr bool EPI = MODE == 1, PRED = MODE == 2;
     constexpr bool REL = BK > 0;
@@ -753,7 +764,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
     // of 8-14 k-steps wastes fewer exponentials on groups of 4 than on groups of 8
     constexpr int GKK = REL ? BQB_REL_GK : exp_group<NT>();
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
-    constexpr bool LOCKSTEP = STREAM || ALIGN;              // warps must keep reaching the CTA barriers
+    constexpr bool LOCKSTEP = STREAM || ALIGN != 0;         // warps must keep reaching the barriers
+    static_assert(ALIGN <= 1 || WARPS % ALIGN == 0, "barrier groups of whole warps");
     constexpr int THREADS = WARPS * 32;
     constexpr int SUB = 4 / NT;                             // sub-tiles of 8 NT points per 32-point super-tile
     extern __shared__ __align__(16) double smem[];
@@ -952,7 +964,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
 
                 if (do_l) {
                     // ---- K_l: cross-kernel fragments, triangular rows then the dense candidate / g rows
-                    if (ALIGN) __syncthreads();          // all warps enter the exp phase together (DMMA / DFMA mixing costs pipe throughput)
+                    phase_sync<ALIGN>();                 // enter the exp phase together (DMMA / DFMA mixing costs pipe throughput)
                     // relative mask of the register tile (empty on the wide path, which generates its windows itself)
                     const rmask_t rm_l = REL ? (wd_l.on ? (rmask_t)0 : (rmask_t)(mask >> k0_l)) : (rmask_t)mask;
                     gen_exps<KB, NT, TABN, false, GKK>(bf, x, Cl, dmax_l, rm_l, kq, s_xs + 4 * k0_l, s_atl, s_tab, tm, tol2_hi, close);
@@ -993,7 +1005,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) bq_score_kernel(ScoreArgs a)
                     // ---- K_tl: fragments, gp_log_l.mean and the isclose test
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) { q0[nt] = q1[nt] = 0.0; }
-                    if (ALIGN) __syncthreads();
+                    phase_sync<ALIGN>();
                     mask = mask_tl;
                     const rmask_t rm_tl = REL ? (wd_tl.on ? (rmask_t)0 : (rmask_t)(mask >> k0_tl)) : (rmask_t)mask;
                     if (REL && wd_tl.on) {                   // wide band: gp_log_l.mean and the isclose pre-filter, window by window
@@ -1207,7 +1219,7 @@ static size_t smem_need(const ScoreArgs &a, int chunk_frags) {
            SMEM_STATIC_MISC;
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, int BK, int MODE>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, int ALIGN, bool ROLLED, int BK, int MODE>
 static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     using SM = ScoreSmem<KS, NT, WARPS, STREAM, TABN>;
     a.chunk_frags = 0;
@@ -1233,7 +1245,7 @@ static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
-template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, bool ALIGN, bool ROLLED, int BK = 0>
+template <int KS, int NT, int WARPS, int MINB, bool STREAM, int TABN, int ALIGN, bool ROLLED, int BK = 0>
 static cudaError_t launch_cfg(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x) {
     // the fused expected-variance / argmin epilogue is a separate instantiation so that plain scoring keeps its registers
     if (a.predict) return launch_cfg2<KS, NT, WARPS, MINB, STREAM, TABN, ALIGN, ROLLED, BK, 2>(a, n_inst, sm_count, stream, grid_x);
@@ -1313,7 +1325,21 @@ BQB_LAUNCH_DECL(16) { return launch_cfg<4, 2, 8, 2, false, 2048, false, false>(a
 #elif BQB_SCORE_CLASS == 64
 // (rolled pairs, free-running warps and 4 x 4-warp CTAs were all slower with band skipping: 0.31 / 0.37 / 0.34 / 0.47 ms vs 0.28)
 // (the band-relative loops <16, NT=1, 16 warps, BK=16> measured 0.364 ms against 0.286: at ns = 64 the band is most of the tile)
-BQB_LAUNCH_DECL(64) { return launch_cfg<16, 2, 8, 2, false, 2048, true, false>(a, n_inst, sm_count, stream, grid_x); }
+cudaError_t launch_score_team_64(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x);
+// Round-2 experiments on this class (profiles/score64_experiments_r02.md; 10^6 points, ns = 64, ms): this kernel 0.285; free
+// running (ALIGN = 0) 0.335; barrier groups of 4 / 2 warps (ALIGN = 4 / 2) 0.284 / 0.293; rolled row-block loop 0.333; NT = 1
+// with three CTAs per SM 0.43-0.57; 512-entry table 0.288; one CTA per SM 0.422 (=> T = 0.149 + 2.18 / warps: latency bound);
+// the team kernel of bq_score_team.cu (cross-kernel tile shared by four warps through shared memory, 20-32 warps per SM)
+// 0.298-0.333.  BQB_TEAM=1 selects the team kernel (kept as a cross-check of this one in the tests).
+BQB_LAUNCH_DECL(64) {
+    const char *env = getenv("BQB_TEAM");                  // read per launch (tests switch it between calls)
+    const int use_team = env ? atoi(env) : 0;
+    if (use_team) {
+        const cudaError_t e = launch_score_team_64(a, n_inst, sm_count, stream, grid_x);
+        if (e != cudaErrorInvalidConfiguration) return e;
+    }
+    return launch_cfg<16, 2, 8, 2, false, 2048, 1, false>(a, n_inst, sm_count, stream, grid_x);
+}
 #elif BQB_SCORE_CLASS == 128
 BQB_LAUNCH_REL_DECL(128);
 BQB_LAUNCH_DECL(128) {

@@ -571,3 +571,57 @@ def test_conditioning_sweep_against_truth(lib, tag):
     if tag == "a":      # well conditioned: plain parity with the reference as well
         assert_close(esm[0], g["esm"], "esm")
     b.close()
+
+
+@pytest.mark.parametrize("ns,nc", [(64, 4), (40, 2), (17, 0), (64, 6)])
+def test_team_kernel_of_the_64_class_agrees(lib, oracle, ns, nc, monkeypatch):
+    """The 64-observation class has a second scoring kernel (bq_score_team.cu, BQB_TEAM=1: four warps share one cross-kernel
+    tile through shared memory, contiguous k-step bands at exact granularity).  Same sums in a different order: scores agree
+    with the default kernel to ~1e-12 and with the oracle to the parity tolerance, statuses exactly -- grid, scattered
+    points, shortcut / jitter-pattern / invalid points, dense cut-off, fused expected-variance epilogue and prediction mode."""
+    import torch
+    from bayesian_quadrature_b200 import synthetic
+    rs = np.random.RandomState(ns)
+    x_s, l_s = synthetic.observations(ns)
+    x_c = np.sort(np.concatenate([x_s.max() + 1.1 + 1.3 * np.arange(nc // 2), x_s.min() - 0.9 - 1.2 * np.arange(nc - nc // 2)]))
+    opt = synthetic.options(ns)
+    b = lib.Batch(1, ns)
+    info = b.setup([ns], [nc], x_s[None], l_s[None], x_c[None] if nc else np.zeros((1, 0)),
+                   np.array([synthetic.PARAMS_TL + synthetic.PARAMS_L]), np.array([[opt["x_mean"], opt["x_var"], 0.5]]))
+    assert info["status"][0] == 0
+    m = oracle.OracleModel(x_s, l_s, x_c, synthetic.PARAMS_TL, synthetic.PARAMS_L, opt["x_mean"], opt["x_var"], 0.5)
+    grid = synthetic.query_grid(ns, 20011)
+    pts = np.concatenate([rs.uniform(grid[0], grid[-1], 3001), x_s[:7], x_s[:7] + 0.9e-4, x_c, x_c + 0.3, [np.nan, 1e7, -np.inf]])
+    for cut in (72.0, float("inf")):
+        b.set_cutoff(cut)
+        for name, x_a in (("grid", grid), ("points", pts)):
+            monkeypatch.setenv("BQB_TEAM", "0")
+            e0, m0, s0 = b.score_host(x_a)
+            ev0, f0 = b.expected_var_host(x_a)
+            p0 = b.predict_host(x_a[np.isfinite(x_a)])
+            monkeypatch.setenv("BQB_TEAM", "1")
+            e1, m1, s1 = b.score_host(x_a)
+            ev1, f1 = b.expected_var_host(x_a)
+            p1 = b.predict_host(x_a[np.isfinite(x_a)])
+            tag = "%s ns=%d nc=%d cut=%g" % (name, ns, nc, cut)
+            assert (s0 == s1).all() and f0 == f1, tag
+            ok = np.isfinite(x_a)
+            assert_close(e1[0][ok], e0[0][ok], "esm " + tag, rtol=1e-11, atol=1e-300)
+            assert_close(m1[0][ok], m0[0][ok], "em " + tag, rtol=1e-11, atol=1e-300)
+            assert_close(ev1[ok], ev0[ok], "ev " + tag, rtol=1e-11, atol=1e-18)
+            assert_close(p1[0][0], p0[0][0], "l_mean " + tag, rtol=1e-11, atol=1e-300)
+            assert_close(p1[1][0], p0[1][0], "v_log_l " + tag, rtol=1e-9, atol=1e-12)
+            if cut == 72.0:
+                o_esm, o_em, o_st = m.esm_and_em(x_a)
+                assert ((s1[0] & 3) == (o_st & 3)).all()
+                assert_close(e1[0][ok], o_esm[ok], "esm vs oracle " + tag)
+    # device entry point with the fused epilogue: same (min, first index)
+    x_d = torch.from_numpy(grid).cuda()
+    esm = torch.empty_like(x_d); ev = torch.empty_like(x_d); pair = torch.empty(2, dtype=torch.float64, device="cuda")
+    res = []
+    for t in ("0", "1"):
+        monkeypatch.setenv("BQB_TEAM", t)
+        b.choose_step_device(x_d, esm, ev, pair)
+        res.append(pair.cpu().numpy().copy())
+    assert res[0][1] == res[1][1] and abs(res[0][0] - res[1][0]) <= 1e-11 * abs(res[0][0])
+    b.close()
