@@ -42,6 +42,8 @@ SYMBOLS = {
     "bqb_batch_capacity": (ctypes.c_int, [_vp]),
     "bqb_batch_info": (ctypes.c_int, [_vp, _dp, _dp, _dp, _ip, _dp]),
     "bqb_score_device": (ctypes.c_int, [_vp, _vp, _ll, ctypes.c_int, _vp, _vp, _vp, _ll, _vp, _vp]),
+    "bqb_score_device_range": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _ll, ctypes.c_int, _vp, _vp, _vp, _ll, _vp, _vp]),
+    "bqb_sum_neg_accum_device": (ctypes.c_int, [_vp, _vp, _ll, ctypes.c_int, _ll, _vp, _vp]),
     "bqb_predict_device": (ctypes.c_int, [_vp, _vp, _ll, ctypes.c_int, _vp, _vp, _ll, _vp]),
     "bqb_predict_host": (ctypes.c_int, [_vp, _dp, _ll, ctypes.c_int, _dp, _dp]),
     "bqb_expected_var_host": (ctypes.c_int, [_vp, ctypes.c_int, _dp, ctypes.c_int, _dp, _ip]),
@@ -56,6 +58,7 @@ SYMBOLS = {
     "bqb_argmin_rows_device": (ctypes.c_int, [_vp, _vp, _ll, _ll, _vp, _vp, _vp]),
     "bqb_batch_set_cutoff": (ctypes.c_int, [_vp, ctypes.c_double]),
     "bqb_batch_set_presort": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "bqb_batch_set_zero_copy": (ctypes.c_int, [_vp, ctypes.c_int]),
     "bqb_batch_work_counter": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
     "bqb_launch_count": (ctypes.c_ulonglong, [_vp]),
     "bqb_model_doubles": (ctypes.c_int, [_vp]),
@@ -297,6 +300,22 @@ class Batch(object):
         _check(load().bqb_score_device(self._h, _ptr(x_a), stride, na, _ptr(esm), _ptr(em), _ptr(status), out_stride,
                                        _ptr(flags), _vp(stream) if stream else None), "bqb_score_device")
 
+    def score_device_range(self, inst0, n_inst, x_a, esm, em=None, status=None, flags=None, stream=None):
+        """score_device for instances [inst0, inst0 + n_inst); row 0 of esm / em / status / flags belongs to inst0."""
+        if x_a.dim() == 1:
+            stride, na = 0, x_a.shape[0]
+        else:
+            stride, na = x_a.stride(0), x_a.shape[1]
+        out_stride = esm.stride(0) if esm.dim() == 2 else esm.shape[0]
+        _check(load().bqb_score_device_range(self._h, int(inst0), int(n_inst), _ptr(x_a), stride, na, _ptr(esm), _ptr(em),
+                                             _ptr(status), out_stride, _ptr(flags), _vp(stream) if stream else None),
+               "bqb_score_device_range")
+
+    def sum_neg_accum_device(self, esm, n_rows, acc, stream=None):
+        """acc[p] += sum over the first n_rows rows of -esm[:, p], in row order (running form of mean_neg_device)."""
+        _check(load().bqb_sum_neg_accum_device(self._h, _ptr(esm), esm.stride(0), int(n_rows), esm.shape[1], _ptr(acc),
+                                               _vp(stream) if stream else None), "bqb_sum_neg_accum_device")
+
     def expected_var_device(self, inst, esm, out, stream=None):
         _check(load().bqb_expected_var_device(self._h, int(inst), _ptr(esm), esm.numel(), _ptr(out),
                                               _vp(stream) if stream else None), "bqb_expected_var_device")
@@ -339,6 +358,10 @@ class Batch(object):
     def set_presort(self, mode):
         """Pre-sort of unsorted query vectors in the host entry points: 0 never, 1 automatic (default), 2 always."""
         _check(load().bqb_batch_set_presort(self._h, int(mode)), "bqb_batch_set_presort")
+
+    def set_zero_copy(self, enable):
+        """Host entry points with page-locked arrays: in-place PCIe access by the kernel (True, default) or staged copies."""
+        _check(load().bqb_batch_set_zero_copy(self._h, int(bool(enable))), "bqb_batch_set_zero_copy")
 
     def work_counter(self, enable=True):
         """DMMA instructions executed since the last call (0 if the counter was off); (re)arms or disarms the counter."""

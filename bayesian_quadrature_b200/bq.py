@@ -493,11 +493,19 @@ class BQ(object):
         self.__setstate__(state)
         return values
 
-    def marginal_loss(self, x_a, hypers_tl, hypers_l, params):
+    #: score buffer of the chunked marginal loss: [chunk, na] doubles of at most this many bytes (stays L2-resident on a B200)
+    LOSS_CHUNK_BYTES = 64 << 20
+
+    def marginal_loss(self, x_a, hypers_tl, hypers_l, params, reduce="mean"):
         """Marginal loss of choose_next — the mean over hyper-parameter samples of
         ``-expected_squared_mean(x_a)`` (bq.py:660-662) — for ALL samples in one device batch.
         Each sample goes through the semantics of ``_set_gp_log_l_params`` / ``_set_gp_l_params``
-        (bq.py:933-965: l_c recomputed, "GP mean is too large" guard)."""
+        (bq.py:933-965: l_c recomputed, "GP mean is too large" guard).
+
+        The samples are scored chunk by chunk through one [chunk, na] buffer and accumulated in sample order
+        (``bqb_sum_neg_accum_device``): the additions of ``values[0].mean(axis=0)`` in the same order, without the
+        [n, na] matrix (819 MB at 1024 samples x 10^5 points).  ``reduce="sum"`` returns the sum over the samples
+        instead of the mean (what a rank contributes when the samples are sharded across GPUs)."""
         import torch
         x_a = self._check_x_a(x_a)
         n = len(hypers_tl)
@@ -523,19 +531,32 @@ class BQ(object):
                 _raise_setup(info["status"][bad[0]])
             dev = torch.device("cuda", self.device)
             x_d = torch.from_numpy(x_a).to(dev)
+            na = x_a.shape[0]
             # points in arbitrary order defeat the kernels' band skipping: score them in ascending order
             perm = None
-            if x_a.shape[0] >= 8192 and self.ns > 64 and not _looks_sorted(x_a):      # (pays from the ns <= 128 class up)
+            if na >= 8192 and self.ns > 64 and not _looks_sorted(x_a):      # (pays from the ns <= 128 class up)
                 x_d, perm = torch.sort(x_d)
-            loss = torch.zeros(x_a.shape[0], dtype=torch.float64, device=dev)
-            esm = torch.empty(n, x_a.shape[0], dtype=torch.float64, device=dev)
-            flags = torch.zeros(n, dtype=torch.int32, device=dev)
-            batch.score_device(x_d, esm, None, None, flags)
-            batch.mean_neg_device(esm, loss)
+            loss = torch.zeros(na, dtype=torch.float64, device=dev)
+            chunk = int(max(1, min(n, self.LOSS_CHUNK_BYTES // max(8 * na, 1))))
+            for c in (148, 74, 37):           # whole shares of the 148 SMs per instance: the launches fill exactly one wave
+                if n > c and chunk >= c:
+                    chunk = c
+                    break
+            esm = torch.empty(chunk, max(na, 1), dtype=torch.float64, device=dev)
+            flags = torch.zeros(chunk, dtype=torch.int32, device=dev)
+            seen = torch.zeros(chunk, dtype=torch.int32, device=dev)          # OR of the status bits, slot-wise over the chunks
+            for i0 in range(0, n, chunk):
+                cnt = min(chunk, n - i0)
+                batch.score_device_range(i0, cnt, x_d, esm, None, None, flags)
+                batch.sum_neg_accum_device(esm, cnt, loss)
+                seen[:cnt] |= flags[:cnt]
+            if reduce == "mean":
+                loss = loss / n                                                # bq.py:662
+            elif reduce != "sum":
+                raise ValueError("reduce must be 'mean' or 'sum'")
             if perm is not None:
                 loss = torch.empty_like(loss).scatter_(0, perm, loss)         # back to the caller's order
-            fl = int(np.bitwise_or.reduce(flags.cpu().numpy()))
-            if fl & (_lib.ST_ESM_BAD | _lib.ST_EM_BAD):
+            if int(np.bitwise_or.reduce(seen.cpu().numpy())) & (_lib.ST_ESM_BAD | _lib.ST_EM_BAD):
                 raise RuntimeError("invalid expected squared mean under a sampled hyper-parameter set")
             return loss, batch
         except Exception:

@@ -27,6 +27,8 @@ void launch_setup(const SetupArgs &a, int n_inst, cudaStream_t stream);
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x = nullptr);
 cudaError_t launch_argmin_partials(double *bv, long long *bi, int nblocks, long long offset, double *pair, cudaStream_t s);
 cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, long long na, double *loss, cudaStream_t s);
+cudaError_t launch_pack_info(const double *models, long long model_stride, int off_lc, int n_inst, double *out, cudaStream_t s);
+cudaError_t launch_sum_neg_accum(const double *esm, long long stride, int n_rows, long long na, double *acc, cudaStream_t s);
 cudaError_t launch_expected_var(const double *esm, long long na, double msm, double *out, cudaStream_t s);
 cudaError_t launch_argmin(const double *v, long long n, double *scratch_val, long long *scratch_idx, int sm_count,
                           cudaStream_t s);
@@ -68,6 +70,8 @@ struct bqb_batch {
     unsigned long long *d_work_ctr = nullptr;
     // pre-sort of query vectors that do not look sorted (bq_sort.cu): 0 never, 1 automatic (default), 2 always
     int presort = 1;
+    // host entry points with page-locked buffers: 1 = the kernel reads / writes them in place (zero copy, default), 0 = staged copies
+    int zero_copy = 1;
     double *d_xsorted = nullptr;
     int *d_perm = nullptr, *d_iota = nullptr;
     void *d_sort_tmp = nullptr;
@@ -84,6 +88,7 @@ struct bqb_batch {
     double *d_red_val = nullptr;
     long long *d_red_idx = nullptr;
     std::vector<double> h_hdr, h_lc;   // per-instance headers and l_c rows fetched by the last setup
+    double *d_info = nullptr, *h_info = nullptr;       // [n_inst][H_COUNT + NC_MAX] packed on the device / page-locked mirror
     bool ready = false;
     int ndb_max = 1;
     int nb_max = 0, nrow_max = 0;      // largest ceil(ns / 8) and nc + 2 over the instances (sizes the kernels' shared memory)
@@ -146,6 +151,8 @@ int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     if (getenv("BQB_DENSE") && atoi(getenv("BQB_DENSE"))) b->cut_arg = INFINITY;
     b->h_hdr.resize((size_t)n_inst * H_COUNT);
     b->h_lc.resize((size_t)n_inst * NC_MAX);
+    CU(cudaMalloc(&b->d_info, sizeof(double) * (size_t)n_inst * (H_COUNT + NC_MAX)));
+    CU(cudaMallocHost(&b->h_info, sizeof(double) * (size_t)n_inst * (H_COUNT + NC_MAX)));
     b->h_ns.resize(n_inst);
     b->h_nc.resize(n_inst);
     *out = b;
@@ -161,6 +168,8 @@ void bqb_batch_destroy(bqb_batch *b) {
     for (cudaStream_t st : b->pipe) if (st) cudaStreamDestroy(st);
     if (b->h_flags) cudaFreeHost(b->h_flags);
     if (b->h_cta_flags) cudaFreeHost(b->h_cta_flags);
+    if (b->d_info) cudaFree(b->d_info);
+    if (b->h_info) cudaFreeHost(b->h_info);
     delete b;
 }
 
@@ -178,14 +187,18 @@ static int run_setup(bqb_batch *b, int check_max, cudaStream_t s) {
         CU(cudaGetLastError());
         b->launches++;
     }
-    // headers back to the host (Z_mean, Z_var, log_lh, status)
-    CU(cudaMemcpy2DAsync(b->h_hdr.data(), sizeof(double) * H_COUNT, b->d_models, sizeof(double) * b->lay.total,
-                         sizeof(double) * H_COUNT, B, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpy2DAsync(b->h_lc.data(), sizeof(double) * NC_MAX, b->d_models + b->lay.off_lc, sizeof(double) * b->lay.total,
-                         sizeof(double) * NC_MAX, B, cudaMemcpyDeviceToHost, s));
+    // headers (Z_mean, Z_var, log_lh, status) and l_c rows back to the host: gathered on the device, one contiguous copy
+    constexpr int IW = H_COUNT + NC_MAX;
+    CU(launch_pack_info(b->d_models, b->lay.total, b->lay.off_lc, B, b->d_info, s));
+    b->launches++;
+    CU(cudaMemcpyAsync(b->h_info, b->d_info, sizeof(double) * (size_t)B * IW, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(b->h_ns.data(), b->d_ns, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(b->h_nc.data(), b->d_nc, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
+    for (int i = 0; i < B; ++i) {
+        memcpy(&b->h_hdr[(size_t)i * H_COUNT], b->h_info + (size_t)i * IW, sizeof(double) * H_COUNT);
+        memcpy(&b->h_lc[(size_t)i * NC_MAX], b->h_info + (size_t)i * IW + H_COUNT, sizeof(double) * NC_MAX);
+    }
     b->ndb_max = 1; b->nb_max = 1; b->nrow_max = 2;
     for (int i = 0; i < B; ++i) {
         const int d = (b->h_nc[i] + 2 + 7) / 8, nbk = (b->h_ns[i] + 7) / 8, nr = b->h_nc[i] + 2;
@@ -353,11 +366,18 @@ static int check_ready(bqb_batch *b, const char *who) {
 }
 
 static int score_device_impl(bqb_batch *b, const double *d_x_a, long long xa_stride, int na, double *d_esm, double *d_em,
-                             int *d_status, long long out_stride, int *d_flags, const int *d_perm, void *stream);
+                             int *d_status, long long out_stride, int *d_flags, const int *d_perm, void *stream, int first = 0,
+                             int count = -1);
 
 int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int na, double *d_esm, double *d_em,
                      int *d_status, long long out_stride, int *d_flags, void *stream) {
     return score_device_impl(b, d_x_a, xa_stride, na, d_esm, d_em, d_status, out_stride, d_flags, nullptr, stream);
+}
+
+int bqb_score_device_range(bqb_batch *b, int inst0, int n_inst, const double *d_x_a, long long xa_stride, int na, double *d_esm,
+                           double *d_em, int *d_status, long long out_stride, int *d_flags, void *stream) {
+    if (!b || inst0 < 0 || n_inst < 1 || inst0 + n_inst > b->n_inst) return fail(BQB_EINVAL, "bqb_score_device_range: bad instance range");
+    return score_device_impl(b, d_x_a, xa_stride, na, d_esm, d_em, d_status, out_stride, d_flags, nullptr, stream, inst0, n_inst);
 }
 
 // A query vector "looks sorted" if ~2000 evenly spaced samples are ascending at stride 1 and at the sampling stride.
@@ -403,22 +423,26 @@ static bool want_presort(const bqb_batch *b, const double *x, int n) {
     return b->ns_cap >= 128 && !looks_sorted(x, n);
 }
 
+// Instances [first, first + count) (count < 0: all).  The per-instance rows of x_a / esm / em / status / flags are relative
+// to `first` (row 0 belongs to instance `first`), so a caller can walk a large batch through one chunk-sized buffer.
 static int score_device_impl(bqb_batch *b, const double *d_x_a, long long xa_stride, int na, double *d_esm, double *d_em,
-                             int *d_status, long long out_stride, int *d_flags, const int *d_perm, void *stream) {
+                             int *d_status, long long out_stride, int *d_flags, const int *d_perm, void *stream, int first, int count) {
     int rc = check_ready(b, "bqb_score_device");
     if (rc) return rc;
     if (!d_x_a || !d_esm || na < 0 || out_stride < na) return fail(BQB_EINVAL, "bqb_score_device: bad arguments");
     if (na == 0) return 0;
+    if (count < 0) count = b->n_inst - first;
     CU(cudaSetDevice(b->device));
     ScoreArgs a;
     a.cut_arg = b->cut_arg; a.work = b->d_work_ctr; a.nb_max = b->nb_max; a.nrow_max = b->nrow_max;
-    a.models = b->d_models; a.lay = b->lay; a.x_a = d_x_a; a.xa_stride = xa_stride; a.na = na;
-    a.esm = d_esm; a.em = d_em; a.status = d_status; a.out_stride = out_stride; a.exp_tab = b->d_tab;
-    a.flags = d_flags; a.ndb_max = b->ndb_max; a.perm = d_perm;
-    if (d_flags) CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * b->n_inst, (cudaStream_t)stream));
+    a.models = b->d_models; a.lay = b->lay; a.x_a = d_x_a - (size_t)first * xa_stride; a.xa_stride = xa_stride; a.na = na;
+    a.esm = d_esm - (size_t)first * out_stride; a.em = d_em ? d_em - (size_t)first * out_stride : nullptr;
+    a.status = d_status ? d_status - (size_t)first * out_stride : nullptr; a.out_stride = out_stride; a.exp_tab = b->d_tab;
+    a.flags = d_flags ? d_flags - first : nullptr; a.ndb_max = b->ndb_max; a.perm = d_perm;
+    if (d_flags) CU(cudaMemsetAsync(d_flags, 0, sizeof(int) * count, (cudaStream_t)stream));
     // gridDim.y is limited to 65535
-    for (int i0 = 0; i0 < b->n_inst; i0 += 32768) {
-        const int cnt = (b->n_inst - i0 < 32768) ? b->n_inst - i0 : 32768;
+    for (int i0 = first; i0 < first + count; i0 += 32768) {
+        const int cnt = (first + count - i0 < 32768) ? first + count - i0 : 32768;
         a.inst0 = i0;
         CU(launch_score(a, cnt, b->sm_count, (cudaStream_t)stream));
         b->launches++;
@@ -531,7 +555,8 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
     if (inst < 0 || inst >= b->n_inst || !x_a || !out || na < 0) return fail(BQB_EINVAL, "bqb_expected_var_host: bad arguments");
     if (na == 0) { if (flags_out) *flags_out = 0; return 0; }
     CU(cudaSetDevice(b->device));
-    static const int zero_copy = getenv("BQB_ZERO_COPY") ? atoi(getenv("BQB_ZERO_COPY")) : 1;
+    static const int zero_copy_env = getenv("BQB_ZERO_COPY") ? atoi(getenv("BQB_ZERO_COPY")) : 1;
+    const int zero_copy = zero_copy_env && b->zero_copy;
     const bool presort = want_presort(b, x_a, na);
     void *dx = nullptr, *dout = nullptr;
     const bool in_mapped = !presort && zero_copy && mapped_host(x_a, &dx);      // a vector to be sorted is staged on the device
@@ -610,6 +635,15 @@ int bqb_mean_neg_device(bqb_batch *b, const double *d_esm, long long stride, lon
     if (!b || !d_esm || !d_loss || na < 0) return fail(BQB_EINVAL, "bqb_mean_neg_device: bad arguments");
     CU(cudaSetDevice(b->device));
     CU(launch_mean_neg(d_esm, stride, b->n_inst, na, d_loss, (cudaStream_t)stream));
+    b->launches++;
+    return 0;
+}
+
+int bqb_sum_neg_accum_device(bqb_batch *b, const double *d_esm, long long stride, int n_rows, long long na, double *d_acc, void *stream) {
+    if (!b || !d_esm || !d_acc || na < 0 || n_rows < 0 || stride < na) return fail(BQB_EINVAL, "bqb_sum_neg_accum_device: bad arguments");
+    if (na == 0 || n_rows == 0) return 0;
+    CU(cudaSetDevice(b->device));
+    CU(launch_sum_neg_accum(d_esm, stride, n_rows, na, d_acc, (cudaStream_t)stream));
     b->launches++;
     return 0;
 }
@@ -705,6 +739,12 @@ unsigned long long bqb_launch_count(bqb_batch *b) { return b ? b->launches : 0; 
 int bqb_batch_set_presort(bqb_batch *b, int mode) {
     if (!b || mode < 0 || mode > 2) return fail(BQB_EINVAL, "bqb_batch_set_presort: mode must be 0 (never), 1 (automatic) or 2 (always)");
     b->presort = mode;
+    return 0;
+}
+
+int bqb_batch_set_zero_copy(bqb_batch *b, int enable) {
+    if (!b) return fail(BQB_EINVAL, "bqb_batch_set_zero_copy: null batch");
+    b->zero_copy = enable ? 1 : 0;
     return 0;
 }
 

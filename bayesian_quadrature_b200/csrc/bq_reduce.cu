@@ -15,6 +15,17 @@ __global__ void mean_neg_kernel(const double *__restrict__ esm, long long stride
     }
 }
 
+// acc[p] += -esm[0][p] - esm[1][p] - ... in row order, starting from acc[p]: walking a batch of hyper-parameter samples
+// through a chunk-sized score buffer performs exactly the additions of mean_neg_kernel (and of numpy's mean(axis=0)), in the
+// same order, without ever holding the [n_samples, na] matrix (819 MB at BASELINE configs[3]).
+__global__ void sum_neg_accum_kernel(const double *__restrict__ esm, long long stride, int n_rows, long long na, double *__restrict__ acc) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < na; p += (long long)gridDim.x * blockDim.x) {
+        double s = acc[p];
+        for (int b = 0; b < n_rows; ++b) s += -esm[(size_t)b * stride + p];
+        acc[p] = s;
+    }
+}
+
 __global__ void expected_var_kernel(const double *__restrict__ esm, long long na, double msm, double *__restrict__ out) {
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < na; p += (long long)gridDim.x * blockDim.x)
         out[p] = msm - esm[p];
@@ -85,6 +96,23 @@ __global__ void argmin_rows_kernel(const double *__restrict__ v, long long strid
     }
 }
 
+// Per-instance setup results (header + l_c row) gathered into one contiguous [n_inst][H_COUNT + NC_MAX] array, so that they
+// reach the host in ONE copy (a strided cudaMemcpy2D of 16384 rows of 256 B costs a DMA descriptor per row)
+__global__ void pack_info_kernel(const double *__restrict__ models, long long model_stride, int off_lc, int n_inst, double *__restrict__ out) {
+    constexpr int W = H_COUNT + NC_MAX;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)n_inst * W; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / W;
+        const int j = (int)(e - i * W);
+        out[e] = models[i * model_stride + (j < H_COUNT ? j : off_lc + (j - H_COUNT))];
+    }
+}
+cudaError_t launch_pack_info(const double *models, long long model_stride, int off_lc, int n_inst, double *out, cudaStream_t s) {
+    const long long n = (long long)n_inst * (H_COUNT + NC_MAX);
+    const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    pack_info_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(models, model_stride, off_lc, n_inst, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_argmin_rows(const double *v, long long stride, long long n, int rows, double *mins, long long *idxs,
                                cudaStream_t s) {
     argmin_rows_kernel<<<rows, 256, 0, s>>>(v, stride, n, mins, idxs);
@@ -94,6 +122,12 @@ cudaError_t launch_argmin_rows(const double *v, long long stride, long long n, i
 cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, long long na, double *loss, cudaStream_t s) {
     const int blocks = (int)((na + 255) / 256 < 2368 ? (na + 255) / 256 : 2368);
     mean_neg_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(esm, stride, n_inst, na, loss);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sum_neg_accum(const double *esm, long long stride, int n_rows, long long na, double *acc, cudaStream_t s) {
+    const int blocks = (int)((na + 255) / 256 < 2368 ? (na + 255) / 256 : 2368);
+    sum_neg_accum_kernel<<<blocks > 0 ? blocks : 1, 256, 0, s>>>(esm, stride, n_rows, na, acc);
     return cudaGetLastError();
 }
 

@@ -1236,7 +1236,10 @@ static cudaError_t launch_cfg2(ScoreArgs a, int n_inst, int sm_count, cudaStream
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     const int n_units = (a.na + 8 * NT * WARPS - 1) / (8 * NT * WARPS);
-    int per_inst = (sm_count * MINB + n_inst - 1) / n_inst;      // persistent: ~MINB CTAs per SM in total
+    // persistent: at most MINB CTAs per SM in total.  Rounding the share of an instance UP (the round-1 rule) put e.g. 64
+    // instances x 5 CTAs = 320 CTAs on 296 slots: a second wave of 24 CTAs that doubled the launch's duration.  With fewer
+    // instances than slots every instance gets floor(slots / n_inst) CTAs (one wave); with more, one CTA each.
+    int per_inst = (sm_count * MINB) / n_inst;
     if (per_inst > n_units) per_inst = n_units;
     if (per_inst < 1) per_inst = 1;
     dim3 grid(per_inst, n_inst);

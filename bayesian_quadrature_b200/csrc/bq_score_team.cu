@@ -582,7 +582,7 @@ static cudaError_t launch_one(ScoreArgs a, int n_inst, int sm_count, cudaStream_
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     const long long n_super = ((long long)a.na + PTS - 1) / PTS;
-    long long per_inst = (sm_count + n_inst - 1) / n_inst;          // persistent: one CTA per SM in total
+    long long per_inst = sm_count / n_inst;                         // persistent: one CTA per SM in total, a single wave
     const long long need = (n_super + TEAMS - 1) / TEAMS;
     if (per_inst > need) per_inst = need;
     if (per_inst < 1) per_inst = 1;

@@ -247,9 +247,9 @@ def choose_next_sharded(bq, x_a, hypers_tl, hypers_l, params, shard="points"):
         total = torch.zeros(x_a.shape[0], dtype=torch.float64, device=dev)
         try:
             if hi > lo:
-                loss, batch = bq.marginal_loss(x_a, hypers_tl[lo:hi], hypers_l[lo:hi], params)
+                part, batch = bq.marginal_loss(x_a, hypers_tl[lo:hi], hypers_l[lo:hi], params, reduce="sum")
                 batch.close()
-                total += loss * (hi - lo)
+                total += part
         except Exception as e:                              # noqa: BLE001
             err = e
         raise_together(err, device=dev)

@@ -138,6 +138,12 @@ int bqb_score_device(bqb_batch *b, const double *d_x_a, long long xa_stride, int
 int bqb_score_host(bqb_batch *b, const double *x_a, long long xa_stride, int na, double *esm, double *em,
                    int *status);
 
+/* bqb_score_device for the instances [inst0, inst0 + n_inst) only.  Row 0 of x_a (when xa_stride != 0), esm, em, status and
+ * d_flags belongs to instance inst0: a batch of many hyper-parameter sets (bq.py:640-652) can be walked through one
+ * chunk-sized score buffer. */
+int bqb_score_device_range(bqb_batch *b, int inst0, int n_inst, const double *d_x_a, long long xa_stride, int na, double *d_esm,
+                           double *d_em, int *d_status, long long out_stride, int *d_flags, void *stream);
+
 /* Batched prediction at na points for every instance: l_mean = gp_l.mean(x), the mean of the final
  * approximation (BQ.l_mean, bq.py:177-200), and v_log_l = diag gp_log_l.cov(x), from which BQ.l_var (bq.py:202-231) is
  * max(v_log_l * l_mean^2, 0).  Same layout conventions as bqb_score_*; requires s_l = 0 (the scoring factors are those
@@ -159,6 +165,13 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
  * BQ.choose_next (bq.py:660-662: values[0].mean(axis=0)).  DEVICE pointers. */
 int bqb_mean_neg_device(bqb_batch *b, const double *d_esm, long long stride, long long na, double *d_loss,
                         void *stream);
+
+/* d_acc[p] += -esm[0][p] - esm[1][p] - ... over n_rows rows, in row order, starting from d_acc[p]: the running form of
+ * bqb_mean_neg_device.  Zero d_acc, feed the samples chunk by chunk in sample order, divide by the number of samples: the
+ * same additions in the same order as values[0].mean(axis=0) (bq.py:662), without the [n_samples, na] matrix in memory; and
+ * the partial sum a rank contributes when the samples are sharded across GPUs (all-reduce, then divide). */
+int bqb_sum_neg_accum_device(bqb_batch *b, const double *d_esm, long long stride, int n_rows, long long na, double *d_acc,
+                             void *stream);
 
 /* Deterministic minimum of a DEVICE vector and the FIRST index attaining it (np.min / np.argmin of
  * bq.py:663).  Results are written to HOST scalars; synchronises `stream`. */
@@ -209,6 +222,10 @@ int bqb_batch_set_cutoff(bqb_batch *b, double cut_arg);
  * points), score them in ascending order and write every result to its original position.  mode: 0 never, 1 automatic
  * (default: batches of capacity >= 128 observations, where the sort pays), 2 always.  The DEVICE entry points never sort: pass sorted vectors for full speed. */
 int bqb_batch_set_presort(bqb_batch *b, int mode);
+/* bqb_expected_var_host with page-locked arrays: enable = 1 (default) lets the scoring kernel read the query points from and
+ * write the results to host memory in place over PCIe (no staging copy, transfers overlap the arithmetic point by point);
+ * enable = 0 stages through device buffers with chunked asynchronous copies on two streams, as for pageable arrays. */
+int bqb_batch_set_zero_copy(bqb_batch *b, int enable);
 /* Executed-work counter of the scoring kernel: returns in *dmma_out (may be NULL) the number of DMMA.8x8x4
  * instructions (512 flop each) executed by the launches since the last call, then clears it; enable = 1 keeps
  * counting (a few integer instructions per sub-tile), enable = 0 switches it off (the default). */
