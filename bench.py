@@ -387,6 +387,10 @@ def run_cuda(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this path has no CPU fallback)")
+    # ONE JSON line on stdout: whatever libraries print while the run lasts (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     host_cores, cores_per_rank = bind_cores(world, local)
     torch.cuda.set_device(local)
     if world > 1:
@@ -658,7 +662,8 @@ def run_cuda(args):
                                         "single_process_sample": "1 process, OPENBLAS_NUM_THREADS=1, 12000 points, %.1f s" % wall1}
             else:
                 line["cpu_baseline"] = None
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

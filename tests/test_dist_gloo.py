@@ -114,3 +114,43 @@ def test_two_rank_gloo(n):
         assert p.exitcode == 0
     for rank, g, a, l in res:
         assert g and a and l, (rank, g, a, l)
+
+
+def _raise_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = []
+        bqdist.raise_together(None)                       # nobody failed: returns on every rank
+        out.append("ok")
+        try:
+            bqdist.raise_together(ValueError("rank 1 failed") if rank == 1 else None)
+            out.append("no raise")
+        except ValueError as e:
+            out.append("own:" + str(e))
+        except RuntimeError as e:
+            out.append("peer:" + str(e)[:30])
+        # the collectives that follow still line up: nobody is left waiting
+        t = torch.ones(1)
+        dist.all_reduce(t)
+        out.append(float(t))
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_a_failure_on_one_rank_raises_on_all():
+    """a rank whose marginal_loss raised must not leave the others in the all-gather / all-reduce."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_raise_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][0] == "ok" and res[0][1].startswith("peer:sharded call aborted") and res[0][2] == 2.0
+    assert res[1] == ["ok", "own:rank 1 failed", 2.0]
