@@ -222,6 +222,40 @@ def max_over_ranks(v, dev, world):
     return float(t.item())
 
 
+def measure_pcie(world, dev, mb=64, reps=12):
+    """What the platform gives for the e2e traffic pattern: every rank copies `mb` MB page-locked host -> device and device ->
+    page-locked host AT THE SAME TIME (two streams), all ranks concurrently.  Returns the aggregate GB/s over the ranks (both
+    directions summed) and this rank's share; 16 bytes cross PCIe per evaluation of the e2e path (8 in, 8 out)."""
+    import torch
+    import torch.distributed as dist
+    n = mb * (1 << 20) // 8
+    h_in = torch.empty(n, dtype=torch.float64).pin_memory()
+    h_out = torch.empty(n, dtype=torch.float64).pin_memory()
+    d_in = torch.empty(n, dtype=torch.float64, device=dev)
+    d_out = torch.ones(n, dtype=torch.float64, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    def burst():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    for _ in range(2):
+        burst()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        burst()
+    torch.cuda.synchronize()
+    mine = 2 * n * 8 * reps / (time.perf_counter() - t0) * 1e-9
+    t = torch.tensor([mine], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return {"aggregate_gbs_both_directions": float(t.item()), "rank0_gbs_both_directions": mine, "mb_per_copy": mb,
+            "pattern": "H2D and D2H copies of page-locked buffers running concurrently on every rank"}
+
+
 def cfg_c3_strong(world, rank, dev, steps=10):
     """BASELINE configs[2]: ns = 256, 10^7 query points FIXED, block-cyclic shards over the ranks, (min, first index) of the
     expected variance exchanged by the reduction kernel.  Strong scaling.  Checked against rank 0 scoring all 10^7 points."""
@@ -599,6 +633,7 @@ def run_cuda(args):
     e2e_staged = time_e2e(x_pin.numpy(), max(args.steps // 2, 3))  # page-locked input, staged asynchronous copies
     batch.set_zero_copy(True)
     e2e_pageable = time_e2e(np.array(shard), max(args.steps // 2, 3))   # what a caller with a plain numpy array gets
+    pcie = measure_pcie(world, dev)
 
     extra = {}
     if not args.no_configs:
@@ -643,7 +678,9 @@ def run_cuda(args):
                          "hbm_bytes_per_eval": 28, "hbm_gbs": 28 * NA / (kern_ms_avg * 1e-3) * 1e-9},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * NA, "d2h_bytes_per_step": d2h_bytes,
                     "input": "page-locked numpy array, read and written in place by the kernel over PCIe (zero copy)",
-                    "pinned_staged_copies": e2e_staged, "pageable_input": e2e_pageable},
+                    "pinned_staged_copies": e2e_staged, "pageable_input": e2e_pageable,
+                    "pcie": pcie, "pcie_gbs_used": 16 * e2e_value * 1e-9,
+                    "frac_of_pcie": 16 * e2e_value * 1e-9 / pcie["aggregate_gbs_both_directions"]},
             "gpu_launches": int(launches), "setup_ms": setup_ms, "rehyper_ms": float(np.median(rehyper)),
             "clocks": clocks, "argmin": {"min": result[0], "index": result[1]}, "argmin_check": argmin_check,
             "sustained": sustained, "configs": extra,

@@ -626,3 +626,124 @@ def test_team_kernel_of_the_64_class_agrees(lib, oracle, ns, nc, monkeypatch):
         res.append(pair.cpu().numpy().copy())
     assert res[0][1] == res[1][1] and abs(res[0][0] - res[1][0]) <= 1e-11 * abs(res[0][0])
     b.close()
+
+
+def test_full_size_properties_c4(lib, oracle):
+    """BASELINE configs[3] at full size (1024 hyper-parameter sets x 10^5 points, ns = 64): every set through the semantics of
+    _set_gp_log_l_params (guard on), the marginal loss accumulated chunk by chunk in sample order == the one-shot mean over
+    the materialised [1024, 10^5] matrix bit for bit, independent of the chunk size, deterministic; device argmin == host
+    argmin; 16 points of the loss against the oracle's mean over ALL 1024 sets, and three whole sets on a 500-point subsample."""
+    import torch
+    from bayesian_quadrature_b200 import synthetic
+    g = load_golden("c2")
+    ns, nc, n_hyper, na = 64, g["x_c"].size, 1024, 10 ** 5
+    hyp4 = synthetic.hyper_sets(n_hyper)
+    hyp = np.zeros((n_hyper, 6))
+    hyp[:, 0], hyp[:, 1], hyp[:, 3], hyp[:, 4] = hyp4.T
+    prior = np.tile([float(g["x_mean"]), float(g["x_var"]), float(g["candidate_thresh"])], (n_hyper, 1))
+    b = lib.Batch(n_hyper, ns)
+    info = b.setup(np.full(n_hyper, ns), np.full(n_hyper, nc), np.tile(g["x_s"], (n_hyper, 1)), np.tile(g["l_s"], (n_hyper, 1)),
+                   np.tile(g["x_c"], (n_hyper, 1)), hyp, prior, check_max=True)
+    assert (info["status"] == 0).all()
+    dev = torch.device("cuda", 0)
+    grid = synthetic.query_grid(ns, na)
+    x_d = torch.from_numpy(grid).to(dev)
+
+    def chunked(chunk):
+        esm = torch.empty(chunk, na, dtype=torch.float64, device=dev)
+        flags = torch.zeros(chunk, dtype=torch.int32, device=dev)
+        acc = torch.zeros(na, dtype=torch.float64, device=dev)
+        seen = 0
+        for i0 in range(0, n_hyper, chunk):
+            cnt = min(chunk, n_hyper - i0)
+            b.score_device_range(i0, cnt, x_d, esm, None, None, flags)
+            b.sum_neg_accum_device(esm, cnt, acc)
+            seen |= int(np.bitwise_or.reduce(flags[:cnt].cpu().numpy()))
+        return acc / n_hyper, seen
+    loss74, fl = chunked(74)
+    loss74b, _ = chunked(74)
+    loss37, _ = chunked(37)
+    assert not fl & ~(lib.ST_SHORTCUT | lib.ST_NOTPD)
+    assert torch.equal(loss74, loss74b) and torch.equal(loss74, loss37)
+    full = torch.empty(n_hyper, na, dtype=torch.float64, device=dev)            # 819 MB: what round 1 materialised
+    b.score_device(x_d, full)
+    loss_full = torch.empty(na, dtype=torch.float64, device=dev)
+    b.mean_neg_device(full, loss_full)
+    assert torch.equal(loss_full, loss74)
+    lh = loss74.cpu().numpy()
+    assert np.isfinite(lh).all() and (lh <= 0).all()
+    mn, idx = b.argmin_device(loss74)
+    assert idx == int(np.argmin(lh)) and mn == lh.min()
+    # the oracle: the loss at 16 grid points over ALL 1024 sets, and three sets on 500 points
+    pts = np.unique(np.concatenate([np.linspace(0, na - 1, 14).astype(np.int64), [idx, min(idx + 1, na - 1)]]))
+    sub = np.random.RandomState(7).choice(na, 500, replace=False)
+    acc = np.zeros(pts.size)
+    for i in range(n_hyper):
+        m = oracle.OracleModel(g["x_s"], g["l_s"], g["x_c"], (hyp[i, 0], hyp[i, 1], 0.0), (hyp[i, 3], hyp[i, 4], 0.0), float(g["x_mean"]),
+                               float(g["x_var"]), float(g["candidate_thresh"]), check_max=True)
+        o_esm, _, _ = m.esm_and_em(grid[pts])
+        acc += -o_esm
+        if i in (0, 511, 1023):
+            o_sub, _, _ = m.esm_and_em(grid[sub])
+            assert_close(full[i].cpu().numpy()[sub], o_sub, "c4 hyper set %d esm" % i)
+            assert_close(info["Z_mean"][i], m.Z_mean(), "Z_mean[%d]" % i)
+            assert_close(info["l_c"][i, :nc], m.l_c, "l_c[%d]" % i)
+        m.close()
+    assert_close(lh[pts], acc / n_hyper, "c4 marginal loss vs the oracle over all 1024 sets")
+    b.close()
+
+
+def test_full_size_properties_c5_round(lib, oracle):
+    """One active-sampling round of BASELINE configs[4] at full size (16384 independent problems x 4096 points, ns = 128):
+    device-resident and host-driven batches draw the same candidates (per-problem numpy-compatible MT19937 streams) and
+    choose the same points; scores are deterministic; the per-problem device argmin equals the host argmin of the score
+    rows; eight problems against the oracle on a 256-point subsample."""
+    import torch
+    from bayesian_quadrature_b200 import BatchBQ, synthetic
+    P, ns, na = 16384, 128, 4096
+    opt = synthetic.options(ns)
+    x0, _ = synthetic.observations(ns)
+    sp = synthetic.span(ns)
+    shifts = np.array([synthetic.problem_shift(p) for p in range(P)])
+    npdf = lambda x, m, s: np.exp(-0.5 * ((x - m) / s) ** 2) / (np.sqrt(2 * np.pi) * s)
+    lik = lambda x: (0.5 * npdf(x, (-0.3 + shifts[:, 0]) * sp, 0.16 * sp) + 0.3 * npdf(x, (0.4 + shifts[:, 1]) * sp, 0.10 * sp)
+                     + 0.2 * npdf(x, (0.1 + shifts[:, 2]) * sp, 0.3 * sp))
+    l0 = np.stack([lik(np.full(P, x)) for x in x0], axis=1)
+    args = (np.tile(x0, (P, 1)), l0, synthetic.PARAMS_TL, synthetic.PARAMS_L, opt["n_candidate"], opt["candidate_thresh"],
+            opt["x_mean"], opt["x_var"])
+    dev_b = BatchBQ(*args, seed=synthetic.SEED, device_resident=True)
+    host_b = BatchBQ(*args, seed=synthetic.SEED, ns_reserve=1)
+    dev_b.sync_host()
+    assert np.array_equal(dev_b.nc, host_b.nc) and np.array_equal(dev_b.x_c, host_b.x_c)
+    assert np.array_equal(dev_b.Z_mean(), host_b.Z_mean())
+    grid = synthetic.query_grid(ns, na)
+    grid_d = torch.from_numpy(grid).cuda()
+    idx_d, x_d = dev_b.choose_next(grid_d, on_device=True)
+    loss1 = dev_b._esm.clone()
+    idx_d2, _ = dev_b.choose_next(grid_d, on_device=True)
+    assert torch.equal(loss1, dev_b._esm) and torch.equal(idx_d, idx_d2)              # deterministic
+    idx_h, x_h = host_b.choose_next(grid)
+    assert np.array_equal(idx_d.cpu().numpy(), idx_h) and np.array_equal(x_d.cpu().numpy(), x_h)
+    loss = loss1.cpu().numpy()                                                        # -esm
+    assert np.isfinite(loss).all() and (loss <= 0).all()
+    assert np.array_equal(loss.argmin(axis=1), idx_h)
+    sub = np.random.RandomState(8).choice(na, 256, replace=False)
+    for p in (0, 1, 777, 4095, 8192, 12345, 16000, 16383):
+        c = host_b.nc[p]
+        m = oracle.OracleModel(host_b.x_s[p, :ns], host_b.l_s[p, :ns], host_b.x_c[p, :c], synthetic.PARAMS_TL, synthetic.PARAMS_L,
+                               opt["x_mean"], opt["x_var"], opt["candidate_thresh"])
+        o_esm, _, _ = m.esm_and_em(grid[sub])
+        assert_close(-loss[p, sub], o_esm, "c5 problem %d esm" % p)
+        assert_close(host_b.Z_mean()[p], m.Z_mean(), "Z_mean[%d]" % p)
+        m.close()
+    # the round's update: same merged / appended observations on both sides
+    l_new = lik(x_h)
+    host_b.add_observations(x_h, l_new)
+    dev_b.add_observations(x_d, torch.from_numpy(l_new).cuda())
+    dev_b.sync_host()
+    assert np.array_equal(dev_b.ns, host_b.ns)
+    n1 = int(host_b.ns.max())
+    assert np.array_equal(dev_b.x_s[:, :n1], host_b.x_s[:, :n1]) and np.array_equal(dev_b.x_c, host_b.x_c)
+    assert np.array_equal(dev_b.Z_mean(), host_b.Z_mean())
+    dev_b.close()
+    host_b.close()
