@@ -610,7 +610,7 @@ def test_team_kernel_of_the_64_class_agrees(lib, oracle, ns, nc, monkeypatch):
             assert_close(m1[0][ok], m0[0][ok], "em " + tag, rtol=1e-11, atol=1e-300)
             # ev = Zm^2 + Zv - esm cancels near the data: judged on the scale of its terms
             assert_close(ev1[ok], ev0[ok], "ev " + tag, rtol=1e-11, atol=1e-11 * float(np.abs(e0[0][ok & np.isfinite(e0[0])]).min() + info["Z_mean"][0] ** 2))
-            assert_close(p1[0][0], p0[0][0], "l_mean " + tag, rtol=1e-11, atol=1e-300)
+            assert_close(p1[0][0], p0[0][0], "l_mean " + tag, rtol=1e-11, atol=1e-11 * np.abs(p0[0][0]).max())    # k . alpha cancels in the far field
             assert_close(p1[1][0], p0[1][0], "v_log_l " + tag, rtol=1e-9, atol=1e-12)
             if cut == 72.0:
                 o_esm, o_em, o_st = m.esm_and_em(x_a)
