@@ -606,8 +606,11 @@ def test_team_kernel_of_the_64_class_agrees(lib, oracle, ns, nc, monkeypatch):
             tag = "%s ns=%d nc=%d cut=%g" % (name, ns, nc, cut)
             assert (s0 == s1).all() and f0 == f1, tag
             ok = np.isfinite(x_a)
-            assert_close(e1[0][ok], e0[0][ok], "esm " + tag, rtol=1e-11, atol=1e-300)
-            assert_close(m1[0][ok], m0[0][ok], "em " + tag, rtol=1e-11, atol=1e-300)
+            # points ON a candidate have a Schur pivot of 1e-4 of the diagonal (the jitter): rounding differences of the two
+            # summation orders are amplified 1e4-fold there
+            rt = 1e-11 if name == "grid" else 1e-9
+            assert_close(e1[0][ok], e0[0][ok], "esm " + tag, rtol=rt, atol=1e-300)
+            assert_close(m1[0][ok], m0[0][ok], "em " + tag, rtol=rt, atol=1e-300)
             # ev = Zm^2 + Zv - esm cancels near the data: judged on the scale of its terms
             assert_close(ev1[ok], ev0[ok], "ev " + tag, rtol=1e-11, atol=1e-11 * float(np.abs(e0[0][ok & np.isfinite(e0[0])]).min() + info["Z_mean"][0] ** 2))
             assert_close(p1[0][0], p0[0][0], "l_mean " + tag, rtol=1e-11, atol=1e-11 * np.abs(p0[0][0]).max())    # k . alpha cancels in the far field
