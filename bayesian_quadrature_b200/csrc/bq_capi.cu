@@ -13,17 +13,8 @@
 #include "bq_common.cuh"
 
 namespace bqb {
-struct SetupArgs {
-    const int *ns, *nc;
-    const double *x_s, *l_s, *x_c, *hyp, *prior;
-    int in_stride, check_max;
-    double *models;
-    Layout lay;
-    double *work;
-    size_t work_stride;
-    int n_cap, inst0;
-};
 void launch_setup(const SetupArgs &a, int n_inst, cudaStream_t stream);
+cudaError_t launch_setup2(const SetupArgs &a, int n_inst, cudaStream_t stream);
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x = nullptr);
 cudaError_t launch_argmin_partials(double *bv, long long *bi, int nblocks, long long offset, double *pair, cudaStream_t s);
 cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, long long na, double *loss, cudaStream_t s);
@@ -65,6 +56,7 @@ struct bqb_batch {
     unsigned *d_mt = nullptr;          // [624][n_inst] Mersenne-Twister words
     int *d_mti = nullptr, *d_overflow = nullptr;
     std::vector<int> h_ns, h_nc;
+    bool counts_fresh = false;         // h_ns / h_nc mirror d_ns / d_nc
     // scoring: relevance cut-off (bq_score.cu, CUT_ARG; +inf = dense) and the optional executed-work counter
     double cut_arg = 72.0;
     unsigned long long *d_work_ctr = nullptr;
@@ -180,11 +172,28 @@ static int run_setup(bqb_batch *b, int check_max, cudaStream_t s) {
     a.ns = b->d_ns; a.nc = b->d_nc; a.x_s = b->d_xs; a.l_s = b->d_ls; a.x_c = b->d_xc; a.hyp = b->d_hyp; a.prior = b->d_prior;
     a.in_stride = b->ns_cap; a.check_max = check_max; a.models = b->d_models; a.lay = b->lay;
     a.work = b->d_work; a.work_stride = b->work_stride; a.n_cap = b->n_cap;
+    // counts on the host before the launch (they size the second-generation kernel's shared memory); the device-side
+    // round kernels (add_observations, draw_candidates) change them without the host seeing it
+    if (!b->counts_fresh) {
+        CU(cudaMemcpyAsync(b->h_ns.data(), b->d_ns, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+        CU(cudaMemcpyAsync(b->h_nc.data(), b->d_nc, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+        b->counts_fresh = true;
+    }
+    static const bool v1 = getenv("BQB_SETUP_V1") && atoi(getenv("BQB_SETUP_V1"));
+    int n_max = 8, nc_max = 1;
+    for (int i = 0; i < B; ++i) {
+        const int ns_i = b->h_ns[i], nc_i = b->h_nc[i];
+        if (!(ns_i >= 1 && ns_i <= b->ns_cap && nc_i >= 0 && nc_i <= NC_MAX)) continue;      // the kernel reports it
+        if (ns_i + nc_i > n_max) n_max = ns_i + nc_i;
+        if (nc_i > nc_max) nc_max = nc_i;
+    }
+    a.n_max = n_max; a.nc_max = nc_max;
     for (int i0 = 0; i0 < B; i0 += b->work_inst) {
         const int cnt = (B - i0 < b->work_inst) ? B - i0 : b->work_inst;
         a.inst0 = i0;
-        launch_setup(a, cnt, s);
-        CU(cudaGetLastError());
+        if (v1) { launch_setup(a, cnt, s); CU(cudaGetLastError()); }
+        else CU(launch_setup2(a, cnt, s));
         b->launches++;
     }
     // headers (Z_mean, Z_var, log_lh, status) and l_c rows back to the host: gathered on the device, one contiguous copy
@@ -192,8 +201,6 @@ static int run_setup(bqb_batch *b, int check_max, cudaStream_t s) {
     CU(launch_pack_info(b->d_models, b->lay.total, b->lay.off_lc, B, b->d_info, s));
     b->launches++;
     CU(cudaMemcpyAsync(b->h_info, b->d_info, sizeof(double) * (size_t)B * IW, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(b->h_ns.data(), b->d_ns, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(b->h_nc.data(), b->d_nc, sizeof(int) * B, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     for (int i = 0; i < B; ++i) {
         memcpy(&b->h_hdr[(size_t)i * H_COUNT], b->h_info + (size_t)i * IW, sizeof(double) * H_COUNT);
@@ -229,6 +236,7 @@ int bqb_batch_stage(bqb_batch *b, const int *ns, const double *x_s, const double
     CU(cudaStreamSynchronize(s));          // the host arrays may be pageable and are free to change after this call
     b->staged = true;
     b->ready = false;
+    b->counts_fresh = false;
     return 0;
 }
 
@@ -245,6 +253,8 @@ int bqb_batch_setup(bqb_batch *b, const int *ns, const int *nc, const double *x_
     const int B = b->n_inst;
     CU(cudaMemcpyAsync(b->d_nc, nc, sizeof(int) * B, cudaMemcpyHostToDevice, s));
     if (x_c) CU(cudaMemcpyAsync(b->d_xc, x_c, sizeof(double) * (size_t)B * NC_MAX, cudaMemcpyHostToDevice, s));
+    for (int i = 0; i < B; ++i) { b->h_ns[i] = ns[i]; b->h_nc[i] = nc[i]; }
+    b->counts_fresh = true;
     return run_setup(b, check_max, s);
 }
 
@@ -310,6 +320,7 @@ int bqb_batch_draw_candidates(bqb_batch *b, int n_candidate, void *stream) {
                               b->d_nc, b->n_inst, (cudaStream_t)stream));
     b->launches++;
     b->ready = false;
+    b->counts_fresh = false;
     return 0;
 }
 
@@ -323,6 +334,7 @@ int bqb_batch_add_observations(bqb_batch *b, const double *d_x_new, const double
     CU(launch_add_observations(b->d_xs, b->d_ls, b->d_ns, b->ns_cap, b->d_prior, d_x_new, d_l_new, b->n_inst, b->d_overflow, s));
     b->launches++;
     b->ready = false;
+    b->counts_fresh = false;
     int ov = 0;
     CU(cudaMemcpyAsync(&ov, b->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));

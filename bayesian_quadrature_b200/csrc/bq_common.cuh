@@ -107,6 +107,27 @@ struct ScoreArgs {
     unsigned long long *work = nullptr; // optional counter: DMMA instructions executed (all warps, atomically added)
 };
 
+// Arguments of one setup launch (bq_setup.cu, bq_setup2.cu); shared with the C-ABI layer (bq_capi.cu)
+struct SetupArgs {
+    // inputs, one row per instance
+    const int *ns, *nc;
+    const double *x_s, *l_s;   // [B][in_stride]
+    const double *x_c;         // [B][NC_MAX]
+    const double *hyp;         // [B][6]  h_tl, w_tl, s_tl, h_l, w_l, s_l
+    const double *prior;       // [B][3]  mu, sigma2, candidate_thresh
+    int in_stride;
+    int check_max;             // apply the bq.py:942-947 guard
+    // outputs
+    double *models;            // [B][lay.total]
+    Layout lay;
+    // scratch, per instance: 4 matrices of n_cap^2 + 32 vectors of n_cap
+    double *work;
+    size_t work_stride;
+    int n_cap;
+    int inst0;                 // first instance of this chunk
+    int n_max, nc_max;         // bq_setup2.cu: largest ns + nc / nc over the instances of the launch (size the shared memory)
+};
+
 #ifdef __CUDACC__
 
 // D(8x8) += A(8x4) * B(4x8), FP64 tensor path (SASS: DMMA.8x8x4).  Lane l holds

@@ -21,24 +21,6 @@ constexpr int SETUP_THREADS = 256;
 constexpr double LOG_2PI = 1.8378770664093453;
 constexpr double SQRT_2PI = 2.5066282746310002;
 
-struct SetupArgs {
-    // inputs, one row per instance
-    const int *ns, *nc;
-    const double *x_s, *l_s;   // [B][in_stride]
-    const double *x_c;         // [B][NC_MAX]
-    const double *hyp;         // [B][6]  h_tl, w_tl, s_tl, h_l, w_l, s_l
-    const double *prior;       // [B][3]  mu, sigma2, candidate_thresh
-    int in_stride;
-    int check_max;             // apply the bq.py:942-947 guard
-    // outputs
-    double *models;            // [B][lay.total]
-    Layout lay;
-    // scratch, per instance: 4 matrices of n_cap^2 + 32 vectors of n_cap
-    double *work;
-    size_t work_stride;
-    int n_cap;
-    int inst0;                 // first instance of this chunk
-};
 
 __device__ double block_sum(double v, double *red) {
     v = warp_sum(v);

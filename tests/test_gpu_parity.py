@@ -611,8 +611,12 @@ def test_team_kernel_of_the_64_class_agrees(lib, oracle, ns, nc, monkeypatch):
             rt = 1e-11 if name == "grid" else 1e-9
             assert_close(e1[0][ok], e0[0][ok], "esm " + tag, rtol=rt, atol=1e-300)
             assert_close(m1[0][ok], m0[0][ok], "em " + tag, rtol=rt, atol=1e-300)
-            # ev = Zm^2 + Zv - esm cancels near the data: judged on the scale of its terms
-            assert_close(ev1[ok], ev0[ok], "ev " + tag, rtol=1e-11, atol=1e-11 * float(np.abs(e0[0][ok & np.isfinite(e0[0])]).min() + info["Z_mean"][0] ** 2))
+            # ev = Zm^2 + Zv - esm cancels near the data: judged on the scale of its terms, point by point (the two
+            # kernels' esm may differ by rt * |esm|, and so may ev)
+            fin = ok & np.isfinite(e0[0]) & np.isfinite(ev0)
+            assert (np.isfinite(ev0) == np.isfinite(ev1)).all(), tag
+            bound = rt * np.abs(e0[0][fin]) + 1e-11 * info["Z_mean"][0] ** 2
+            assert (np.abs(ev1[fin] - ev0[fin]) <= bound).all(), ("ev " + tag, float(np.max(np.abs(ev1[fin] - ev0[fin]) / bound)))
             assert_close(p1[0][0], p0[0][0], "l_mean " + tag, rtol=1e-11, atol=1e-11 * np.abs(p0[0][0]).max())    # k . alpha cancels in the far field
             assert_close(p1[1][0], p0[1][0], "v_log_l " + tag, rtol=1e-9, atol=1e-12)
             if cut == 72.0:

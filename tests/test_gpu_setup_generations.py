@@ -1,0 +1,56 @@
+"""The shared-memory setup kernel (csrc/bq_setup2.cu, the default) against the first-generation kernel
+(csrc/bq_setup.cu, BQB_SETUP_V1=1) on ragged instances of every capacity class: same status, and every number of the
+model block -- header scalars, vectors, candidate block, fragment-ordered operands -- equal up to the rounding of two
+different (blocked) factorisation orders."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _dump(tmp_path, name, v1):
+    out = str(tmp_path / name)
+    env = dict(os.environ)
+    env.pop("BQB_SETUP_V1", None)
+    if v1:
+        env["BQB_SETUP_V1"] = "1"
+    subprocess.run([sys.executable, os.path.join(HERE, "setup_dump.py"), out], check=True, env=env, timeout=600)
+    return dict(np.load(out))
+
+
+def test_second_generation_setup_equals_the_first(tmp_path):
+    a = _dump(tmp_path, "v1.npz", True)
+    b = _dump(tmp_path, "v2.npz", False)
+    assert sorted(a) == sorted(b)
+    from bayesian_quadrature_b200 import _lib
+    H_ZV = 16
+    checked = 0
+    for key in sorted(a):
+        if key.endswith("_status") or key.endswith("_ns") or key.endswith("_nc"):
+            assert (a[key] == b[key]).all(), key
+        elif key.endswith("_Z_var"):
+            # a 6-10 digit cancellation of two O(1e-3 .. 1) terms: absolute tolerance
+            assert np.allclose(a[key], b[key], rtol=1e-6, atol=1e-13), (key, a[key], b[key])
+        elif key.endswith("_models"):
+            ma, mb = a[key].copy(), b[key].copy()
+            ma[:, H_ZV] = mb[:, H_ZV] = 0.0
+            assert ((np.abs(ma) > 1e100) == (np.abs(mb) > 1e100)).all()          # padding observations (x = 1e150)
+            ma[np.abs(ma) > 1e100] = mb[np.abs(mb) > 1e100] = 0.0
+            scale = np.abs(ma).max(axis=1, keepdims=True)
+            # element-wise: relative to the element where it is large, relative to the block's largest element
+            # otherwise (entries of L^-1 far from the diagonal and of K_tl^-1 log l are differences of much larger
+            # terms: two factorisation orders differ there by cond * eps, cond(K_tl) = 1.5e5 for these instances)
+            err = np.abs(ma - mb) / np.maximum(np.abs(ma), 1e-6 * scale)
+            assert err.max() < 1e-6, (key, err.max(), np.unravel_index(err.argmax(), err.shape))
+            checked += ma.shape[0]
+        elif key.endswith("_log_lh"):
+            # -y' K^-1 y / 2 - sum log L_ii: the quadratic form carries cond(K_tl) * eps = 3e-11 per factorisation order
+            assert np.allclose(a[key], b[key], rtol=1e-8, atol=1e-300), (key, a[key], b[key])
+        else:
+            assert np.allclose(a[key], b[key], rtol=1e-10, atol=1e-300), (key, a[key], b[key])
+    assert checked >= 30
