@@ -130,7 +130,9 @@ __device__ __forceinline__ void chol_diag_block(double *T, int n, int jb, double
 #pragma unroll
         for (int k = j + 1; k < 8; ++k) {
             const double lkj = __shfl_sync(0xffffffffu, d[j], k);
-            if (lane >= k) d[k] = fma(-d[j], lkj, d[k]);
+            // lane k's own diagonal does not wait for the shuffle: the next pivot (lane j + 1) is one FMA away
+            if (lane == k) d[k] = fma(-d[j], d[j], d[k]);
+            else if (lane > k) d[k] = fma(-d[j], lkj, d[k]);
         }
     }
     if (lane < 8) {
@@ -283,11 +285,21 @@ __device__ void tri_inverse_packed(double *T, int n, double *stage, int lds, con
         for (int J = warp; J <= nJ; J += NT / 32) {
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
             const int jc = 8 * J + lr;
-            for (int kb = 8 * J; kb < ib; kb += 8) {
-                const int k0 = kb + lc, k1 = kb + 4 + lc;
-                const double a0 = stage[lr * lds + k0], a1 = stage[lr * lds + k1];
-                const double b0 = (jc <= k0) ? T[tri(k0) + jc] : 0.0;
-                const double b1 = (jc <= k1) ? T[tri(k1) + jc] : 0.0;
+            if (8 * J < ib) {
+                // operands of K-step K + 1 are loaded before the DMMAs of K-step K; only K = J touches the diagonal
+                // block of X (its upper part reads as zero)
+                int kb = 8 * J;
+                const double *sa = stage + lr * lds + lc;
+                double a0 = sa[kb], a1 = sa[kb + 4];
+                double b0 = (jc <= kb + lc) ? T[tri(kb + lc) + jc] : 0.0;
+                double b1 = (jc <= kb + 4 + lc) ? T[tri(kb + 4 + lc) + jc] : 0.0;
+                for (kb += 8; kb < ib; kb += 8) {
+                    const double a0n = sa[kb], a1n = sa[kb + 4];
+                    const double b0n = T[tri(kb + lc) + jc], b1n = T[tri(kb + 4 + lc) + jc];
+                    dmma(c0, c1, a0, b0);
+                    dmma(e0, e1, a1, b1);
+                    a0 = a0n; a1 = a1n; b0 = b0n; b1 = b1n;
+                }
                 dmma(c0, c1, a0, b0);
                 dmma(e0, e1, a1, b1);
             }
@@ -787,14 +799,23 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
         // |L_tl^-1 beta|^2 = beta' K_tl^-1 beta, L_tl^-1 from its fragment-ordered copy (scaled by c_tl)
         double q = 0.0;
         {
+            // a warp per row block: every fragment is one coalesced 256-byte read (lane l <-> row l >> 2, column l & 3),
+            // the four lanes of a row are combined by two shuffles
             const double *F = M + lay.off_af_tl_tri;
-            for (int r = warp; r < ns; r += NW) {
-                const int rb = r >> 3;
-                const double *Fr = F + ((size_t)(rb * (rb + 1)) << 5) + ((r & 7) << 2);
-                double s = 0.0;
-                for (int k = lane; k <= r; k += 32) s = fma(Fr[((k >> 2) << 5) + (k & 3)], beta[k], s);
-                s = warp_sum(s);
-                if (lane == 0) q = fma(s, s, q);
+            const int lc = lane & 3;
+            for (int rb = warp; rb < (ns + 7) >> 3; rb += NW) {
+                const double *Fb = F + ((size_t)(rb * (rb + 1)) << 5) + lane;
+                const int nk = 2 * rb + 2;
+                double s0 = 0.0, s1 = 0.0;
+                for (int ks = 0; ks < nk; ks += 2) {
+                    const int k0 = 4 * ks + lc, k1 = k0 + 4;
+                    s0 = fma(Fb[ks << 5], k0 < ns ? beta[k0] : 0.0, s0);
+                    s1 = fma(Fb[(ks + 1) << 5], k1 < ns ? beta[k1] : 0.0, s1);
+                }
+                double sr = s0 + s1;
+                sr += __shfl_xor_sync(0xffffffffu, sr, 1);
+                sr += __shfl_xor_sync(0xffffffffu, sr, 2);
+                if (lc == 0) q = fma(sr, sr, q);
             }
         }
         const double beta2 = block_sum2<NT>(q, red) / (c_tl * c_tl);

@@ -1,76 +1,86 @@
-#!/usr/bin/env python
-"""Turns the ncu artefacts brought back in gpurun_out/ into the committed summaries under profiles/.
+"""Turns one `ncu --set full --clock-control none` capture (.ncu-rep) of a kernel into the committed summary files:
 
-    python profiles/summarize.py gpurun_out/launches_r01.csv gpurun_out/prof_score_XXX.ncu-rep profiles/ncu_score_r01.md
-"""
-import collections
+    python profiles/summarize.py gpurun_out/prof_score_c2_r02.ncu-rep profiles/ncu_score_r02   [--traffic]
+
+writes <out>.json (the numbers bench.py quotes: pipe-busy percentages, issue-active, DRAM bytes per launch, stall
+shares) and <out>.md (the same as a table).  With --traffic it also refreshes profiles/ncu_score_traffic.json, the
+`roofline.traffic` source of the bench line.  Needs `ncu` on PATH (reads the report, does not profile)."""
 import csv
+import io
+import json
+import os
 import subprocess
 import sys
 
-WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size", "launch__block_size",
-        "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "sm__cycles_elapsed.avg"]
+KEEP = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size", "launch__block_size",
+    "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.avg", "lts__t_sector_hit_rate.pct",
+]
+UNIT_SCALE = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
 
 
-def launches(path):
-    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
-    hdr, agg = None, collections.OrderedDict()
-    for r in rows:
-        if r[0] == "ID":
-            hdr = r
-            continue
-        if hdr:
-            d = dict(zip(hdr, r))
-            agg.setdefault(d["Kernel Name"], []).append(float(d["Metric Value"].replace(",", "")))
-    tot = sum(sum(v) for v in agg.values())
-    out = ["| kernel | launches | avg us | share of GPU time |", "|---|---|---|---|"]
-    for k, v in agg.items():
-        out.append("| `%s` | %d | %.1f | %.1f %% |" % (k[:90], len(v), sum(v) / len(v) / 1e3, 100 * sum(v) / tot))
-    return out
+def raw_page(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                         text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    return rows[0], rows[1], rows[2:]
 
 
-def raw(path):
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(txt.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
-    out = ["kernel: `%s`" % vals[hdr.index("Kernel Name")], "", "| metric | value | unit |", "|---|---|---|"]
-    for w in WANT:
-        if w in hdr:
-            i = hdr.index(w)
-            out.append("| %s | %s | %s |" % (w, vals[i], units[i]))
-    st = {}
-    for i, h in enumerate(hdr):
-        if h.startswith("smsp__pcsamp_warps_issue_stalled_") and not h.endswith("_not_issued"):
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    hdr, units, rows = raw_page(rep)
+    row = rows[-1]
+    d = dict(zip(hdr, row))
+    u = dict(zip(hdr, units))
+    res = {"kernel": d.get("Kernel Name"), "source": rep, "metrics": {}}
+    for k in KEEP:
+        if k in d and d[k] not in ("", None):
             try:
-                st[h.replace("smsp__pcsamp_warps_issue_stalled_", "")] = float(vals[i])
+                res["metrics"][k] = {"value": float(d[k].replace(",", "")), "unit": u.get(k, "")}
             except ValueError:
                 pass
-    try:        # the bench's roofline.traffic reads this
-        import json
-        import os
-        rd, wr = float(vals[hdr.index("dram__bytes_read.sum")]), float(vals[hdr.index("dram__bytes_write.sum")])
-        mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        rd *= mult[units[hdr.index("dram__bytes_read.sum")]]
-        wr *= mult[units[hdr.index("dram__bytes_write.sum")]]
-        json.dump({"kernel": vals[hdr.index("Kernel Name")], "dram_bytes_read": rd, "dram_bytes_write": wr, "source": path},
-                  open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_score_traffic.json"), "w"))
-    except Exception as e:
-        print("traffic json not written:", e)
-    tot = sum(st.values()) or 1
-    out += ["", "warp stall sampling: " + ", ".join("%s %.1f %%" % (k, 100 * v / tot)
-                                                    for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:8])]
-    return out
+    stalls = {}
+    for k, v in d.items():
+        if k.startswith("smsp__pcsamp_warps_issue_stalled_") and not k.endswith("_not_issued") and v:
+            try:
+                stalls[k[len("smsp__pcsamp_warps_issue_stalled_"):]] = float(v.replace(",", ""))
+            except ValueError:
+                pass
+    tot = sum(stalls.values())
+    if tot:
+        res["stall_pct"] = {k: round(100 * v / tot, 1) for k, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:8]}
+    m = res["metrics"]
+    g = lambda k: m[k]["value"] if k in m else None
+    res["dmma_pipe_pct"] = g("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active")
+    res["fp64_pipe_pct"] = g("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
+    res["issue_active_pct"] = g("smsp__issue_active.avg.pct_of_peak_sustained_active")
+
+    def nbytes(k):
+        if k not in m:
+            return None
+        return m[k]["value"] * UNIT_SCALE.get(m[k]["unit"], 1.0)
+    res["dram_bytes_read"], res["dram_bytes_write"] = nbytes("dram__bytes_read.sum"), nbytes("dram__bytes_write.sum")
+    with open(out + ".json", "w") as fh:
+        json.dump(res, fh, indent=1)
+    with open(out + ".md", "w") as fh:
+        fh.write("# `ncu --set full --clock-control none`: %s\n\nsource: `%s`\n\n| metric | value | unit |\n|---|---|---|\n"
+                 % (res["kernel"], rep))
+        for k in KEEP:
+            if k in m:
+                fh.write("| %s | %s | %s |\n" % (k, m[k]["value"], m[k]["unit"]))
+        if "stall_pct" in res:
+            fh.write("\nwarp stall sampling: " + ", ".join("%s %.1f %%" % kv for kv in res["stall_pct"].items()) + "\n")
+    if "--traffic" in sys.argv:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_score_traffic.json"), "w") as fh:
+            json.dump({"kernel": res["kernel"], "dram_bytes_read": res["dram_bytes_read"],
+                       "dram_bytes_write": res["dram_bytes_write"], "source": rep}, fh)
+    print(json.dumps({k: res[k] for k in ("kernel", "dmma_pipe_pct", "fp64_pipe_pct", "issue_active_pct", "dram_bytes_read")}))
 
 
 if __name__ == "__main__":
-    launch_csv, rep, dest = sys.argv[1:4]
-    lines = ["# ncu summary (round 1)", "", "## launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; "
-             "per-launch times are cold-cache and serialised: compare shares)", ""] + launches(launch_csv)
-    lines += ["", "## `ncu --set full --clock-control none` of the scoring kernel", ""] + raw(rep)
-    open(dest, "w").write("\n".join(lines) + "\n")
-    print("\n".join(lines))
+    main()

@@ -52,5 +52,6 @@ def test_second_generation_setup_equals_the_first(tmp_path):
             # -y' K^-1 y / 2 - sum log L_ii: the quadratic form carries cond(K_tl) * eps = 3e-11 per factorisation order
             assert np.allclose(a[key], b[key], rtol=1e-8, atol=1e-300), (key, a[key], b[key])
         else:
-            assert np.allclose(a[key], b[key], rtol=1e-10, atol=1e-300), (key, a[key], b[key])
+            # Z_mean, l_c: linear in K^-1 y, cond * eps between two factorisation orders
+            assert np.allclose(a[key], b[key], rtol=1e-9, atol=1e-300), (key, np.abs(a[key] / b[key] - 1).max())
     assert checked >= 30
