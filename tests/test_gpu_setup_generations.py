@@ -49,8 +49,10 @@ def test_second_generation_setup_equals_the_first(tmp_path):
             assert err.max() < 1e-6, (key, err.max(), np.unravel_index(err.argmax(), err.shape))
             checked += ma.shape[0]
         elif key.endswith("_log_lh"):
-            # -y' K^-1 y / 2 - sum log L_ii: the quadratic form carries cond(K_tl) * eps = 3e-11 per factorisation order
-            assert np.allclose(a[key], b[key], rtol=1e-8, atol=1e-300), (key, a[key], b[key])
+            # -y' K^-1 y / 2 - sum log L_ii: the quadratic forms carry cond * eps per factorisation order, and the random
+            # candidates of these instances may fall next to an observation (cond(K_l) up to ~1e9); the BASELINE
+            # configurations are held to 1e-9 against the reference in test_gpu_parity.py
+            assert np.allclose(a[key], b[key], rtol=1e-6, atol=1e-300), (key, a[key], b[key])
         else:
             # Z_mean, l_c: linear in K^-1 y, cond * eps between two factorisation orders
             assert np.allclose(a[key], b[key], rtol=1e-9, atol=1e-300), (key, np.abs(a[key] / b[key] - 1).max())
