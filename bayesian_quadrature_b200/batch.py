@@ -87,6 +87,9 @@ class BatchBQ(object):
         self.seed = int(seed)
         self.rngs = None if self.device_resident else [np.random.RandomState(seed + p) for p in range(self.P)]
         self._ns_max = ns0                                 # upper bound of ns over the problems (device mode)
+        # capacity class chosen for ns0 + ns_reserve from the start (both modes, so that they run the same kernels): a
+        # batch that is known to grow does not migrate to the next class after the first appended observation
+        self._class_hint = min(self.cap, 256)
         self.device = int(device)
         self.batch = None
         self.x_c = np.zeros((self.P, _lib.NC_MAX))
@@ -109,7 +112,7 @@ class BatchBQ(object):
     def _init_device(self):
         """Device-resident (re-)initialisation: candidates are drawn, filtered and sorted on the GPU."""
         if self.batch is None:                             # first call: upload the observations, seed the generators
-            cap_class = _lib.load().bqb_ns_capacity(int(self._ns_max))
+            cap_class = _lib.load().bqb_ns_capacity(max(int(self._ns_max), self._class_hint))
             if cap_class < 0:
                 raise NotImplementedError("more than 256 observations per problem")
             self.batch = _lib.Batch(self.P, cap_class, device=self.device)
@@ -162,7 +165,7 @@ class BatchBQ(object):
         self.nc = (~np.isnan(xc)).sum(axis=1).astype(np.int32)
         self.x_c[:] = 0.0
         self.x_c[:, :self.n_candidate] = np.nan_to_num(xc, nan=0.0)
-        cap_class = _lib.load().bqb_ns_capacity(int(self.ns.max()))
+        cap_class = _lib.load().bqb_ns_capacity(max(int(self.ns.max()), self._class_hint))
         if cap_class < 0:
             raise NotImplementedError("more than 256 observations per problem")
         if self.batch is None or self._cap_class != cap_class:       # crossed a kernel capacity class: new device batch

@@ -29,8 +29,11 @@ def build(case, rs):
     if shuffled:
         p = rs.permutation(ns)
         x_s, l_s = x_s[p], l_s[p]
-    lo, hi = x_s.min() - 2.0, x_s.max() + 2.0
-    x_c = np.sort(rs.uniform(lo, hi, size=nc))
+    # candidates as bq.py:967-991 leaves them: at least candidate_thresh = 0.5 from every observation and from each other
+    # (mid-points of random gaps of the 1.25-spaced observations, and points beyond both ends)
+    xs = np.sort(x_s)
+    spots = np.concatenate([xs[:-1] + 0.625, xs[:1] - 0.9 - 1.1 * np.arange(8), xs[-1:] + 0.9 + 1.1 * np.arange(8)])
+    x_c = np.sort(rs.choice(spots, size=nc, replace=False)) if nc else np.zeros(0)
     opt = synthetic.options(max(ns, 9))
     hyp = np.array([15.0, 2.0, s_tl, 0.2, 1.3, s_l])
     prior = np.array([opt["x_mean"], opt["x_var"], opt["candidate_thresh"]])

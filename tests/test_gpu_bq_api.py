@@ -268,7 +268,7 @@ def test_device_resident_rounds_equal_the_host_rounds():
     opt = synthetic.options(ns0)
     args = (np.tile(x0, (P, 1)), np.stack([f(x0) for f in fl]), synthetic.PARAMS_TL, synthetic.PARAMS_L,
             opt["n_candidate"], opt["candidate_thresh"], opt["x_mean"], opt["x_var"])
-    host = BatchBQ(*args, seed=123, ns_reserve=8)
+    host = BatchBQ(*args, seed=123)                      # no ns_reserve: both start in the 64 class and migrate
     dev = BatchBQ(*args, seed=123, device_resident=True)
     grid = synthetic.query_grid(ns0, 1201)
     grid_d = torch.from_numpy(grid).cuda()
