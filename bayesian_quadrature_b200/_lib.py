@@ -32,6 +32,7 @@ SYMBOLS = {
     "bqb_batch_setup": (ctypes.c_int, [_vp, _ip, _ip, _dp, _dp, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, _vp]),
     "bqb_batch_stage": (ctypes.c_int, [_vp, _ip, _dp, _dp, ctypes.c_int, _dp, _dp, _vp]),
     "bqb_batch_set_hypers": (ctypes.c_int, [_vp, _dp, _vp]),
+    "bqb_batch_set_approx": (ctypes.c_int, [_vp, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, _ll, ctypes.c_int]),
     "bqb_batch_setup_device": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "bqb_batch_seed_candidates": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint), _vp]),
     "bqb_batch_rng_get": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_uint), _ip]),
@@ -194,6 +195,27 @@ class Batch(object):
         """Replace the hyper-parameters [n_inst, 6] of the staged instances (the next setup_device uses them)."""
         hyp = _d(hyp).reshape(self.n_inst, 6)
         _check(load().bqb_batch_set_hypers(self._h, _pd(hyp), _vp(stream) if stream else None), "bqb_batch_set_hypers")
+
+    def set_approx(self, kernel_kind=0, period=None, xo=None, p_xo=None, force_generic=False):
+        """Kernel kind (0 Gaussian, 1 periodic with period [n_inst, 2] = p of gp_log_l / gp_l) and, when ``xo`` / ``p_xo``
+        are given ([n_xo] shared or [n_inst, n_xo]), the trapezoid approximation of the integrals over that grid
+        (``use_approx`` of the reference).  Takes effect at the next setup."""
+        n_xo, stride = 0, 0
+        if period is not None:
+            period = _d(period).reshape(self.n_inst, 2)
+        if xo is not None:
+            xo, p_xo = _d(xo), _d(p_xo)
+            if xo.shape != p_xo.shape:
+                raise ValueError("xo and p_xo must have the same shape")
+            n_xo = xo.shape[-1]
+            if xo.ndim == 2:
+                if xo.shape[0] != self.n_inst:
+                    raise ValueError("per-instance grids must be [n_inst, n_xo]")
+                stride = n_xo
+        self._approx_keep = (period, xo, p_xo)
+        _check(load().bqb_batch_set_approx(self._h, int(kernel_kind), _pd(period) if period is not None else None,
+                                           _pd(xo) if xo is not None else None, _pd(p_xo) if p_xo is not None else None,
+                                           int(n_xo), int(stride), int(bool(force_generic))), "bqb_batch_set_approx")
 
     def setup_device(self, check_max=False, stream=None):
         _check(load().bqb_batch_setup_device(self._h, int(check_max), _vp(stream) if stream else None), "bqb_batch_setup_device")

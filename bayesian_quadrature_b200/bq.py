@@ -75,8 +75,12 @@ class _DeviceModel(object):
             self.batch.close()
         self.batch, self.key, self.data_key = None, None, None
 
-    def refresh(self, data_key, x_s, l_s, x_c, hyp, prior, check_max):
-        key = (data_key, tuple(float(v) for v in hyp))
+    def refresh(self, data_key, x_s, l_s, x_c, hyp, prior, check_max, approx=None):
+        """``approx``: None (Gaussian kernel, closed-form integrals) or (kind, (p_tl, p_l), xo, p_xo) for the generic
+        path (periodic kernel and / or the trapezoid approximation over the grid ``xo``; ``xo`` may be None)."""
+        akey = None if approx is None else (approx[0], tuple(approx[1]), None if approx[2] is None else
+                                            (approx[2].tobytes(), approx[3].tobytes()))
+        key = (data_key, tuple(float(v) for v in hyp), akey)
         if key == self.key and (self.guarded or not check_max):
             return self
         ns, nc = x_s.shape[0], x_c.shape[0]
@@ -84,8 +88,16 @@ class _DeviceModel(object):
         if self.batch is None or cap != self.cap:
             self.close()
             self.batch, self.cap = _lib.Batch(1, cap, device=self.device), cap
+            self.approx_key = None
         hyp = np.asarray(hyp, dtype=DTYPE).reshape(1, 6)
         self.key = None
+        if akey != getattr(self, "approx_key", None):
+            if approx is None:
+                self.batch.set_approx(0)
+            else:
+                self.batch.set_approx(approx[0], period=np.array([approx[1]], dtype=DTYPE) if approx[0] else None,
+                                      xo=approx[2], p_xo=approx[3])
+            self.approx_key = akey
         if data_key != self.data_key:
             info = self.batch.setup([ns], [nc], x_s[None], l_s[None], x_c[None] if nc else np.zeros((1, 0)), hyp,
                                     np.asarray(prior, dtype=DTYPE).reshape(1, 3), check_max=check_max)
@@ -183,16 +195,9 @@ class BQ(object):
         if self.options["use_approx"]:
             logger.debug("Using approximate solutions for non-Gaussian kernel")
 
-    def _require_exact(self, what):
-        if self.options["use_approx"]:
-            raise NotImplementedError(
-                "%s: only GaussianKernel runs on the CUDA path; the reference's trapezoid approximation for "
-                "other kernels (bq_c.pyx:216-261, :358-422, :538-598) is outside this package's scope" % what)
-
     # ------------------------------------------------------------------ initialisation
     def init(self, params_tl, params_l):
         """Build the two GPs and draw the candidate points (bq.py:132-171)."""
-        self._require_exact("init")
         kernel = self.options["kernel"]
         self.gp_log_l = GP(kernel(*params_tl[:-1]), self.x_s, self.tl_s, s=params_tl[-1])
         self.gp_log_l.jitter = np.zeros(self.ns, dtype=DTYPE)
@@ -236,9 +241,20 @@ class BQ(object):
             if self._dev_model is not None:
                 self._dev_model.close()
             self._dev_model = _DeviceModel(self.device)
-        hyp = np.concatenate([np.asarray(params_tl, dtype=DTYPE), np.asarray(params_l, dtype=DTYPE)])
+        ptl, pl = np.asarray(params_tl, dtype=DTYPE), np.asarray(params_l, dtype=DTYPE)
+        hyp = np.array([ptl[0], ptl[1], ptl[-1], pl[0], pl[1], pl[-1]], dtype=DTYPE)      # (h, w, s) of both GPs
         prior = (float(self.options["x_mean"][0]), float(self.options["x_cov"][0, 0]), self.options["candidate_thresh"])
-        return self._dev_model.refresh(self._data_key(), self.x_s, self.l_s, self.x_c, hyp, prior, check_max)
+        approx = None
+        periodic = self.options["kernel"] is PeriodicKernel
+        if periodic or self.options["use_approx"]:
+            # generic device path (csrc/bq_score_generic.cu): periodic kernel and / or trapezoid integrals over the grid of
+            # bq.py:167-171.  During init the candidates' values are needed before the grid exists (bq.py:985 comes
+            # before :168): l_c only involves gp_log_l, so that pass runs with closed forms / without a grid.
+            xo = p_xo = None
+            if self.options["use_approx"] and (self.initialized or self.gp_l is not None):
+                xo, p_xo = self._approx()
+            approx = (1 if periodic else 0, (ptl[2], pl[2]) if periodic else (1.0, 1.0), xo, p_xo)
+        return self._dev_model.refresh(self._data_key(), self.x_s, self.l_s, self.x_c, hyp, prior, check_max, approx)
 
     def _log_l_values(self, params_tl, params_l, check_max):
         """l_c = exp(gp_log_l.mean(x_c)) from the device (bq.py:985 / :942-950).  Only gp_log_l is involved, as in the
@@ -252,7 +268,6 @@ class BQ(object):
     def _device_model(self):
         """Device factors for the *current* state; rebuilt only when data or parameters changed
         (the counterpart of the `gp` package's memoised Kxx / Lxx / inv_Kxx_y)."""
-        self._require_exact("device model")
         if not self.initialized and self.gp_l is None:
             raise RuntimeError("BQ object is not initialized: call init() first")
         model = self._refresh_device(self.gp_log_l.params, self.gp_l.params, check_max=False)
@@ -512,15 +527,22 @@ class BQ(object):
         base_tl, base_l = self.gp_log_l.params, self.gp_l.params
         names = list(self.gp_log_l.K.names) + ["s"]
         hyp = np.empty((n, 6))
+        periodic = self.options["kernel"] is PeriodicKernel
+        period = np.ones((n, 2))
         for i in range(n):
             ptl, pl = base_tl.copy(), base_l.copy()
             for name, v in zip(params, hypers_tl[i]):
                 ptl[names.index(name)] = v
             for name, v in zip(params, hypers_l[i]):
                 pl[names.index(name)] = v
-            hyp[i, :3], hyp[i, 3:] = ptl, pl
+            hyp[i] = [ptl[0], ptl[1], ptl[-1], pl[0], pl[1], pl[-1]]
+            if periodic:
+                period[i] = [ptl[2], pl[2]]
         batch = _lib.Batch(n, self.ns, device=self.device)
         try:
+            if periodic or self.options["use_approx"]:       # generic device path, the grid of bq.py:167-171 for every sample
+                xo, p_xo = self._approx() if self.options["use_approx"] else (None, None)
+                batch.set_approx(1 if periodic else 0, period=period if periodic else None, xo=xo, p_xo=p_xo)
             prior = np.tile([float(self.options["x_mean"][0]), float(self.options["x_cov"][0, 0]),
                              self.options["candidate_thresh"]], (n, 1))
             info = batch.setup(np.full(n, self.ns), np.full(n, self.nc), np.tile(self.x_s, (n, 1)),
@@ -692,6 +714,12 @@ class BQ(object):
             x = self._approx_x
         mu = float(self.options["x_mean"][0])
         var = float(self.options["x_cov"][0, 0])
+        if self.options["wrapped"]:
+            # bq_c.p_x_vonmises / vonmises_logpdf (bq_c.pyx:31-60) with kappa = 1 / x_cov; the reference normalises with
+            # libc's j0 (the Bessel function of the FIRST kind), not I0: kept, so that results stay identical
+            from scipy.special import j0
+            kappa = 1.0 / var
+            return np.exp(-np.log(2 * np.pi * j0(kappa)) + kappa * np.cos(np.asarray(x, dtype=DTYPE) - mu))
         return np.exp(-0.5 * (np.log(2 * np.pi) + np.log(var) + (x - mu) ** 2 / var))
 
     # ------------------------------------------------------------------ plotting (host, optional matplotlib)

@@ -16,6 +16,7 @@ namespace bqb {
 void launch_setup(const SetupArgs &a, int n_inst, cudaStream_t stream);
 cudaError_t launch_setup2(const SetupArgs &a, int n_inst, cudaStream_t stream);
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x = nullptr);
+cudaError_t launch_score_generic(const ScoreArgs &a, int n_inst, cudaStream_t stream, int *grid_x);
 cudaError_t launch_argmin_partials(double *bv, long long *bi, int nblocks, long long offset, double *pair, cudaStream_t s);
 cudaError_t launch_mean_neg(const double *esm, long long stride, int n_inst, long long na, double *loss, cudaStream_t s);
 cudaError_t launch_pack_info(const double *models, long long model_stride, int off_lc, int n_inst, double *out, cudaStream_t s);
@@ -57,6 +58,11 @@ struct bqb_batch {
     int *d_mti = nullptr, *d_overflow = nullptr;
     std::vector<int> h_ns, h_nc;
     bool counts_fresh = false;         // h_ns / h_nc mirror d_ns / d_nc
+    // non-Gaussian kernels / trapezoid approximation (bqb_batch_set_approx): generic scoring kernel
+    int kind = 0, n_xo = 0;
+    long long xo_stride = 0;
+    bool generic = false;
+    double *d_period = nullptr, *d_xo = nullptr, *d_pxo = nullptr, *d_wp = nullptr, *d_gz = nullptr;
     // scoring: relevance cut-off (bq_score.cu, CUT_ARG; +inf = dense) and the optional executed-work counter
     double cut_arg = 72.0;
     unsigned long long *d_work_ctr = nullptr;
@@ -155,7 +161,8 @@ void bqb_batch_destroy(bqb_batch *b) {
     if (!b) return;
     cudaSetDevice(b->device);
     void *ptrs[] = {b->d_models, b->d_tab, b->d_work, b->d_ns, b->d_nc, b->d_xs, b->d_ls, b->d_xc, b->d_hyp, b->d_prior,
-                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags, b->d_mt, b->d_mti, b->d_overflow, b->d_work_ctr, b->d_xsorted, b->d_perm, b->d_iota, b->d_sort_tmp};
+                    b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags, b->d_mt, b->d_mti, b->d_overflow, b->d_work_ctr, b->d_xsorted, b->d_perm, b->d_iota, b->d_sort_tmp,
+                    b->d_period, b->d_xo, b->d_pxo, b->d_wp, b->d_gz};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaStream_t st : b->pipe) if (st) cudaStreamDestroy(st);
     if (b->h_flags) cudaFreeHost(b->h_flags);
@@ -189,6 +196,9 @@ static int run_setup(bqb_batch *b, int check_max, cudaStream_t s) {
         if (nc_i > nc_max) nc_max = nc_i;
     }
     a.n_max = n_max; a.nc_max = nc_max;
+    a.kind = b->kind; a.period = b->d_period; a.xo = b->d_xo; a.pxo = b->d_pxo; a.n_xo = b->n_xo; a.xo_stride = b->xo_stride;
+    a.wp = b->d_wp; a.gz = b->d_gz;
+    if (v1 && (b->kind || b->n_xo)) return fail(BQB_EUNSUPPORTED, "BQB_SETUP_V1: the first-generation setup kernel has no periodic kernel / trapezoid mode");
     for (int i0 = 0; i0 < B; i0 += b->work_inst) {
         const int cnt = (B - i0 < b->work_inst) ? B - i0 : b->work_inst;
         a.inst0 = i0;
@@ -265,6 +275,34 @@ int bqb_batch_set_hypers(bqb_batch *b, const double *hyp, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     CU(cudaMemcpyAsync(b->d_hyp, hyp, sizeof(double) * (size_t)b->n_inst * 6, cudaMemcpyHostToDevice, s));
     CU(cudaStreamSynchronize(s));          // the host array may be pageable and is free to change after this call
+    b->ready = false;
+    return 0;
+}
+
+int bqb_batch_set_approx(bqb_batch *b, int kernel_kind, const double *period, const double *xo, const double *p_xo, int n_xo,
+                         long long xo_stride, int force_generic) {
+    if (!b || kernel_kind < 0 || kernel_kind > 1 || n_xo < 0 || (n_xo == 1) || xo_stride < 0)
+        return fail(BQB_EINVAL, "bqb_batch_set_approx: bad arguments");
+    if (kernel_kind == 1 && !period) return fail(BQB_EINVAL, "bqb_batch_set_approx: the periodic kernel needs its periods");
+    if (n_xo > 0 && (!xo || !p_xo || (xo_stride != 0 && xo_stride < n_xo))) return fail(BQB_EINVAL, "bqb_batch_set_approx: bad grid");
+    CU(cudaSetDevice(b->device));
+    const size_t B = (size_t)b->n_inst;
+    for (double **p : {&b->d_period, &b->d_xo, &b->d_pxo, &b->d_wp, &b->d_gz}) { if (*p) cudaFree(*p); *p = nullptr; }
+    if (kernel_kind == 1) {
+        CU(cudaMalloc(&b->d_period, sizeof(double) * B * 2));
+        CU(cudaMemcpy(b->d_period, period, sizeof(double) * B * 2, cudaMemcpyHostToDevice));
+    }
+    if (n_xo > 0) {
+        const size_t n_grid = xo_stride ? B * (size_t)xo_stride : (size_t)n_xo;
+        CU(cudaMalloc(&b->d_xo, sizeof(double) * n_grid));
+        CU(cudaMalloc(&b->d_pxo, sizeof(double) * n_grid));
+        CU(cudaMemcpy(b->d_xo, xo, sizeof(double) * n_grid, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(b->d_pxo, p_xo, sizeof(double) * n_grid, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&b->d_wp, sizeof(double) * B * (size_t)n_xo));
+        CU(cudaMalloc(&b->d_gz, sizeof(double) * (size_t)b->work_inst * (size_t)n_xo));
+    }
+    b->kind = kernel_kind; b->n_xo = n_xo; b->xo_stride = xo_stride;
+    b->generic = kernel_kind != 0 || n_xo > 0 || force_generic != 0;
     b->ready = false;
     return 0;
 }
@@ -369,6 +407,15 @@ int bqb_batch_info(bqb_batch *b, double *Z_mean, double *Z_var, double *log_lh, 
     return 0;
 }
 
+// the tensor-core kernels (Gaussian kernel, closed-form integrals) or the generic kernel (bqb_batch_set_approx)
+static cudaError_t score_dispatch(bqb_batch *b, ScoreArgs &a, int n_inst, cudaStream_t s, int *grid_x = nullptr) {
+    if (b->generic) {
+        a.xo = b->d_xo; a.wp = b->d_wp; a.n_xo = b->n_xo; a.xo_stride = b->xo_stride;
+        return launch_score_generic(a, n_inst, s, grid_x);
+    }
+    return score_dispatch(b, a, n_inst, s, grid_x);
+}
+
 static int check_ready(bqb_batch *b, const char *who) {
     if (!b || !b->ready) return fail(BQB_ESTATE, std::string(who) + ": batch was not set up");
     for (int i = 0; i < b->n_inst; ++i)
@@ -456,7 +503,7 @@ static int score_device_impl(bqb_batch *b, const double *d_x_a, long long xa_str
     for (int i0 = first; i0 < first + count; i0 += 32768) {
         const int cnt = (first + count - i0 < 32768) ? first + count - i0 : 32768;
         a.inst0 = i0;
-        CU(launch_score(a, cnt, b->sm_count, (cudaStream_t)stream));
+        CU(score_dispatch(b, a, cnt, (cudaStream_t)stream));
         b->launches++;
     }
     return 0;
@@ -466,6 +513,7 @@ int bqb_predict_device(bqb_batch *b, const double *d_x, long long x_stride, int 
                        long long out_stride, void *stream) {
     int rc = check_ready(b, "bqb_predict_device");
     if (rc) return rc;
+    if (b->generic) return fail(BQB_EUNSUPPORTED, "bqb_predict_device: not offered with bqb_batch_set_approx (generic kernel)");
     if (!d_x || !d_l_mean || !d_v_log_l || na < 0 || out_stride < na) return fail(BQB_EINVAL, "bqb_predict_device: bad arguments");
     if (na == 0) return 0;
     CU(cudaSetDevice(b->device));
@@ -477,7 +525,7 @@ int bqb_predict_device(bqb_batch *b, const double *d_x, long long x_stride, int 
     for (int i0 = 0; i0 < b->n_inst; i0 += 32768) {
         const int cnt = (b->n_inst - i0 < 32768) ? b->n_inst - i0 : 32768;
         a.inst0 = i0;
-        CU(launch_score(a, cnt, b->sm_count, (cudaStream_t)stream));
+        CU(score_dispatch(b, a, cnt, (cudaStream_t)stream));
         b->launches++;
     }
     return 0;
@@ -619,11 +667,11 @@ int bqb_expected_var_host(bqb_batch *b, int inst, const double *x_a, int na, dou
             // fused epilogue: Zm^2 + Zv - esm written straight into the caller's page-locked array
             a.esm = nullptr; a.ev = (double *)dout + lo;
             a.part_val = b->d_red_val + 2048 * (c & 1); a.part_idx = b->d_red_idx + 2048 * (c & 1);
-            CU(launch_score(a, 1, b->sm_count, s, &zc_grid));
+            CU(score_dispatch(b, a, 1, s, &zc_grid));
             b->launches += 1;
         } else {
             a.esm = b->d_esm + lo; a.ev = nullptr;
-            CU(launch_score(a, 1, b->sm_count, s));
+            CU(score_dispatch(b, a, 1, s));
             CU(launch_expected_var(b->d_esm + lo, n, msm, b->d_em + lo, s));
             b->launches += 2;
             CU(cudaMemcpyAsync(out + lo, b->d_em + lo, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
@@ -708,7 +756,7 @@ int bqb_choose_step_device(bqb_batch *b, int inst, const double *d_x_a, int na, 
     a.inst0 = 0; a.ndb_max = b->ndb_max;
     a.ev = d_ev; a.part_val = b->d_red_val; a.part_idx = b->d_red_idx;
     int grid_x = 0;
-    CU(launch_score(a, 1, b->sm_count, s, &grid_x));
+    CU(score_dispatch(b, a, 1, s, &grid_x));
     CU(launch_argmin_partials(b->d_red_val, b->d_red_idx, grid_x, offset, d_pair, s));
     b->launches += 2;
     return 0;
@@ -731,7 +779,7 @@ int bqb_choose_step_exchange(bqb_batch *b, int inst, const double *d_x_a, int na
     a.inst0 = 0; a.ndb_max = b->ndb_max;
     a.ev = d_ev; a.part_val = b->d_red_val; a.part_idx = b->d_red_idx;
     int grid_x = 0;
-    CU(launch_score(a, 1, b->sm_count, s, &grid_x));
+    CU(score_dispatch(b, a, 1, s, &grid_x));
     CU(launch_argmin_exchange(b->d_red_val, b->d_red_idx, grid_x, offset, cyclic_block, peer_slots, world, rank, seq, out4, s));
     b->launches += 2;
     return 0;

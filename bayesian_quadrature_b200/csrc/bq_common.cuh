@@ -33,7 +33,9 @@ constexpr double EPS = 2.220446049250313e-16;        // np.finfo(float64).eps, b
 // ---- header slots of a model block (doubles)
 enum Hdr {
     H_NS = 0, H_NC, H_NSP, H_STATUS, H_CL, H_NHL, H_CTL, H_NHTL, H_KAA_E, H_KAA_N, H_J1, H_KTT, H_MU,
-    H_CB, H_NHB, H_ZM, H_ZV, H_THRESH, H_LOGLH, H_BA_S, H_NDB, H_WL, H_TOL2MAX, H_COUNT = 32
+    H_CB, H_NHB, H_ZM, H_ZV, H_THRESH, H_LOGLH, H_BA_S, H_NDB, H_WL, H_TOL2MAX,
+    H_KIND, H_HP_TL, H_HP_L,          // kernel kind (0 Gaussian, 1 periodic) and 1 / (2 p) of the two kernels (generic path)
+    H_COUNT = 32
 };
 
 // Model block layout (offsets in doubles) for an instance capacity of nsp_cap observations
@@ -105,6 +107,11 @@ struct ScoreArgs {
     double cut_arg = 72.0;              // relevance cut-off of a cross-kernel exponent below its point's largest (+inf: dense)
     int force_wide = 0;                 // band-relative kernels: every warp takes the wide (windowed) path (tests)
     unsigned long long *work = nullptr; // optional counter: DMMA instructions executed (all warps, atomically added)
+    // generic path (bq_score_generic.cu): non-Gaussian kernels and / or the trapezoid approximation of int_K
+    const double *xo = nullptr;         // [n_xo] approximation grid (shared) or [B][xo_stride]
+    const double *wp = nullptr;         // [B][n_xo] trapezoid weight x prior density, written by the setup kernel
+    int n_xo = 0;                       // 0: closed-form int_K (Gaussian kernel)
+    long long xo_stride = 0;
 };
 
 // Arguments of one setup launch (bq_setup.cu, bq_setup2.cu); shared with the C-ABI layer (bq_capi.cu)
@@ -126,6 +133,14 @@ struct SetupArgs {
     int n_cap;
     int inst0;                 // first instance of this chunk
     int n_max, nc_max;         // bq_setup2.cu: largest ns + nc / nc over the instances of the launch (size the shared memory)
+    // non-Gaussian kernels / trapezoid approximation (bq_c.pyx:216-261, :358-422, :538-598); bq_setup2.cu only
+    int kind;                  // 0: gp.GaussianKernel, 1: gp.PeriodicKernel
+    const double *period;      // [B][2] p of gp_log_l's and gp_l's kernel (kind 1), else null
+    const double *xo, *pxo;    // approximation grid and prior density on it: [n_xo] (xo_stride = 0) or [B][xo_stride]
+    int n_xo;                  // 0: closed-form integrals
+    long long xo_stride;
+    double *wp;                // out [B][n_xo]: trapezoid weight x prior density
+    double *gz;                // scratch [launch instances][n_xo]
 };
 
 #ifdef __CUDACC__
@@ -215,6 +230,13 @@ __device__ __forceinline__ double exp_tab(double x, const double *__restrict__ t
     double y = fma(T, p, T);
     y = __hiloint2double(__double2hiint(y) + ((ki >> ExpC<N>::SHIFT) << 20), __double2loint(y));
     return (x < -708.0) ? 0.0 : y;
+}
+
+// exponent part of a stationary kernel at distance d: Gaussian exp(nh d^2) (nh = -1 / (2 w^2)); gp.PeriodicKernel
+// h^2 exp(-2 sin^2(d / (2 p)) / w^2) = h^2 exp(nh D^2) with the chordal distance D = 2 sin(d hp), hp = 1 / (2 p)
+__device__ __forceinline__ double kernel_exp(double d, double nh, int kind, double hp) {
+    if (kind) d = 2.0 * sin(d * hp);
+    return exp((d * d) * nh);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

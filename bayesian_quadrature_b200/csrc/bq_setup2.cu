@@ -391,9 +391,6 @@ __device__ void write_tri_frags(const double *T, int ns, double c, double *dst, 
     }
 }
 
-// gp's GaussianKernel h^2 / (sqrt(2 pi) w) * exp(-0.5 d^2 / w^2) with c = h^2 / (sqrt(2 pi) w), nh = -0.5 / w^2
-__device__ __forceinline__ double gauss_k2(double c, double nh, double d) { return c * exp((d * d) * nh); }
-
 // gauss_c.pyx:20-62 for d = 1 with L = sqrt(var), logdet = 2 log L
 __device__ __forceinline__ double mvn_logpdf1b(double x, double m, double L, double logdet) {
     const double diff = x - m;
@@ -414,7 +411,7 @@ __device__ __forceinline__ double mvn_logpdf1r(double x, double m, double rL, do
 #define PH(i) do { } while (0)
 #endif
 
-template <bool TSMEM, int NT>
+template <bool TSMEM, int NT, int KIND>
 __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
 #ifdef BQB_SETUP_PROF
     __shared__ long long s_prof[24];
@@ -479,8 +476,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
             bad |= !isfinite(x);
             x_sc[ns + i] = x;
         }
-        if (tid == 0)
+        if (tid == 0) {
             bad |= !(h_tl > 0 && w_tl > 0 && s_tl >= 0 && h_l > 0 && w_l > 0 && s_l >= 0 && sig2 > 0 && isfinite(mu));
+            if (KIND) bad |= !(a.period && a.period[inst * 2] > 0 && a.period[inst * 2 + 1] > 0);
+        }
         if (bad) s_fail = SETUP_BAD_INPUT;
     }
     __syncthreads();
@@ -500,15 +499,31 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
     __syncthreads();
 
     PH(1);
-    const double c_tl = (h_tl * h_tl) / (S2_SQRT_2PI * w_tl), nh_tl = -0.5 / (w_tl * w_tl);
-    const double c_l = (h_l * h_l) / (S2_SQRT_2PI * w_l), nh_l = -0.5 / (w_l * w_l);
+    // kernel = c exp(nh D^2): gp.GaussianKernel (D = d, c = h^2 / (sqrt(2 pi) w)) or gp.PeriodicKernel (D = 2 sin(d / 2p), c = h^2)
+    constexpr int kind = KIND;                          // (a template parameter: the Gaussian instantiation carries no sin code)
+    const double hp_tl = kind ? 0.5 / a.period[inst * 2] : 0.0, hp_l = kind ? 0.5 / a.period[inst * 2 + 1] : 0.0;
+    const double c_tl = kind ? h_tl * h_tl : (h_tl * h_tl) / (S2_SQRT_2PI * w_tl), nh_tl = -0.5 / (w_tl * w_tl);
+    const double c_l = kind ? h_l * h_l : (h_l * h_l) / (S2_SQRT_2PI * w_l), nh_l = -0.5 / (w_l * w_l);
+    // trapezoid approximation of the integrals over a grid xo (bq_c.pyx:216-261, :358-422, :538-598) instead of the
+    // closed forms: wp[j] = (trapezoid weight of xo[j]) x (prior density at xo[j])
+    const int n_xo = a.n_xo;
+    const double *xo = n_xo ? a.xo + (size_t)inst * a.xo_stride : nullptr;
+    double *wp = n_xo ? a.wp + (size_t)inst * n_xo : nullptr;
+    double *gz = n_xo ? a.gz + (size_t)blockIdx.x * n_xo : nullptr;
+    if (n_xo) {
+        const double *pxo = a.pxo + (size_t)inst * a.xo_stride;
+        for (int j = tid; j < n_xo; j += NT) {
+            const double tw = 0.5 * ((j > 0 ? xo[j] - xo[j - 1] : 0.0) + (j + 1 < n_xo ? xo[j + 1] - xo[j] : 0.0));
+            wp[j] = tw * pxo[j];
+        }
+    }
 
     // ---- P1/P2: tl_s = log l_s (bq.py:73); K_tl = K(x_s, x_s) + s_tl^2 I, lower triangle
     for (int i = tid; i < ns; i += NT) tl_s[i] = log(l_sc[i]);
     for (int e = tid; e < tri(ns); e += NT) {
         int i, j;
         tri_decode(e, i, j);
-        double v = gauss_k2(c_tl, nh_tl, x_sc[i] - x_sc[j]);
+        double v = c_tl * kernel_exp(x_sc[i] - x_sc[j], nh_tl, kind, hp_tl);
         if (i == j) v += s_tl * s_tl;
         T[e] = v;
     }
@@ -539,7 +554,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
         const int nbt = (nc - j0 < 4) ? nc - j0 : 4;
         for (int e = tid; e < nbt * ns; e += NT) {
             const int j = e / ns, k = e - j * ns;
-            stage[j * lds + k] = gauss_k2(c_tl, nh_tl, x_sc[ns + j0 + j] - x_sc[k]);
+            stage[j * lds + k] = c_tl * kernel_exp(x_sc[ns + j0 + j] - x_sc[k], nh_tl, kind, hp_tl);
         }
         __syncthreads();
         if (a.check_max) {
@@ -589,7 +604,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
     for (int e = tid; e < tri(n); e += NT) {
         int i, j;
         tri_decode(e, i, j);
-        T[e] = gauss_k2(c_l, nh_l, x_sc[i] - x_sc[j]);
+        T[e] = c_l * kernel_exp(x_sc[i] - x_sc[j], nh_l, kind, hp_l);
     }
     __syncthreads();
     PH(9);
@@ -613,7 +628,19 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
     // ---- P9: b_sc = int_K (gauss_c.pyx:95-164): h^2 exp(mvn_logpdf(x; mu, w_l^2 + sigma2))
     const double var_b = sig2 + w_l * w_l;
     const double Lb = sqrt(var_b), logdet_b = 2 * log(Lb);
-    for (int i = tid; i < n; i += NT) b_sc[i] = (h_l * h_l) * exp(mvn_logpdf1b(x_sc[i], mu, Lb, logdet_b));
+    if (n_xo) {
+        // int_K by the trapezoid rule (bq_c.pyx:585-593): sum_j wp[j] K_l(x_i, xo[j]), a warp per row
+        __syncthreads();                                 // wp is complete
+        for (int i = warp; i < n; i += NW) {
+            const double xi = x_sc[i];
+            double sacc = 0.0;
+            for (int j = lane; j < n_xo; j += 32) sacc = fma(wp[j], kernel_exp(xi - xo[j], nh_l, kind, hp_l), sacc);
+            sacc = warp_sum(sacc);
+            if (lane == 0) b_sc[i] = c_l * sacc;
+        }
+    } else {
+        for (int i = tid; i < n; i += NT) b_sc[i] = (h_l * h_l) * exp(mvn_logpdf1b(x_sc[i], mu, Lb, logdet_b));
+    }
     __syncthreads();
     PH(13);
     // ---- P10: pattern-independent pieces
@@ -712,7 +739,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
         for (int e = tid; e < tri(n); e += NT) {
             int i, j;
             tri_decode(e, i, j);
-            double v = gauss_k2(c_l, nh_l, x_sc[i] - x_sc[j]);
+            double v = c_l * kernel_exp(x_sc[i] - x_sc[j], nh_l, kind, hp_l);
             if (i == j) v += s_l * s_l;
             T[e] = v;
         }
@@ -743,10 +770,48 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
     // ---- P12: Z_mean = int_K . alpha_l  (bq_c.pyx:207-209)
     double pz = 0.0;
     for (int i = tid; i < n; i += NT) pz = fma(b_sc[i], alpha[i], pz);
-    const double Zm = block_sum2<NT>(pz, red);
+    double Zm = block_sum2<NT>(pz, red);
     // ---- P13: Z_var = alpha' M alpha - beta' K_tl^-1 beta  (bq_c.pyx:342-351)
-    //   M_ij = h_l^4 h_tl^2 exp(N1_i + N1_j + N2_ij)          gauss_c.pyx:488-529 (d = 1); symmetric, evaluated for i <= j
     {
+        double quad;                                            // first term; `beta` receives the vector of the second
+        if (n_xo) {
+            // trapezoid versions (bq.py:256-266, :315-327): m_j = gp_l.mean(xo_j), g_j = wp_j m_j,
+            //   Z_mean = sum_j g_j                                                     bq_c.pyx:255-259
+            //   Z_var  = g' K_tl(xo, xo) g - (K_tl(x_s, xo) g)' K_tl^-1 (K_tl(x_s, xo) g)    bq_c.pyx:404-420 with
+            //            C_tl = gp_log_l.cov(xo) written out, so that the n_xo x n_xo matrix is never stored
+            for (int j = tid; j < n_xo; j += NT) {
+                const double xj = xo[j];
+                double m = 0.0;
+                for (int i = 0; i < n; ++i) m = fma(kernel_exp(xj - x_sc[i], nh_l, kind, hp_l), alpha[i], m);
+                gz[j] = wp[j] * (c_l * m);
+            }
+            __syncthreads();
+            double zp = 0.0;
+            for (int j = tid; j < n_xo; j += NT) zp += gz[j];
+            Zm = block_sum2<NT>(zp, red);
+            double acc = 0.0;
+            for (int i = warp; i < n_xo; i += NW) {
+                const double xi = xo[i];
+                double col = 0.0;
+                for (int j = lane; j <= i; j += 32) {
+                    const double kij = kernel_exp(xi - xo[j], nh_tl, kind, hp_tl);
+                    col = fma(gz[j], j < i ? 2.0 * kij : kij, col);
+                }
+                col = warp_sum(col);
+                if (lane == 0) acc = fma(col, gz[i], acc);
+            }
+            quad = c_tl * block_sum2<NT>(acc, red);
+            for (int i = warp; i < ns; i += NW) {
+                const double xi = x_sc[i];
+                double r = 0.0;
+                for (int j = lane; j < n_xo; j += 32) r = fma(kernel_exp(xi - xo[j], nh_tl, kind, hp_tl), gz[j], r);
+                r = warp_sum(r);
+                if (lane == 0) beta[i] = c_tl * r;
+            }
+            __syncthreads();
+            PH(19);
+        } else {
+        //   M_ij = h_l^4 h_tl^2 exp(N1_i + N1_j + N2_ij)          gauss_c.pyx:488-529 (d = 1); symmetric, evaluated for i <= j
         const double A_ = sig2 * ((sig2 / Lb) / Lb);            // cov (W1 + cov)^-1 cov     :496-500
         const double C2 = w_tl * w_tl + 2 * sig2 - 2 * A_;     // :515
         const double L2 = sqrt(C2), logdet2 = 2 * log(L2), rL2 = 1.0 / L2;
@@ -768,7 +833,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
             col = warp_sum(col);
             if (lane == 0) acc += col * alpha[j];
         }
-        const double aMa = block_sum2<NT>(acc, red);
+        quad = block_sum2<NT>(acc, red);
         PH(19);
         //   int_K1_K2[i, j] = h_tl^2 h_l^2 N([x_s_i, x_sc_j] | [mu, mu], [[w_tl^2 + cov, cov], [cov, w_l^2 + cov]])
         //   gauss_c.pyx:305-337 with the 2 x 2 Cholesky done in closed form
@@ -793,6 +858,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
             if (lane == 0) beta[i] = s;
         }
         __syncthreads();
+        }
         PH(20);
         // |L_tl^-1 beta|^2 = beta' K_tl^-1 beta, L_tl^-1 from its fragment-ordered copy (scaled by c_tl)
         double q = 0.0;
@@ -824,7 +890,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
         const double yKy_tl = block_sum2<NT>(y1, red), yKy_l = block_sum2<NT>(y2, red);
         if (tid == 0) {
             M[H_ZM] = Zm;
-            M[H_ZV] = aMa - beta2;
+            M[H_ZV] = quad - beta2;
             M[H_LOGLH] = (-0.5 * yKy_tl - sumlog_tl - 0.5 * ns * S2_LOG_2PI) + (-0.5 * yKy_l - sumlog_l - 0.5 * n * S2_LOG_2PI);
         }
     }
@@ -846,6 +912,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
         // isclose pre-filter of the scoring kernel: an upper bound of every tolerance squared
         M[H_TOL2MAX] = t2 * 1.000001;
         M[H_MU] = mu; M[H_THRESH] = thresh; M[H_BA_S] = BA_S;
+        M[H_KIND] = kind; M[H_HP_TL] = hp_tl; M[H_HP_L] = hp_l;
         // int_K at a new point: h^2 exp(-1/2 (log 2pi + logdet)) * exp(-1/2 diff^2 / var)  (gauss_c.pyx:110, :162)
         M[H_CB] = (h_l * h_l) * exp(-0.5 * (S2_LOG_2PI + logdet_b)); M[H_NHB] = -0.5 / var_b;
     }
@@ -867,12 +934,16 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
 #endif
 }
 
+template <bool TSMEM, int NT, int KIND>
+static cudaError_t launch_kind(const SetupArgs &a, int n_inst, size_t bytes, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(bq_setup2_kernel<TSMEM, NT, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    bq_setup2_kernel<TSMEM, NT, KIND><<<n_inst, NT, bytes, stream>>>(a);
+    return cudaGetLastError();
+}
 template <bool TSMEM, int NT>
 static cudaError_t launch_one(const SetupArgs &a, int n_inst, size_t bytes, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(bq_setup2_kernel<TSMEM, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return e;
-    bq_setup2_kernel<TSMEM, NT><<<n_inst, NT, bytes, stream>>>(a);
-    return cudaGetLastError();
+    return a.kind ? launch_kind<TSMEM, NT, 1>(a, n_inst, bytes, stream) : launch_kind<TSMEM, NT, 0>(a, n_inst, bytes, stream);
 }
 
 // a.n_max / a.nc_max must be >= ns + nc / nc of every instance of the launch (instances above report SETUP_BAD_INPUT)
@@ -883,8 +954,8 @@ cudaError_t launch_setup2(const SetupArgs &a, int n_inst, cudaStream_t stream) {
     if (bytes_sm <= cta_max) {
         // two CTAs of 256 threads per SM when two instances fit (their serial phases overlap), else one of 512
         int per_sm = 0;
-        cudaError_t e = cudaFuncSetAttribute(bq_setup2_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_sm);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bq_setup2_kernel<true, 256>, 256, bytes_sm);
+        cudaError_t e = cudaFuncSetAttribute(bq_setup2_kernel<true, 256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes_sm);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bq_setup2_kernel<true, 256, 0>, 256, bytes_sm);
         if (e != cudaSuccess) return e;
         // (a launch that does not fill the SMs once is a latency problem, not a throughput one: 512 threads per instance)
         int dev = 0, sms = 148;

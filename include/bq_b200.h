@@ -95,6 +95,17 @@ int bqb_batch_stage(bqb_batch *b, const int *ns, const double *x_s, const double
  * the hyper-parameter log-density costs (BQ._make_llh_params, bq.py:533-552: _set_gp_log_l_params :933-957 +
  * _set_gp_l_params :959-965 + gp.log_lh) -- no buffer is reallocated, nothing but 48 bytes per instance is uploaded. */
 int bqb_batch_set_hypers(bqb_batch *b, const double *hyp, void *stream);
+/* Non-Gaussian kernels and the trapezoid approximation.  Replaces gp.PeriodicKernel as used by bq.py:139-165 and
+ * bq_c.approx_Z_mean (bq_c.pyx:216-261), approx_Z_var (:358-422), approx_expected_squared_mean_and_mean (:538-598),
+ * i.e. what BQ does when options['use_approx'] is set (bq.py:251-252, :310-311, :498-510).
+ *   kernel_kind 0: gp.GaussianKernel(h, w);  1: gp.PeriodicKernel(h, w, p) with period[i] = {p of gp_log_l, p of gp_l}
+ *   n_xo > 0: the integrals over the prior are trapezoid sums over the grid xo with prior density p_xo (HOST arrays,
+ *             [n_xo] shared by all instances when xo_stride = 0, else [n_inst][xo_stride]); n_xo = 0: closed forms
+ *             (Gaussian kernel only).
+ *   force_generic != 0 runs the plain-FP64 scoring kernel even for the Gaussian / closed-form case (cross-checks).
+ * Takes effect at the next setup call; afterwards every scoring entry point except bqb_predict_* works as before. */
+int bqb_batch_set_approx(bqb_batch *b, int kernel_kind, const double *period, const double *xo, const double *p_xo, int n_xo,
+                         long long xo_stride, int force_generic);
 /* The setup half: runs the setup kernel on whatever is staged on the device (after bqb_batch_stage /
  * bqb_batch_add_observations / bqb_batch_draw_candidates).  Stands in for BQ.init (bq.py:132-171) of every
  * instance.  Synchronises `stream`. */

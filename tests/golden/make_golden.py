@@ -315,7 +315,58 @@ def main_edge():
     print("sample_hypers_c2: %d seeds x 4 samples, max cond per seed %s" % (seeds.size, np.array(conds)))
 
 
+
+def main_approx():
+    """Round-2 fixtures of the trapezoid path (`use_approx`, bq.py:251-252, :310-311, :498-510; bq_c.pyx:216-261, :358-422,
+    :538-598): the Gaussian fixture with use_approx switched on (the reference's own test does that,
+    tests/test_bq_object.py:179), and gp.PeriodicKernel problems (tests/util.py:76-91: von Mises likelihood and prior,
+    wrapped domain)."""
+    import logging
+    import scipy.special
+    logging.disable(logging.CRITICAL)
+    bqmod, gp = build_ref.import_reference()
+    BQ = bqmod.BQ
+
+    def rec_approx(bq, x_a, kind):
+        r = record(bq, x_a)
+        r.update(kind=kind, xo=np.array(bq._approx_x), p_xo=np.array(bq._approx_px), use_approx=1,
+                 wrapped=int(bool(bq.options["wrapped"])))
+        return r
+
+    # ---- 9. Gaussian kernel, integrals by the trapezoid rule
+    bq = fixture_bq(BQ, gp, (15, 2, 0.), (0.2, 1.3, 0.))
+    bq.options["use_approx"] = True
+    x_a = np.concatenate([np.linspace(-10, 10, 101), edge_points(bq)])
+    rec = rec_approx(bq, x_a, 0)
+    np.savez(os.path.join(OUT, "approx_gauss.npz"), **rec)
+    print("approx_gauss: Z_mean %.12g Z_var %.6g (exact: %.12g %.6g), nc=%d" % (rec["Z_mean"], rec["Z_var"], bq._exact_Z_mean(),
+                                                                              bq._exact_Z_var(), bq.nc))
+
+    # ---- 10. periodic kernel: (a) the reference's own test problem (tests/util.py:76-91), (b) narrower kernels and fewer
+    #      observations, so that candidates survive the filter and most points take the regular branch
+    def vmpdf(x, mu, kappa):
+        return np.exp(-np.log(2 * np.pi * scipy.special.iv(0, kappa)) + kappa * np.cos(x - mu))
+    for name, nobs, ptl, pl in (("periodic_a", 8, (5, 2 * np.pi, 1, 0.), (0.2, np.pi / 2., 1, 0.)),
+                                ("periodic_b", 5, (3, 1.2, 1, 0.), (0.3, 0.8, 1, 0.))):
+        np.random.seed(8728)
+        x = np.linspace(-np.pi, np.pi, nobs + 1)[:-1]
+        y = vmpdf(x, 0.1, 1.1)
+        bq = BQ(x, y, n_candidate=10, x_mean=0.0, x_var=10.0, candidate_thresh=0.5, kernel=gp.PeriodicKernel,
+                optim_method="L-BFGS-B")
+        bq.init(params_tl=ptl, params_l=pl)
+        x_a = np.concatenate([np.linspace(-np.pi, np.pi, 61), edge_points(bq)[:-5]])
+        rec = rec_approx(bq, x_a, 1)
+        np.savez(os.path.join(OUT, name + ".npz"), **rec)
+        moved = (~np.isclose(rec["esm"], rec["Z_mean"] ** 2, rtol=1e-12)).sum()
+        print("%s: ns=%d nc=%d Z_mean %.12g Z_var %.6g cond_l %.3g cond_tl %.3g; %d of %d points off the shortcut / fallback value" % (
+            name, bq.ns, bq.nc, rec["Z_mean"], rec["Z_var"], rec["cond_K_l"], rec["cond_K_tl"], moved, x_a.size))
+
+
 if __name__ == "__main__":
-    if "--edge-only" not in sys.argv:
-        main()
-    main_edge()
+    if "--approx-only" in sys.argv:
+        main_approx()
+    else:
+        if "--edge-only" not in sys.argv:
+            main()
+        main_edge()
+        main_approx()

@@ -1,0 +1,155 @@
+"""The generic device path (csrc/bq_score_generic.cu + the trapezoid / periodic modes of csrc/bq_setup2.cu): SURVEY 8(f).4,
+the reference's `use_approx` branch (bq.py:251-252, :310-311, :498-510; bq_c.pyx:216-261, :358-422, :538-598) and
+gp.PeriodicKernel.  Checked against fixtures produced by the unmodified reference (tests/golden/approx_gauss.npz,
+periodic_a.npz, periodic_b.npz), against the numpy oracle (oracle/approx.py) on seeded problems, and -- with the Gaussian
+kernel and closed-form integrals -- against the tensor-core kernels, which compute the same thing."""
+import numpy as np
+import pytest
+
+from conftest import ATOL, RTOL, assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from bayesian_quadrature_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def setup_generic(lib, g, kind=None, approx=True, force=False):
+    ns, nc = g["x_s"].size, g["x_c"].size
+    b = lib.Batch(1, ns)
+    ptl, pl = g["params_tl"], g["params_l"]
+    kind = int(g["kind"]) if kind is None else kind
+    hyp = np.array([ptl[0], ptl[1], ptl[-1], pl[0], pl[1], pl[-1]])
+    prior = np.array([float(g["x_mean"]), float(g["x_var"]), float(g["candidate_thresh"])])
+    b.set_approx(kind, period=[[ptl[2], pl[2]]] if kind else None, xo=g["xo"] if approx else None,
+                 p_xo=g["p_xo"] if approx else None, force_generic=force)
+    info = b.setup([ns], [nc], g["x_s"][None], g["l_s"][None], g["x_c"][None] if nc else np.zeros((1, 0)), hyp[None], prior[None])
+    assert info["status"][0] == lib.SETUP_OK
+    return b, info
+
+
+@pytest.mark.parametrize("name", ["fixture", "c1", "c2", "c5", "edge_noise"])
+def test_generic_kernel_equals_the_tensor_core_kernels(lib, name):
+    """Gaussian kernel, closed-form integrals: the plain-FP64 kernel against the DMMA kernels (dense cut-off) and the
+    reference's fixture -- scores, expected variance (fused epilogue) and status bits."""
+    g = dict(load_golden(name))
+    g["kind"], g["xo"], g["p_xo"] = 0, None, None
+    b0, _ = setup_generic(lib, g, approx=False, force=False)
+    b0.set_cutoff(float("inf"))
+    b1, _ = setup_generic(lib, g, approx=False, force=True)
+    x_a = np.concatenate([g["x_a"], [np.nan, np.inf]])
+    e0, m0, s0 = b0.score_host(x_a)
+    e1, m1, s1 = b1.score_host(x_a)
+    ok = np.isfinite(x_a)
+    assert (s0 == s1).all()
+    assert_close(e1[0][ok], e0[0][ok], name + " esm generic vs tensor-core", rtol=1e-9, atol=1e-300)
+    assert_close(m1[0][ok], m0[0][ok], name + " em generic vs tensor-core", rtol=1e-9, atol=1e-300)
+    assert_close(e1[0][:g["x_a"].size], g["esm"], name + " esm generic vs reference")
+    ev0, f0 = b0.expected_var_host(g["x_a"])
+    ev1, f1 = b1.expected_var_host(g["x_a"])
+    assert f0 == f1
+    assert_close(ev1, ev0, name + " expected variance", rtol=1e-9, atol=1e-9 * float(np.abs(g["esm"]).max()))
+    with pytest.raises(NotImplementedError):
+        b1.predict_host(g["x_a"][:4])
+    b0.close(); b1.close()
+
+
+@pytest.mark.parametrize("name", ["approx_gauss", "periodic_a", "periodic_b"])
+def test_trapezoid_path_vs_reference_fixture(lib, name):
+    g = load_golden(name)
+    b, info = setup_generic(lib, g)
+    nc = g["x_c"].size
+    if nc:
+        assert_close(info["l_c"][0, :nc], g["l_c"], name + " l_c")
+    assert_close(info["Z_mean"][0], g["Z_mean"], name + " Z_mean")
+    # Z_var = g' K_tl(xo, xo) g - r' K_tl^-1 r cancels to rounding noise when gp_log_l is nearly deterministic: the reference's
+    # explicit-inverse route leaves cond * eps * (scale of the terms) there (-1.6e-9 at cond 4.7e8 in periodic_a)
+    ptl = g["params_tl"]
+    k0 = ptl[0] ** 2 if int(g["kind"]) else ptl[0] ** 2 / (np.sqrt(2 * np.pi) * ptl[1])
+    tol = max(1e-13, 10 * float(g["cond_K_tl"]) * np.finfo(np.float64).eps * float(g["Z_mean"]) ** 2 * k0)
+    assert abs(info["Z_var"][0] - float(g["Z_var"])) < tol, (info["Z_var"][0], float(g["Z_var"]), tol)
+    assert abs(info["log_lh"][0] - float(g["log_lh"])) <= 1e-8 * abs(float(g["log_lh"]))
+    esm, em, st = b.score_host(g["x_a"])
+    assert ((st[0] & lib.ST_SHORTCUT) == g["shortcut"]).all()
+    assert not (st[0] & (lib.ST_ESM_BAD | lib.ST_EM_BAD | lib.ST_XA_BAD)).any()
+    assert_close(esm[0], g["esm"], name + " esm")
+    assert_close(em[0], g["em"], name + " em")
+    ev, _ = b.expected_var_host(g["x_a"])
+    assert_close(ev, g["expected_Z_var"], name + " expected_Z_var", atol=max(ATOL, tol))
+    b.close()
+
+
+@pytest.mark.parametrize("kind,ns,seed", [(1, 6, 0), (1, 12, 1), (0, 20, 2), (1, 40, 3), (0, 70, 4)])
+def test_trapezoid_path_vs_numpy_oracle(lib, kind, ns, seed):
+    """Seeded problems of several sizes (one and two capacity classes), with candidates, both kernels."""
+    from oracle import approx
+    rs = np.random.RandomState(seed)
+    if kind:
+        x_s = np.sort(rs.uniform(-np.pi, np.pi, ns))
+        x_s = np.linspace(-np.pi, np.pi, ns + 1)[:-1] + rs.uniform(-0.05, 0.05, ns)
+        l_s = np.exp(1.1 * np.cos(x_s - 0.1)) * rs.uniform(0.8, 1.2, ns) * 0.1
+        gap = 2 * np.pi / ns
+        ptl, pl = (3.0, 1.6 * gap, 1.0, 0.0), (0.3, 1.2 * gap, 1.0, 0.0)    # widths follow the spacing (cond ~1e4)
+        x_c = (x_s[:-1] + gap / 2)[rs.choice(ns - 1, size=min(3, ns - 1), replace=False)] if gap > 1.0 else np.zeros(0)
+        xo = np.linspace(-np.pi, np.pi, 400)
+        from scipy.special import j0
+        p_xo = np.exp(-np.log(2 * np.pi * j0(0.1)) + 0.1 * np.cos(xo))
+        mu, var = 0.0, 10.0
+    else:
+        x_s = 1.25 * (np.arange(ns) - (ns - 1) / 2.0) + rs.uniform(-0.1, 0.1, ns)
+        l_s = np.exp(-0.5 * (x_s / (0.2 * np.ptp(x_s))) ** 2) * rs.uniform(0.5, 1.5, ns) * 0.3 + 1e-3
+        ptl, pl = (6.0, 1.5, 0.0), (0.4, 1.1, 0.0)
+        x_c = np.sort(x_s[rs.choice(ns - 1, size=3, replace=False)] + 0.625)
+        xo = np.linspace(x_s.min() - 3, x_s.max() + 3, 700)
+        mu, var = 0.3, float(np.ptp(x_s) ** 2 / 9)
+        p_xo = np.exp(-0.5 * (np.log(2 * np.pi * var) + (xo - mu) ** 2 / var))
+    x_c = np.sort(x_c)
+    m = approx.ApproxModel(x_s, l_s, x_c, ptl, pl, mu, var, 0.5, kind, xo, p_xo)
+    g = dict(x_s=x_s, l_s=l_s, x_c=x_c, params_tl=np.array(ptl), params_l=np.array(pl), x_mean=mu, x_var=var,
+             candidate_thresh=0.5, kind=kind, xo=xo, p_xo=p_xo)
+    b, info = setup_generic(lib, g)
+    assert_close(info["Z_mean"][0], m.Z_mean(), "Z_mean")
+    assert abs(info["Z_var"][0] - m.Z_var()) < 1e-12 * max(1.0, m.Z_mean() ** 2 * 1e3)
+    lo, hi = xo[0], xo[-1]
+    x_a = np.concatenate([rs.uniform(lo, hi, 150), x_s[:4], x_s[:4] + 0.9e-4, x_s[:4] + 1.2e-4, x_c, x_c + 0.3, x_c - 0.499])
+    esm, em, st = b.score_host(x_a)
+    o_esm, o_em, o_st = m.esm_and_em(x_a)
+    assert ((st[0] & 3) == (o_st & 3)).all()
+    assert_close(esm[0], o_esm, "esm kind=%d ns=%d" % (kind, ns))
+    assert_close(em[0], o_em, "em kind=%d ns=%d" % (kind, ns))
+    b.close()
+
+
+def test_bq_object_with_the_periodic_kernel():
+    """The public class end to end (tests/util.py:76-91 of the reference: von Mises likelihood, wrapped domain, prior
+    normalised as the reference does): same candidates, Z_mean, Z_var and scores as the reference's own run, and
+    choose_next / add_observation keep working (tests/test_bq_object.py:303-350, :387-395)."""
+    from scipy.special import iv
+    from bayesian_quadrature_b200 import BQ, PeriodicKernel
+    g = load_golden("periodic_b")
+    np.random.seed(8728)
+    x = np.linspace(-np.pi, np.pi, 6)[:-1]
+    y = np.exp(-np.log(2 * np.pi * iv(0, 1.1)) + 1.1 * np.cos(x - 0.1))
+    bq = BQ(x, y, n_candidate=10, x_mean=0.0, x_var=10.0, candidate_thresh=0.5, kernel=PeriodicKernel, optim_method="L-BFGS-B")
+    bq.init(params_tl=(3, 1.2, 1, 0.), params_l=(0.3, 0.8, 1, 0.))
+    assert bq.options["use_approx"] and bq.options["wrapped"]
+    assert np.array_equal(bq.x_c, g["x_c"])
+    assert_close(bq._approx_x, g["xo"], "approximation grid")
+    assert_close(bq._approx_px, g["p_xo"], "prior on the grid")
+    assert_close(bq.l_c, g["l_c"], "l_c")
+    assert_close(bq.Z_mean(), g["Z_mean"], "Z_mean")
+    assert abs(bq.Z_var() - float(g["Z_var"])) < 1e-12
+    assert_close(bq.expected_squared_mean(g["x_a"]), g["esm"], "expected_squared_mean")
+    assert_close(bq.expected_mean(g["x_a"]), g["em"], "expected_mean")
+    assert_close(bq.expected_Z_var(g["x_a"]), g["expected_Z_var"], "expected_Z_var", atol=max(ATOL, 1e-13))
+    assert_close(bq.l_mean(g["x_a"][:7]), bq.gp_l.mean(g["x_a"][:7]), "l_mean (host GPs)")
+    grid = np.linspace(-np.pi, np.pi, 101)
+    nxt = bq.choose_next(grid, n=2, params=["h", "w"])
+    assert nxt in grid
+    ns0 = bq.ns
+    bq.add_observation(float(nxt), float(np.exp(-np.log(2 * np.pi * iv(0, 1.1)) + 1.1 * np.cos(nxt - 0.1))))
+    assert bq.ns in (ns0, ns0 + 1) and np.isfinite(bq.Z_mean())

@@ -33,13 +33,21 @@ def test_constructor_validation():
     assert bq.options["x_mean"].shape == (1,) and bq.options["x_cov"].shape == (1, 1)
 
 
-def test_non_gaussian_kernel_is_refused_loudly():
+def test_non_gaussian_kernel_options_and_prior():
+    """gp.PeriodicKernel selects the trapezoid path on a wrapped domain (bq.py:124-125); the prior on the approximation
+    grid is the reference's von Mises density, normalised with libc's j0 as bq_c.pyx:31-60 does (tests/golden/periodic_b.npz
+    holds the grid and density the unmodified reference produced).  Without a GPU the device pass of init fails loudly."""
+    from conftest import load_golden
+    g = load_golden("periodic_b")
     opt = dict(OPTIONS, kernel=PeriodicKernel)
     x = np.linspace(-3, 3, 8)
     bq = BQ(x, np.ones_like(x), **opt)
     assert bq.options["use_approx"] and bq.options["wrapped"]
-    with pytest.raises(NotImplementedError):
-        bq.init((5, 6.0, 1, 0), (0.2, 1.5, 1, 0))
+    np.testing.assert_allclose(bq._make_approx_px(g["xo"]), g["p_xo"], rtol=1e-13)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            bq.init((5, 6.0, 1, 0), (0.2, 1.5, 1, 0))
 
 
 def test_filter_candidates_matches_reference_fixture_draw():
