@@ -413,7 +413,7 @@ static cudaError_t score_dispatch(bqb_batch *b, ScoreArgs &a, int n_inst, cudaSt
         a.xo = b->d_xo; a.wp = b->d_wp; a.n_xo = b->n_xo; a.xo_stride = b->xo_stride;
         return launch_score_generic(a, n_inst, s, grid_x);
     }
-    return score_dispatch(b, a, n_inst, s, grid_x);
+    return launch_score(a, n_inst, b->sm_count, s, grid_x);
 }
 
 static int check_ready(bqb_batch *b, const char *who) {
