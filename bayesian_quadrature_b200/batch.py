@@ -89,7 +89,7 @@ class BatchBQ(object):
         self._ns_max = ns0                                 # upper bound of ns over the problems (device mode)
         # capacity class chosen for ns0 + ns_reserve from the start (both modes, so that they run the same kernels): a
         # batch that is known to grow does not migrate to the next class after the first appended observation
-        self._class_hint = min(self.cap, 256)
+        self._class_hint = min(self.cap, 512)
         self.device = int(device)
         self.batch = None
         self.x_c = np.zeros((self.P, _lib.NC_MAX))
@@ -114,7 +114,7 @@ class BatchBQ(object):
         if self.batch is None:                             # first call: upload the observations, seed the generators
             cap_class = _lib.load().bqb_ns_capacity(max(int(self._ns_max), self._class_hint))
             if cap_class < 0:
-                raise NotImplementedError("more than 256 observations per problem")
+                raise NotImplementedError("more than 512 observations per problem")
             self.batch = _lib.Batch(self.P, cap_class, device=self.device)
             self._cap_class = cap_class
             stride = min(self.cap, cap_class)
@@ -145,7 +145,7 @@ class BatchBQ(object):
         old_cap = self.batch.capacity
         cap_class = _lib.load().bqb_ns_capacity(old_cap + 1)
         if cap_class < 0:
-            raise NotImplementedError("more than 256 observations per problem")
+            raise NotImplementedError("more than 512 observations per problem")
         self.batch.close()
         self.batch = _lib.Batch(self.P, cap_class, device=self.device)
         self._cap_class = cap_class
@@ -167,7 +167,7 @@ class BatchBQ(object):
         self.x_c[:, :self.n_candidate] = np.nan_to_num(xc, nan=0.0)
         cap_class = _lib.load().bqb_ns_capacity(max(int(self.ns.max()), self._class_hint))
         if cap_class < 0:
-            raise NotImplementedError("more than 256 observations per problem")
+            raise NotImplementedError("more than 512 observations per problem")
         if self.batch is None or self._cap_class != cap_class:       # crossed a kernel capacity class: new device batch
             self.close()
             self.batch = _lib.Batch(self.P, cap_class, device=self.device)

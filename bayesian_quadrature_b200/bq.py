@@ -284,8 +284,8 @@ class BQ(object):
     def _predict(self, x):
         """(gp_l.mean(x), diag gp_log_l.cov(x)) for a vector of points in one device pass; None when the device factors
         do not apply (noisy gp_l: they are those of the noise-free bordered matrix) and the host GPs must answer."""
-        if self.options["use_approx"] or self.gp_l.get_param("s") != 0:
-            return None
+        if self.options["use_approx"] or self.gp_l.get_param("s") != 0 or self.ns > 256:
+            return None                                  # (the generic kernel has no prediction mode)
         x = np.ascontiguousarray(x, dtype=DTYPE)
         if x.ndim != 1 or not np.isfinite(x).all():
             return None

@@ -62,6 +62,7 @@ struct bqb_batch {
     int kind = 0, n_xo = 0;
     long long xo_stride = 0;
     bool generic = false;
+    bool big_class = false;            // capacity 512: no tensor-core scoring kernels, no first-generation setup kernel
     double *d_period = nullptr, *d_xo = nullptr, *d_pxo = nullptr, *d_wp = nullptr, *d_gz = nullptr;
     // scoring: relevance cut-off (bq_score.cu, CUT_ARG; +inf = dense) and the optional executed-work counter
     double cut_arg = 72.0;
@@ -111,13 +112,14 @@ int bqb_ns_capacity(int ns) {
     if (ns <= 128) return 128;
     if (ns <= 160) return 160;
     if (ns <= 256) return 256;
+    if (ns <= 512) return 512;          // generic (plain FP64) scoring kernel only: the tensor-core kernels' k-step masks end at 256
     return BQB_EUNSUPPORTED;
 }
 
 int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     if (!out || n_inst < 1) return fail(BQB_EINVAL, "bqb_batch_create: bad arguments");
     const int cap = bqb_ns_capacity(ns_max);
-    if (cap < 0) return fail(cap, "bqb_batch_create: ns_max outside the supported range [1, 256]");
+    if (cap < 0) return fail(cap, "bqb_batch_create: ns_max outside the supported range [1, 512]");
     CU(cudaSetDevice(device));
     bqb_batch *b = new bqb_batch();
     b->device = device; b->n_inst = n_inst; b->ns_cap = cap; b->lay = make_layout(cap);
@@ -136,6 +138,13 @@ int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     b->n_cap = cap + NC_MAX;
     b->work_stride = 4 * (size_t)b->n_cap * b->n_cap + 32 * (size_t)b->n_cap;
     b->work_inst = n_inst < 2048 ? n_inst : 2048;
+    if (cap > 256) {
+        // 257 .. 512 observations: second-generation setup kernel with its packed triangle in this scratch, generic scoring
+        b->big_class = true;
+        b->generic = true;
+        b->work_stride = ((size_t)b->n_cap * (b->n_cap + 1) / 2 + 64) & ~(size_t)1;
+        if (b->work_inst > 256) b->work_inst = 256;
+    }
     CU(cudaMalloc(&b->d_work, sizeof(double) * b->work_stride * b->work_inst));
     CU(cudaMalloc(&b->d_ns, sizeof(int) * n_inst));
     CU(cudaMalloc(&b->d_nc, sizeof(int) * n_inst));
@@ -198,7 +207,8 @@ static int run_setup(bqb_batch *b, int check_max, cudaStream_t s) {
     a.n_max = n_max; a.nc_max = nc_max;
     a.kind = b->kind; a.period = b->d_period; a.xo = b->d_xo; a.pxo = b->d_pxo; a.n_xo = b->n_xo; a.xo_stride = b->xo_stride;
     a.wp = b->d_wp; a.gz = b->d_gz;
-    if (v1 && (b->kind || b->n_xo)) return fail(BQB_EUNSUPPORTED, "BQB_SETUP_V1: the first-generation setup kernel has no periodic kernel / trapezoid mode");
+    if (v1 && (b->kind || b->n_xo || b->big_class))
+        return fail(BQB_EUNSUPPORTED, "BQB_SETUP_V1: the first-generation setup kernel has no periodic kernel / trapezoid mode and ends at 256 observations");
     for (int i0 = 0; i0 < B; i0 += b->work_inst) {
         const int cnt = (B - i0 < b->work_inst) ? B - i0 : b->work_inst;
         a.inst0 = i0;
@@ -302,7 +312,7 @@ int bqb_batch_set_approx(bqb_batch *b, int kernel_kind, const double *period, co
         CU(cudaMalloc(&b->d_gz, sizeof(double) * (size_t)b->work_inst * (size_t)n_xo));
     }
     b->kind = kernel_kind; b->n_xo = n_xo; b->xo_stride = xo_stride;
-    b->generic = kernel_kind != 0 || n_xo > 0 || force_generic != 0;
+    b->generic = kernel_kind != 0 || n_xo > 0 || force_generic != 0 || b->big_class;
     b->ready = false;
     return 0;
 }

@@ -351,16 +351,18 @@ __device__ void lower_matvec_p(const double *T, int n, const double *v1, double 
     __syncthreads();
 }
 
-// o1[c] = sum_{i >= c} X[i][c] v1[i], the same for v2 -> o2 when given; one thread per column, n <= 256
-// (NT = 512: both right-hand sides at once, threads 0 .. 255 and 256 .. 511)
+// o1[c] = sum_{i >= c} X[i][c] v1[i], the same for v2 -> o2 when given; one thread per column
+// (NT = 512 and n <= 256: both right-hand sides at once, threads 0 .. 255 and 256 .. 511)
 template <int NT>
 __device__ void lower_matvec_t_p(const double *T, int n, const double *v1, double *o1, const double *v2, double *o2) {
-    const int c = threadIdx.x & 255;
-    for (int h0 = 0; h0 < 2; h0 += NT / 256) {
-        const int half = h0 + (threadIdx.x >> 8);
+    const bool split = NT == 512 && n <= 256;
+    const int cols = split ? 256 : NT;
+    for (int h0 = 0; h0 < 2; h0 += split ? 2 : 1) {
+        const int half = split ? (int)(threadIdx.x >> 8) : h0;
         const double *v = half ? v2 : v1;
         double *o = half ? o2 : o1;
-        if (c < n && v != nullptr) {
+        if (v == nullptr) continue;
+        for (int c = split ? (int)(threadIdx.x & 255) : (int)threadIdx.x; c < n; c += cols) {
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
             int i = c;
             for (; i + 3 < n; i += 4) {

@@ -24,7 +24,7 @@ extern "C" {
 #endif
 
 #define BQB_EINVAL (-1)        /* bad argument (reference: ValueError) */
-#define BQB_EUNSUPPORTED (-2)  /* outside device limits: ns > 256, nc > 16, not sm_100 */
+#define BQB_EUNSUPPORTED (-2)  /* outside device limits: ns > 512, nc > 16, not sm_100 */
 #define BQB_ESTATE (-3)        /* batch not set up */
 #define BQB_ENUMERIC (-4)      /* an instance failed setup (reference: numpy.linalg.LinAlgError) */
 
@@ -54,7 +54,8 @@ const char *bqb_last_error(void);
 int bqb_version(void);
 int bqb_device_count(int *count);
 
-/* Padded observation capacity the library would use for `ns` observations (16, 64, 128, 160 or 256), or
+/* Padded observation capacity the library would use for `ns` observations (16, 64, 128, 160, 256, or 512: the last class
+ * runs on the generic plain-FP64 scoring kernel only, see bqb_batch_set_approx), or
  * BQB_EUNSUPPORTED. */
 int bqb_ns_capacity(int ns);
 

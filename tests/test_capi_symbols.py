@@ -41,7 +41,8 @@ def test_capacity_and_argument_errors_without_gpu():
     assert L.bqb_ns_capacity(17) == 64 and L.bqb_ns_capacity(64) == 64
     assert L.bqb_ns_capacity(65) == 128 and L.bqb_ns_capacity(129) == 160 and L.bqb_ns_capacity(161) == 256
     assert L.bqb_ns_capacity(256) == 256
-    assert L.bqb_ns_capacity(257) == _lib.EUNSUPPORTED
+    assert L.bqb_ns_capacity(257) == 512 and L.bqb_ns_capacity(512) == 512      # generic scoring kernel only
+    assert L.bqb_ns_capacity(513) == _lib.EUNSUPPORTED
     assert L.bqb_ns_capacity(0) == _lib.EINVAL
     assert L.bqb_batch_create(None, 0, 1, 8) == _lib.EINVAL
     assert b"bad arguments" in L.bqb_last_error()
