@@ -187,3 +187,34 @@ def test_more_than_256_observations_run_on_the_generic_kernel(lib, oracle, ns, n
     assert np.isfinite(ev).all()
     m.close()
     b.close()
+
+
+def test_per_instance_grids_and_periods(lib):
+    """A batch whose instances carry their own approximation grid (xo_stride > 0), period and hyper-parameters gives,
+    instance by instance, exactly what single-instance batches give."""
+    g = load_golden("periodic_b")
+    ns, nc = g["x_s"].size, g["x_c"].size
+    ptl, pl = g["params_tl"], g["params_l"]
+    B = 3
+    hyp = np.array([[ptl[0] * (1 + 0.1 * i), ptl[1] * (1 + 0.05 * i), 0.0, pl[0], pl[1] * (1 - 0.05 * i), 0.0] for i in range(B)])
+    period = np.array([[1.0 + 0.1 * i, 1.0 + 0.05 * i] for i in range(B)])
+    xo = np.stack([np.linspace(-np.pi * (1 + 0.1 * i), np.pi * (1 + 0.1 * i), g["xo"].size) for i in range(B)])
+    p_xo = np.stack([np.interp(xo[i], g["xo"], g["p_xo"]) for i in range(B)])
+    prior = np.tile([float(g["x_mean"]), float(g["x_var"]), float(g["candidate_thresh"])], (B, 1))
+    x_a = np.linspace(-3, 3, 257)
+    b = lib.Batch(B, ns)
+    b.set_approx(1, period=period, xo=xo, p_xo=p_xo)
+    info = b.setup(np.full(B, ns), np.full(B, nc), np.tile(g["x_s"], (B, 1)), np.tile(g["l_s"], (B, 1)), np.tile(g["x_c"], (B, 1)),
+                   hyp, prior)
+    assert (info["status"] == 0).all()
+    esm, em, st = b.score_host(x_a)
+    for i in range(B):
+        b1 = lib.Batch(1, ns)
+        b1.set_approx(1, period=period[i:i + 1], xo=xo[i], p_xo=p_xo[i])
+        i1 = b1.setup([ns], [nc], g["x_s"][None], g["l_s"][None], g["x_c"][None], hyp[i:i + 1], prior[i:i + 1])
+        e1, m1, s1 = b1.score_host(x_a)
+        assert i1["Z_mean"][0] == info["Z_mean"][i] and i1["Z_var"][0] == info["Z_var"][i]
+        assert np.array_equal(e1[0], esm[i]) and np.array_equal(m1[0], em[i]) and np.array_equal(s1[0], st[i])
+        b1.close()
+    assert not np.array_equal(esm[0], esm[1])
+    b.close()
