@@ -406,7 +406,7 @@ __device__ __forceinline__ double mvn_logpdf1r(double x, double m, double rL, do
     return -0.5 * ((S2_LOG_2PI + logdet) + diff * buf);
 }
 
-// -DBQB_SETUP_PROF: CTA 0 prints the clock64() count of every phase (scratch/setup_prof2.py)
+// -DBQB_SETUP_PROF: CTA 0 prints the clock64() count of every phase (bench_micro/setup_prof2.py)
 #ifdef BQB_SETUP_PROF
 #define PH(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) s_prof[i] = clock64(); } while (0)
 #else
