@@ -123,10 +123,13 @@ int bqb_batch_create(bqb_batch **out, int device, int n_inst, int ns_max) {
     CU(cudaSetDevice(device));
     bqb_batch *b = new bqb_batch();
     b->device = device; b->n_inst = n_inst; b->ns_cap = cap; b->lay = make_layout(cap);
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) { delete b; return fail(BQB_EUNSUPPORTED, "bqb_batch_create: needs an sm_100a device (B200)"); }
-    b->sm_count = prop.multiProcessorCount;
+    // (two attribute queries, not cudaGetDeviceProperties: that call alone took 15-20 ms per batch on this pool's hosts,
+    // more than everything else a hyper-parameter batch of choose_next does)
+    int cc_major = 0, sm_count = 0;
+    CU(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (cc_major < 10) { delete b; return fail(BQB_EUNSUPPORTED, "bqb_batch_create: needs an sm_100a device (B200)"); }
+    b->sm_count = sm_count;
     CU(cudaMalloc(&b->d_models, sizeof(double) * (size_t)n_inst * b->lay.total));
     CU(cudaMalloc(&b->d_tab, sizeof(double) * (2048 + 512)));
     std::vector<double> tab(2048 + 512);

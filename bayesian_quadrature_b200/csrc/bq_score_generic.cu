@@ -16,9 +16,23 @@ namespace bqb {
 constexpr int GEN_THREADS = 32;
 constexpr int GEN_MAX_GRID = 2048;            // the fused epilogue leaves one (min, index) partial per CTA
 
-__device__ __forceinline__ int frag_index(int r, int k) {          // element (r, k) of a triangular fragment-ordered operand
+// sum_{k <= r} F[r][k] e[k] for row r of a triangular fragment-ordered operand: a k-step is four consecutive doubles of the
+// row (32-byte aligned: two 16-byte warp-uniform loads); entries with k > r are stored as zeros, so whole k-steps are used
+// (the e buffer is zero for k >= ns)
+__device__ __forceinline__ double tri_row_dot(const double *F, int r, const double *s_e, int lane) {
     const int rb = r >> 3;
-    return ((rb * (rb + 1) + (k >> 2)) << 5) + ((r & 7) << 2) + (k & 3);
+    const double2 *row = reinterpret_cast<const double2 *>(F + ((rb * (rb + 1)) << 5) + ((r & 7) << 2));
+    const double *e = s_e + lane;
+    double s0 = 0.0, s1 = 0.0;
+    for (int ks = 0; ks <= (r >> 2); ++ks) {
+        const double2 f01 = row[ks << 4], f23 = row[(ks << 4) + 1];
+        const double *ek = e + (ks << 2) * GEN_THREADS;
+        s0 = fma(f01.x, ek[0], s0);
+        s1 = fma(f01.y, ek[GEN_THREADS], s1);
+        s0 = fma(f23.x, ek[2 * GEN_THREADS], s0);
+        s1 = fma(f23.y, ek[3 * GEN_THREADS], s1);
+    }
+    return s0 + s1;
 }
 
 __global__ void __launch_bounds__(GEN_THREADS) bq_score_generic_kernel(ScoreArgs a) {
@@ -47,6 +61,7 @@ __global__ void __launch_bounds__(GEN_THREADS) bq_score_generic_kernel(ScoreArgs
     double best_v = INFINITY;
     long long best_i = 0x7fffffffffffffffLL;
     int cta_st = 0;
+    for (int k = ns; k < nsp; ++k) s_e[k * GEN_THREADS + lane] = 0.0;      // padding of the last k-step
     for (long long t0 = (long long)blockIdx.x * GEN_THREADS; t0 < a.na; t0 += (long long)gridDim.x * GEN_THREADS) {
         const long long p = t0 + lane;
         const bool live = p < a.na;
@@ -62,21 +77,21 @@ __global__ void __launch_bounds__(GEN_THREADS) bq_score_generic_kernel(ScoreArgs
         }
         double qs = 0.0;
         for (int r = 0; r < ns; ++r) {
-            double s0 = 0.0, s1 = 0.0;
-            int k = 0;
-            for (; k + 1 <= r; k += 2) {
-                s0 = fma(Fl[frag_index(r, k)], s_e[k * GEN_THREADS + lane], s0);
-                s1 = fma(Fl[frag_index(r, k + 1)], s_e[(k + 1) * GEN_THREADS + lane], s1);
-            }
-            if (k <= r) s0 = fma(Fl[frag_index(r, k)], s_e[k * GEN_THREADS + lane], s0);
-            const double v = s0 + s1;
+            const double v = tri_row_dot(Fl, r, s_e, lane);
             qs = fma(v, v, qs);
         }
         for (int r = 0; r < nc + 2; ++r) {
-            double s = 0.0;
-            const double *row = Fd + (((r >> 3) * nks) << 5) + ((r & 7) << 2);
-            for (int k = 0; k < ns; ++k) s = fma(row[((k >> 2) << 5) + (k & 3)], s_e[k * GEN_THREADS + lane], s);
-            s_dr[r][lane] = s;
+            const double2 *row = reinterpret_cast<const double2 *>(Fd + (((r >> 3) * nks) << 5) + ((r & 7) << 2));
+            double s0 = 0.0, s1 = 0.0;
+            for (int ks = 0; ks < nks; ++ks) {                     // columns k >= ns are stored as zeros
+                const double2 f01 = row[ks << 4], f23 = row[(ks << 4) + 1];
+                const double *ek = s_e + lane + (ks << 2) * GEN_THREADS;
+                s0 = fma(f01.x, ek[0], s0);
+                s1 = fma(f01.y, ek[GEN_THREADS], s1);
+                s0 = fma(f23.x, ek[2 * GEN_THREADS], s0);
+                s1 = fma(f23.y, ek[3 * GEN_THREADS], s1);
+            }
+            s_dr[r][lane] = s0 + s1;
         }
         // ---- K_tl pass: tm = k_t . a_tl, qt = |L_tl^-1 k_t|^2
         double tmv = 0.0;
@@ -87,14 +102,7 @@ __global__ void __launch_bounds__(GEN_THREADS) bq_score_generic_kernel(ScoreArgs
         }
         double qt = 0.0;
         for (int r = 0; r < ns; ++r) {
-            double s0 = 0.0, s1 = 0.0;
-            int k = 0;
-            for (; k + 1 <= r; k += 2) {
-                s0 = fma(Ft[frag_index(r, k)], s_e[k * GEN_THREADS + lane], s0);
-                s1 = fma(Ft[frag_index(r, k + 1)], s_e[(k + 1) * GEN_THREADS + lane], s1);
-            }
-            if (k <= r) s0 = fma(Ft[frag_index(r, k)], s_e[k * GEN_THREADS + lane], s0);
-            const double v = s0 + s1;
+            const double v = tri_row_dot(Ft, r, s_e, lane);
             qt = fma(v, v, qt);
         }
         // ---- tail (the branches of bq.py:447-527 / bq_c.pyx:425-490; same order of operations as bq_score.cu)

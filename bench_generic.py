@@ -58,6 +58,18 @@ def main():
             d_esm = bq.expected_squared_mean(sub)
             out["max_rel_diff_vs_reference"] = float(np.max(np.abs(d_esm - r_esm) / np.abs(r_esm)))
         print(json.dumps(out), flush=True)
+    # more than 256 observations: Gaussian kernel, closed forms, capacity class 512 (generic kernel, dense algorithm)
+    from bayesian_quadrature_b200 import GaussianKernel, synthetic
+    for ns in (300, 512):
+        bq = synthetic.make_bq(BQ, GaussianKernel, ns)
+        x_a = synthetic.query_grid(ns, 10 ** 5)
+        bq.expected_squared_mean(x_a[:1000])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bq.expected_squared_mean(x_a)
+        dt = time.perf_counter() - t0
+        print(json.dumps({"case": "Gaussian kernel, %d observations (capacity class 512, generic kernel), 10^5 points" % ns,
+                          "cuda_s": dt, "cuda_evals_per_s": 10 ** 5 / dt}), flush=True)
 
 
 if __name__ == "__main__":
