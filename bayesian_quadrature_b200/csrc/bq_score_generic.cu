@@ -3,9 +3,12 @@
 // int_K for non-Gaussian kernels (`use_approx`, bq.py:498-510 -> bq_c.approx_expected_squared_mean_and_mean
 // bq_c.pyx:538-598: int_K[i] = trapz(K_l(x_i, xo) p(xo))).
 //
-// One thread per query point, plain FP64: the cross-kernel vector of the point is kept in shared memory ([k][lane],
-// conflict free), the operands c L^-1 (fragment order, as the tensor-core kernels read them) come from global memory
-// as warp-uniform loads.  This is the reference's *slow* path (its own cost is n_xo = 1000 kernel evaluations per query
+// A CTA of eight warps works on a tile of 32 query points, lane = point, plain FP64: the cross-kernel vectors of the 32
+// points are kept in shared memory ([k][lane], conflict free) and shared by the warps, which split the rows of c L^-1
+// (fragment order, as the tensor-core kernels read them; warp-uniform 16-byte loads from global memory), the dense rows, the
+// fill of the cross-kernel vectors and the trapezoid sum; warp 0 combines the partial sums in a fixed order and runs the
+// per-point tail.  (The first version gave every point ONE thread and a warp its own [k][32] buffer: one warp per SM at 512
+// observations, 59 % of the stall samples on the operand loads, FP64 pipe 1.5 % busy -- profiles/ncu_generic_r02.md.)  This is the reference's *slow* path (its own cost is n_xo = 1000 kernel evaluations per query
 // point in a Python loop); the kernel is meant to be correct and complete, not at a roofline: ~n^2 FMA + n_xo
 // kernel evaluations per point.  With the Gaussian kernel and n_xo = 0 it computes exactly what bq_score.cu computes
 // (dense algorithm), which is how tests/test_gpu_generic.py validates it.
@@ -13,7 +16,8 @@
 
 namespace bqb {
 
-constexpr int GEN_THREADS = 32;
+constexpr int GEN_THREADS = 32;              // points per tile (= lanes)
+constexpr int GEN_WARPS = 8;                 // warps of a CTA: they share the tile
 constexpr int GEN_MAX_GRID = 2048;            // the fused epilogue leaves one (min, index) partial per CTA
 
 // sum_{k <= r} F[r][k] e[k] for row r of a triangular fragment-ordered operand: a k-step is four consecutive doubles of the
@@ -35,11 +39,13 @@ __device__ __forceinline__ double tri_row_dot(const double *F, int r, const doub
     return s0 + s1;
 }
 
-__global__ void __launch_bounds__(GEN_THREADS) bq_score_generic_kernel(ScoreArgs a) {
-    extern __shared__ double s_e[];                                  // [nsp][32] cross-kernel exponentials of the warp's points
+__global__ void __launch_bounds__(GEN_THREADS * GEN_WARPS) bq_score_generic_kernel(ScoreArgs a) {
+    extern __shared__ double s_e[];                                  // [nsp][32] cross-kernel exponentials of the tile's points
     __shared__ double s_dr[NC_MAX + 2][GEN_THREADS];                 // dense rows / v_c
+    __shared__ double s_part[4][GEN_WARPS][GEN_THREADS];             // per-warp partial sums: qs, qt, tm, int_K at the point
+    __shared__ int s_close[GEN_WARPS][GEN_THREADS];
     const Layout lay = a.lay;
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int inst = a.inst0 + blockIdx.y;
     const double *M = a.models + (size_t)inst * lay.total;
     const int ns = (int)M[H_NS], nc = (int)M[H_NC], nsp = (int)M[H_NSP];
@@ -61,7 +67,8 @@ __global__ void __launch_bounds__(GEN_THREADS) bq_score_generic_kernel(ScoreArgs
     double best_v = INFINITY;
     long long best_i = 0x7fffffffffffffffLL;
     int cta_st = 0;
-    for (int k = ns; k < nsp; ++k) s_e[k * GEN_THREADS + lane] = 0.0;      // padding of the last k-step
+    if (warp == 0)
+        for (int k = ns; k < nsp; ++k) s_e[k * GEN_THREADS + lane] = 0.0;  // padding of the last k-step
     for (long long t0 = (long long)blockIdx.x * GEN_THREADS; t0 < a.na; t0 += (long long)gridDim.x * GEN_THREADS) {
         const long long p = t0 + lane;
         const bool live = p < a.na;
@@ -69,18 +76,22 @@ __global__ void __launch_bounds__(GEN_THREADS) bq_score_generic_kernel(ScoreArgs
         const bool fin = live && isfinite(xv);
         const double x = fin ? xv : 0.0;
         // ---- K_l pass: e[k] = exp part of K_l(x, x_s[k]);  v_s = (c_l L_ss^-1) e,  dense rows (c_l [W; g_gamma; g_alpha]) e
-        bool close = false;
-        for (int k = 0; k < ns; ++k) {
+        __syncthreads();                                                  // the previous tile's tail has left s_dr / s_part
+        int close_w = 0;
+        for (int k = warp; k < ns; k += GEN_WARPS) {
             const double d = x - xs[k];
-            close |= fabs(d) <= tol[k];                                   // np.isclose(x_a, x_s, atol = 1e-4)  bq.py:456
+            close_w |= fabs(d) <= tol[k];                                 // np.isclose(x_a, x_s, atol = 1e-4)  bq.py:456
             s_e[k * GEN_THREADS + lane] = kernel_exp(d, nhl, kind, hp_l);
         }
+        s_close[warp][lane] = close_w;
+        __syncthreads();
         double qs = 0.0;
-        for (int r = 0; r < ns; ++r) {
+        for (int r = warp; r < ns; r += GEN_WARPS) {
             const double v = tri_row_dot(Fl, r, s_e, lane);
             qs = fma(v, v, qs);
         }
-        for (int r = 0; r < nc + 2; ++r) {
+        s_part[0][warp][lane] = qs;
+        for (int r = warp; r < nc + 2; r += GEN_WARPS) {
             const double2 *row = reinterpret_cast<const double2 *>(Fd + (((r >> 3) * nks) << 5) + ((r & 7) << 2));
             double s0 = 0.0, s1 = 0.0;
             for (int ks = 0; ks < nks; ++ks) {                     // columns k >= ns are stored as zeros
@@ -93,17 +104,38 @@ __global__ void __launch_bounds__(GEN_THREADS) bq_score_generic_kernel(ScoreArgs
             }
             s_dr[r][lane] = s0 + s1;
         }
+        if (a.n_xo) {                                                     // trapezoid int_K at the new point (bq_c.pyx:585-593)
+            double s0 = 0.0;
+            for (int j = warp; j < a.n_xo; j += GEN_WARPS) s0 = fma(wp[j], kernel_exp(x - xo[j], nhl, kind, hp_l), s0);
+            s_part[3][warp][lane] = s0;
+        }
+        __syncthreads();                                                  // every warp is done with the K_l vectors
         // ---- K_tl pass: tm = k_t . a_tl, qt = |L_tl^-1 k_t|^2
         double tmv = 0.0;
-        for (int k = 0; k < ns; ++k) {
+        for (int k = warp; k < ns; k += GEN_WARPS) {
             const double e = kernel_exp(x - xs[k], nhtl, kind, hp_tl);
             s_e[k * GEN_THREADS + lane] = e;
             tmv = fma(atl[k], e, tmv);
         }
+        s_part[2][warp][lane] = tmv;
+        __syncthreads();
         double qt = 0.0;
-        for (int r = 0; r < ns; ++r) {
+        for (int r = warp; r < ns; r += GEN_WARPS) {
             const double v = tri_row_dot(Ft, r, s_e, lane);
             qt = fma(v, v, qt);
+        }
+        s_part[1][warp][lane] = qt;
+        __syncthreads();
+        if (warp != 0) continue;                                          // (the loop is uniform: every warp comes back to the barrier)
+        // warp 0: partial sums in warp order (deterministic)
+        qs = qt = tmv = 0.0;
+        double b_trap = 0.0;
+        bool close = false;
+#pragma unroll
+        for (int w = 0; w < GEN_WARPS; ++w) {
+            qs += s_part[0][w][lane]; qt += s_part[1][w][lane]; tmv += s_part[2][w][lane];
+            if (a.n_xo) b_trap += s_part[3][w][lane];
+            close |= s_close[w][lane] != 0;
         }
         // ---- tail (the branches of bq.py:447-527 / bq_c.pyx:425-490; same order of operations as bq_score.cu)
         double esm, em;
@@ -177,15 +209,8 @@ __global__ void __launch_bounds__(GEN_THREADS) bq_score_generic_kernel(ScoreArgs
                     const double kg = s_dr[nc][lane] + vg;                // k_a . gamma_P
                     const double ka = s_dr[nc + 1][lane] + va;            // k_a . alpha_P
                     double b_a;
-                    if (a.n_xo) {                                         // trapezoid int_K at the new point (bq_c.pyx:585-593)
-                        double s0 = 0.0, s1 = 0.0;
-                        int j = 0;
-                        for (; j + 1 < a.n_xo; j += 2) {
-                            s0 = fma(wp[j], kernel_exp(x - xo[j], nhl, kind, hp_l), s0);
-                            s1 = fma(wp[j + 1], kernel_exp(x - xo[j + 1], nhl, kind, hp_l), s1);
-                        }
-                        if (j < a.n_xo) s0 = fma(wp[j], kernel_exp(x - xo[j], nhl, kind, hp_l), s0);
-                        b_a = c_l * (s0 + s1);
+                    if (a.n_xo) {
+                        b_a = c_l * b_trap;
                     } else {                                              // gauss_c.pyx:162: h^2 N(x_a | mu, w_l^2 + sigma^2)
                         const double diff = x - M[H_MU];
                         b_a = M[H_CB] * exp((diff * diff) * M[H_NHB]);
@@ -229,6 +254,7 @@ __global__ void __launch_bounds__(GEN_THREADS) bq_score_generic_kernel(ScoreArgs
         }
         __syncwarp();
     }
+    if (warp != 0) return;
     if (a.cta_flags) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cta_st |= __shfl_xor_sync(0xffffffffu, cta_st, o);
@@ -255,7 +281,7 @@ cudaError_t launch_score_generic(const ScoreArgs &a, int n_inst, cudaStream_t st
     const size_t bytes = sizeof(double) * (size_t)a.lay.nsp_cap * GEN_THREADS;
     cudaError_t e = cudaFuncSetAttribute(bq_score_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    bq_score_generic_kernel<<<dim3((unsigned)gx, (unsigned)n_inst), GEN_THREADS, bytes, stream>>>(a);
+    bq_score_generic_kernel<<<dim3((unsigned)gx, (unsigned)n_inst), GEN_THREADS * GEN_WARPS, bytes, stream>>>(a);
     if (grid_x) *grid_x = (int)gx;
     return cudaGetLastError();
 }
