@@ -26,6 +26,7 @@ def lib():
         L.bqb_batch_destroy.argtypes = [_vp]
         L.bqb_batch_setup.argtypes = [_vp, _ip, _ip, _dp, _dp, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, _vp]
         L.bqb_batch_info.argtypes = [_vp, _dp, _dp, _dp, _ip, _dp]
+        L.bqb_batch_set_approx.argtypes = [_vp, ctypes.c_int, _dp, _dp, _dp, ctypes.c_int, ctypes.c_longlong, ctypes.c_int]
         L.bqb_score_host.argtypes = [_vp, _dp, ctypes.c_longlong, ctypes.c_int, _dp, _dp, _ip]
         L.bqb_last_error.restype = ctypes.c_char_p
         _lib = L
@@ -48,7 +49,17 @@ class DeviceModel(object):
         x_s, l_s = np.ascontiguousarray(bq.x_s, dtype=np.float64), np.ascontiguousarray(bq.l_s, dtype=np.float64)
         x_c = np.zeros(16)
         x_c[:bq.nc] = bq.x_c
-        hyp = np.concatenate([bq.gp_log_l.params, bq.gp_l.params]).astype(np.float64)      # h_tl, w_tl, s_tl, h_l, w_l, s_l
+        ptl, pl = np.asarray(bq.gp_log_l.params, dtype=np.float64), np.asarray(bq.gp_l.params, dtype=np.float64)
+        hyp = np.array([ptl[0], ptl[1], ptl[-1], pl[0], pl[1], pl[-1]])                     # h_tl, w_tl, s_tl, h_l, w_l, s_l
+        periodic = type(bq.gp_l.K).__name__ == "PeriodicKernel"
+        if periodic or bq.options['use_approx']:
+            # non-Gaussian kernel / trapezoid integrals (bq.py:498-510): kernel kind, the two periods, the grid of bq.py:167-171
+            period = np.array([ptl[2], pl[2]]) if periodic else None
+            xo = np.ascontiguousarray(bq._approx_x, dtype=np.float64) if bq.options['use_approx'] else None
+            p_xo = np.ascontiguousarray(bq._approx_px, dtype=np.float64) if bq.options['use_approx'] else None
+            if L.bqb_batch_set_approx(self.h, int(periodic), _p(period) if periodic else None, _p(xo) if xo is not None else None,
+                                      _p(p_xo) if xo is not None else None, 0 if xo is None else xo.size, 0, 0) != 0:
+                raise RuntimeError(L.bqb_last_error())
         prior = np.array([bq.options['x_mean'][0], bq.options['x_cov'][0, 0], bq.options['candidate_thresh']], dtype=np.float64)
         rc = L.bqb_batch_setup(self.h, _p(ns, _ip), _p(nc, _ip), _p(x_s), _p(l_s), bq.ns, _p(x_c), _p(hyp), _p(prior), 0, None)
         if rc != 0:
@@ -77,7 +88,8 @@ class DeviceModel(object):
 
 def _device_model(self):
     """Memoised like the gp package's Kxx / Lxx: rebuilt when data, candidates or parameters changed."""
-    key = (self.x_s.tobytes(), self.l_s.tobytes(), self.x_c.tobytes(), tuple(self.gp_log_l.params), tuple(self.gp_l.params))
+    key = (self.x_s.tobytes(), self.l_s.tobytes(), self.x_c.tobytes(), tuple(self.gp_log_l.params), tuple(self.gp_l.params),
+           bool(self.options['use_approx']))
     cached = getattr(self, "_b200", None)
     if cached is None or cached[0] != key:
         self._b200 = (key, DeviceModel(self))

@@ -45,6 +45,7 @@ def test_capacity_and_argument_errors_without_gpu():
     assert L.bqb_ns_capacity(513) == _lib.EUNSUPPORTED
     assert L.bqb_ns_capacity(0) == _lib.EINVAL
     assert L.bqb_batch_create(None, 0, 1, 8) == _lib.EINVAL
+    assert L.bqb_batch_set_approx(None, 0, None, None, None, 0, 0, 0) == _lib.EINVAL
     assert b"bad arguments" in L.bqb_last_error()
 
 

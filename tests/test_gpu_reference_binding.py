@@ -83,3 +83,27 @@ def test_reference_choose_next_loop_runs_on_the_library(ref):
     bq = make_bq(BQ_b200, gp)
     chosen = bq.choose_next(g["x_a"], n=int(g["n"]), params=["h", "w"])
     assert chosen == float(g["chosen"])
+
+
+def test_patched_reference_with_the_periodic_kernel(ref):
+    """The reference's own periodic problem (tests/util.py:76-91: PeriodicKernel, wrapped domain, `use_approx`) and a
+    better-conditioned one, scored by the reference's Cython loop and, with the same object state, through the library
+    (bqb_batch_set_approx: kernel kind, periods, the object's own approximation grid)."""
+    from scipy.special import iv
+    BQ, BQ_b200, gp = ref
+    f = lambda x: np.exp(-np.log(2 * np.pi * iv(0, 1.1)) + 1.1 * np.cos(x - 0.1))
+    for nobs, ptl, pl in ((8, (5, 2 * np.pi, 1, 0.), (0.2, np.pi / 2., 1, 0.)), (5, (3, 1.2, 1, 0.), (0.3, 0.8, 1, 0.))):
+        objs = []
+        for cls in (BQ, BQ_b200):
+            np.random.seed(8728)
+            x = np.linspace(-np.pi, np.pi, nobs + 1)[:-1]
+            bq = cls(x, f(x), n_candidate=10, x_mean=0.0, x_var=10.0, candidate_thresh=0.5, kernel=gp.PeriodicKernel,
+                     optim_method="L-BFGS-B")
+            bq.init(params_tl=ptl, params_l=pl)
+            objs.append(bq)
+        a, b = objs
+        assert np.array_equal(a.x_c, b.x_c)
+        x_a = np.linspace(-np.pi, np.pi, 41)
+        ra, rb = a.expected_squared_mean_and_mean(x_a), b.expected_squared_mean_and_mean(x_a)
+        assert_close(rb[:, 0], ra[:, 0], "periodic esm, %d observations" % nobs)
+        assert_close(rb[:, 1], ra[:, 1], "periodic em, %d observations" % nobs)
