@@ -11,8 +11,9 @@
 // CTA barriers behind one-warp / one-thread phases, 440 MB of global scratch thrashing the L2 at C5 scale):
 //   * ONE packed triangle serves K_tl -> L_tl -> L_tl^-1 (in place), then K_l -> L -> [L_ss^-1; C L_cc] (in place),
 //     then (s_l != 0 only) K_l + s_l^2 I.  n (n + 1) / 2 doubles: 92 KB at n = 152.  Two CTAs of 256 threads per SM
-//     while two instances fit (n <= 153), one CTA of 512 threads up to n = 218; larger instances (the 256 class) run
-//     the same code on a packed triangle in global scratch.
+//     while two instances fit (n <= 155 with ten candidates; decided by the occupancy query at launch) and the launch
+//     fills the SMs more than once, one CTA of 512 threads up to n = 218; larger instances (the 256 and 512 classes)
+//     run the same code on a packed triangle in global scratch.
 //   * Cholesky by panels of 8: the 8 x 8 diagonal block is factorised by eight lanes in registers (shuffles; rsqrt with
 //     one Newton step instead of sqrt + divide), the panel below is a column-oriented forward substitution with one
 //     thread per row, the trailing update is DMMA (two mma.m8n8k4 per 8 x 8 block).  Three barriers per panel.
