@@ -2,6 +2,7 @@
 // Plain pointers and sizes only; no torch types.  Every entry point returns 0 on success,
 // a negative BQB_E* code for argument errors and a positive cudaError_t otherwise; the
 // message is kept per thread (bqb_last_error).
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -15,6 +16,7 @@
 namespace bqb {
 void launch_setup(const SetupArgs &a, int n_inst, cudaStream_t stream);
 cudaError_t launch_setup2(const SetupArgs &a, int n_inst, cudaStream_t stream);
+int setup2_two_cta_limit(int nc_max);
 cudaError_t launch_score(const ScoreArgs &a, int n_inst, int sm_count, cudaStream_t stream, int *grid_x = nullptr);
 cudaError_t launch_score_generic(const ScoreArgs &a, int n_inst, cudaStream_t stream, int *grid_x);
 cudaError_t launch_argmin_partials(double *bv, long long *bi, int nblocks, long long offset, double *pair, cudaStream_t s);
@@ -64,6 +66,7 @@ struct bqb_batch {
     bool generic = false;
     bool big_class = false;            // capacity 512: no tensor-core scoring kernels, no first-generation setup kernel
     double *d_period = nullptr, *d_xo = nullptr, *d_pxo = nullptr, *d_wp = nullptr, *d_gz = nullptr;
+    int *d_inst_list = nullptr;        // setup launch groups (instances ordered by size class)
     // scoring: relevance cut-off (bq_score.cu, CUT_ARG; +inf = dense) and the optional executed-work counter
     double cut_arg = 72.0;
     unsigned long long *d_work_ctr = nullptr;
@@ -174,7 +177,7 @@ void bqb_batch_destroy(bqb_batch *b) {
     cudaSetDevice(b->device);
     void *ptrs[] = {b->d_models, b->d_tab, b->d_work, b->d_ns, b->d_nc, b->d_xs, b->d_ls, b->d_xc, b->d_hyp, b->d_prior,
                     b->d_xa, b->d_esm, b->d_em, b->d_st, b->d_red_val, b->d_red_idx, b->d_flags, b->d_mt, b->d_mti, b->d_overflow, b->d_work_ctr, b->d_xsorted, b->d_perm, b->d_iota, b->d_sort_tmp,
-                    b->d_period, b->d_xo, b->d_pxo, b->d_wp, b->d_gz};
+                    b->d_period, b->d_xo, b->d_pxo, b->d_wp, b->d_gz, b->d_inst_list};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (cudaStream_t st : b->pipe) if (st) cudaStreamDestroy(st);
     if (b->h_flags) cudaFreeHost(b->h_flags);
@@ -212,12 +215,47 @@ static int run_setup(bqb_batch *b, int check_max, cudaStream_t s) {
     a.wp = b->d_wp; a.gz = b->d_gz;
     if (v1 && (b->kind || b->n_xo || b->big_class))
         return fail(BQB_EUNSUPPORTED, "BQB_SETUP_V1: the first-generation setup kernel has no periodic kernel / trapezoid mode and ends at 256 observations");
-    for (int i0 = 0; i0 < B; i0 += b->work_inst) {
-        const int cnt = (B - i0 < b->work_inst) ? B - i0 : b->work_inst;
-        a.inst0 = i0;
-        if (v1) { launch_setup(a, cnt, s); CU(cudaGetLastError()); }
-        else CU(launch_setup2(a, cnt, s));
-        b->launches++;
+    a.inst_list = nullptr;
+    // Launch groups: the second-generation kernel runs two CTAs per SM while two instances fit its shared memory, sized for the
+    // LARGEST instance of a launch.  When a few large instances (many surviving candidates) would push a big batch into the
+    // one-CTA variant, they get a launch of their own (C5: the last rounds, profiles/c5_rounds_r02.txt).
+    std::vector<int> order;
+    int n_small_grp = B;
+    if (!v1 && B > 4 * b->sm_count) {
+        const int lim = setup2_two_cta_limit(nc_max);
+        if (lim > 0 && n_max > lim) {
+            std::vector<int> big;
+            order.reserve(B);
+            for (int i = 0; i < B; ++i) {
+                const int n_i = b->h_ns[i] + b->h_nc[i];
+                (n_i <= lim ? order : big).push_back(i);
+            }
+            n_small_grp = (int)order.size();
+            if (n_small_grp >= B - B / 4 && !big.empty()) {            // worth it: at least 3/4 of the batch stays small
+                order.insert(order.end(), big.begin(), big.end());
+                if (!b->d_inst_list) CU(cudaMalloc(&b->d_inst_list, sizeof(int) * B));
+                CU(cudaMemcpyAsync(b->d_inst_list, order.data(), sizeof(int) * B, cudaMemcpyHostToDevice, s));
+                CU(cudaStreamSynchronize(s));                          // `order` is a local
+                a.inst_list = b->d_inst_list;
+            } else {
+                n_small_grp = B;
+            }
+            if (a.inst_list) {
+                int nm = 8;
+                for (int k = 0; k < n_small_grp; ++k) { const int i = order[k]; nm = std::max(nm, b->h_ns[i] + b->h_nc[i]); }
+                a.n_max = nm;                                          // of the first group; the second uses the batch maximum
+            }
+        }
+    }
+    for (int g0 = 0, g1 = n_small_grp; g0 < B; g0 = g1, g1 = B) {      // one or two groups
+        if (g0 > 0) a.n_max = n_max;
+        for (int i0 = g0; i0 < g1; i0 += b->work_inst) {
+            const int cnt = (g1 - i0 < b->work_inst) ? g1 - i0 : b->work_inst;
+            a.inst0 = i0;
+            if (v1) { launch_setup(a, cnt, s); CU(cudaGetLastError()); }
+            else CU(launch_setup2(a, cnt, s));
+            b->launches++;
+        }
     }
     // headers (Z_mean, Z_var, log_lh, status) and l_c rows back to the host: gathered on the device, one contiguous copy
     constexpr int IW = H_COUNT + NC_MAX;

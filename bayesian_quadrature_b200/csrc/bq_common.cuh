@@ -132,6 +132,7 @@ struct SetupArgs {
     size_t work_stride;
     int n_cap;
     int inst0;                 // first instance of this chunk
+    const int *inst_list;      // bq_setup2.cu: when set, CTA b works on instance inst_list[inst0 + b] (launch groups by size)
     int n_max, nc_max;         // bq_setup2.cu: largest ns + nc / nc over the instances of the launch (size the shared memory)
     // non-Gaussian kernels / trapezoid approximation (bq_c.pyx:216-261, :358-422, :538-598); bq_setup2.cu only
     int kind;                  // 0: gp.GaussianKernel, 1: gp.PeriodicKernel

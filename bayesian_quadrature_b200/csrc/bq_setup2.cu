@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) bq_setup2_kernel(SetupArgs a) {
     __shared__ int s_fail, s_info;
     extern __shared__ double s_dyn[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int inst = a.inst0 + blockIdx.x;
+    const int inst = a.inst_list ? a.inst_list[a.inst0 + blockIdx.x] : a.inst0 + blockIdx.x;
     const int ns = a.ns[inst], nc = a.nc[inst], n = ns + nc;
     const Layout &lay = a.lay;
     double *M = a.models + (size_t)inst * lay.total;
@@ -947,6 +947,27 @@ static cudaError_t launch_kind(const SetupArgs &a, int n_inst, size_t bytes, cud
 template <bool TSMEM, int NT>
 static cudaError_t launch_one(const SetupArgs &a, int n_inst, size_t bytes, cudaStream_t stream) {
     return a.kind ? launch_kind<TSMEM, NT, 1>(a, n_inst, bytes, stream) : launch_kind<TSMEM, NT, 0>(a, n_inst, bytes, stream);
+}
+
+// Largest instance order n for which two 256-thread CTAs of the setup kernel fit one SM (0: none), given the launch's nc_max.
+int setup2_two_cta_limit(int nc_max) {
+    static int cache[NC_MAX + 2];
+    static bool have[NC_MAX + 2];
+    if (nc_max < 0 || nc_max > NC_MAX) return 0;
+    if (have[nc_max]) return cache[nc_max];
+    int lo = 0, hi = 218;                              // invariant: lo fits (or is 0), hi + 1 does not
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        const size_t bytes = sizeof(double) * (size_t)s2_carve(mid, nc_max, true).total;
+        int per_sm = 0;
+        bool ok = bytes <= 227 * 1024 - 256 &&
+                  cudaFuncSetAttribute(bq_setup2_kernel<true, 256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess &&
+                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bq_setup2_kernel<true, 256, 0>, 256, bytes) == cudaSuccess && per_sm >= 2;
+        if (ok) lo = mid; else hi = mid - 1;
+    }
+    cudaGetLastError();
+    have[nc_max] = true;
+    return cache[nc_max] = lo;
 }
 
 // a.n_max / a.nc_max must be >= ns + nc / nc of every instance of the launch (instances above report SETUP_BAD_INPUT)
