@@ -57,3 +57,44 @@ def test_second_generation_setup_equals_the_first(tmp_path):
             # Z_mean, l_c: linear in K^-1 y, cond * eps between two factorisation orders
             assert np.allclose(a[key], b[key], rtol=1e-9, atol=1e-300), (key, np.abs(a[key] / b[key] - 1).max())
     assert checked >= 30
+
+
+def test_setup_launch_groups_equal_single_instance_setups():
+    """A batch larger than four waves whose few largest instances exceed the two-CTA limit of the setup kernel is set up in
+    two launch groups through an instance list (csrc/bq_capi.cu run_setup): every instance -- small or large, wherever it
+    sits in the batch -- gets exactly the model block a single-instance batch gives it."""
+    from bayesian_quadrature_b200 import _lib, synthetic
+    B, ns = 640, 144
+    rs = np.random.RandomState(3)
+    x_s, _ = synthetic.observations(ns)
+    xs = np.sort(x_s)
+    opt = synthetic.options(ns)
+    nc = np.full(B, 2, dtype=np.int32)
+    big = rs.choice(B, size=40, replace=False)
+    nc[big] = 14                                                   # n = 158 > 155: the one-CTA variant for these only
+    X = np.tile(x_s, (B, 1))
+    L = np.stack([synthetic.likelihood(ns, synthetic.problem_shift(p))(x_s) for p in range(B)])
+    spots = np.concatenate([xs[:-1] + 0.625, xs[:1] - 0.9 - 1.1 * np.arange(8), xs[-1:] + 0.9 + 1.1 * np.arange(8)])
+    XC = np.zeros((B, 16))
+    for p in range(B):
+        XC[p, :nc[p]] = np.sort(rs.choice(spots, size=nc[p], replace=False))
+    hyp = np.tile(list(synthetic.PARAMS_TL) + list(synthetic.PARAMS_L), (B, 1))
+    prior = np.tile([opt["x_mean"], opt["x_var"], opt["candidate_thresh"]], (B, 1))
+    b = _lib.Batch(B, ns)
+    info = b.setup(np.full(B, ns, dtype=np.int32), nc, X, L, XC, hyp, prior, check_max=True)
+    assert (info["status"] == 0).all()
+    for p in list(big[:4]) + [0, 1, B - 1, int(big.max()) - 1 if int(big.max()) > 0 else 2]:
+        b1 = _lib.Batch(1, ns)
+        i1 = b1.setup([ns], [nc[p]], X[p:p + 1], L[p:p + 1], XC[p:p + 1], hyp[p:p + 1], prior[p:p + 1], check_max=True)
+        m1, mp = b1.read_model(0), b.read_model(int(p))
+        # (a single instance runs the 512-thread variant, the batch's small group the 256-thread one: block-wide sums are
+        # combined over 16 vs 8 warps, so the last bits may differ; the large group runs the same variant: identical)
+        fin = np.abs(m1) < 1e100
+        scale = np.abs(m1[fin]).max()
+        assert np.array_equal(fin, np.abs(mp) < 1e100)
+        assert np.allclose(m1[fin], mp[fin], rtol=1e-9, atol=1e-12 * scale), (p, np.abs(m1[fin] - mp[fin]).max())
+        if p in big:
+            assert np.array_equal(m1, mp), p
+        assert np.isclose(i1["Z_mean"][0], info["Z_mean"][p], rtol=1e-12) and np.isclose(i1["log_lh"][0], info["log_lh"][p], rtol=1e-12)
+        b1.close()
+    b.close()
